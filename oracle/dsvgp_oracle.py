@@ -1,0 +1,345 @@
+"""CPU oracle for the DSVGP minibatch train / predict hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this file.  The product (gp-derivatives-variational-inference_b200/) never does.
+
+It restates, in plain PyTorch on the CPU, the algorithm of the reference's hot path:
+
+  K    RBFKernelDirectionalGrad.forward        /root/reference/directionalvi/RBFKernelDirectionalGrad.py:41-119
+  S    DirectionalGradVariationalStrategy.forward   .../DirectionalGradVariationalStrategy.py:89-208
+  C    _cholesky_factor (fp64, psd_safe_cholesky)   .../DirectionalGradVariationalStrategy.py:72-75
+  S-df DFreeDirectionalGradVariationalStrategy.forward   .../DFreeDirectionalGradVariationalStrategy.py:89-195
+  S-g  GradVariationalStrategy.forward              .../GradVariationalStrategy.py:87-137
+  V/KL/L/E/M/P  the gpytorch==1.4.0 pieces the strategy feeds (graphite_environment.yml:96; gpytorch is a
+       third-party dependency that is NOT under /root/reference and not installed here -- its published
+       algorithm is restated): CholeskyVariationalDistribution, KL(q||N(0,I)), GaussianLikelihood with the
+       GreaterThan(1e-4) noise constraint, VariationalELBO, ConstantMean, softplus positivity transforms.
+
+Pinning: tests/golden/*.pt hold outputs of the UNMODIFIED reference files executed in this container
+against oracle/gpytorch_shim (see oracle/make_golden.py); tests/test_oracle.py checks this oracle against
+them.  The kernel (K) is therefore pinned to the reference's own arithmetic; the gpytorch pieces are pinned
+to a restatement of gpytorch 1.4.0 (not to the gpytorch binary, which cannot be had here) -- "parity pinned
+for K/S/S-df/S-g against the reference files; gpytorch semantics restated, unpinned".
+
+Two structures are offered and must agree to rounding:
+  structure="reference": the reference's op structure -- four kernel evaluations including the full K_xx,
+       two fp64 triangular solves, dense L_s products (this is what the CPU baseline times);
+  structure="lean": one cross kernel, diagonal-only K_xx (Q7 of SURVEY.md section 8a).
+"""
+import math
+from dataclasses import dataclass, fields
+
+import torch
+from torch.nn.functional import softplus
+
+KZZ_JITTER = 1e-3      # add_jitter() default, DGVS.py:144
+PRED_JITTER = 1e-4     # DGVS.py:198,203
+NOISE_FLOOR = 1e-4     # GaussianLikelihood GreaterThan(1e-4)
+CHOL_RETRY_JITTER = 1e-6   # settings.cholesky_jitter.value(), DGVS.py:74
+
+
+class NanError(RuntimeError):
+    pass
+
+
+class NotPSDError(RuntimeError):
+    pass
+
+
+@dataclass
+class Params:
+    """The learnable state of reference GPModel + GaussianLikelihood (directional_vi.py:25-65,172)."""
+    Z: torch.Tensor          # (M, d)     variational_strategy.inducing_points
+    Vz: torch.Tensor         # (M*p, d)   variational_strategy.inducing_directions (point-major)
+    m: torch.Tensor          # (M')       _variational_distribution.variational_mean
+    Ls_raw: torch.Tensor     # (M', M')   _variational_distribution.chol_variational_covar
+    c: torch.Tensor          # (1,)       mean_module.constant
+    raw_os: torch.Tensor     # ()         covar_module.raw_outputscale
+    raw_ell: torch.Tensor    # (1,1)      covar_module.base_kernel.raw_lengthscale
+    raw_noise: torch.Tensor  # (1,)       likelihood.noise_covar.raw_noise
+
+    def requires_grad_(self, flag=True):
+        for f in fields(self):
+            t = getattr(self, f.name)
+            if t is not None:
+                t.requires_grad_(flag)
+        return self
+
+    def clone(self, dtype=None):
+        return Params(**{f.name: (getattr(self, f.name).detach().clone().to(dtype or getattr(self, f.name).dtype))
+                         for f in fields(self)})
+
+    def tensors(self):
+        return {f.name: getattr(self, f.name) for f in fields(self)}
+
+
+def normalize_rows(v):
+    """RBFKernelDirectionalGrad.py:57-58 -- every direction is scaled to unit length inside forward."""
+    return (v.T / torch.norm(v, dim=1)).T
+
+
+# ----------------------------------------------------------------------------------------------- K
+def kernel_closed_form(x1, x2, v1, v2, ell):
+    """K[i(p1+1)+a, j(p2+1)+b] of RBFKernelDirectionalGrad.forward (:41-108), closed form.
+
+    p1 = rows of v1 per point of x1, p2 likewise (the reference asserts p1 == p2, :53; the DFree strategy
+    keeps only b = 0 columns, which is this function with v2 = None).
+    """
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    p1 = 0 if v1 is None else v1.shape[0] // n1
+    p2 = 0 if v2 is None else v2.shape[0] // n2
+    ell2 = (ell * ell).reshape(())
+    diff = x1[:, None, :] - x2[None, :, :]
+    k = torch.exp(-0.5 * (diff * diff).sum(-1) / ell2)
+    K = x1.new_zeros(n1, p1 + 1, n2, p2 + 1)
+    K[:, 0, :, 0] = k
+    if p1:
+        U = normalize_rows(v1).reshape(n1, p1, d)
+        alpha = torch.einsum("ijc,iac->iaj", diff, U) / ell2          # (n1,p1,n2)
+        K[:, 1:, :, 0] = -alpha * k[:, None, :]
+    if p2:
+        W = normalize_rows(v2).reshape(n2, p2, d)
+        beta = torch.einsum("ijc,jbc->ijb", diff, W) / ell2           # (n1,n2,p2)
+        K[:, 0, :, 1:] = beta * k[:, :, None]
+    if p1 and p2:
+        gamma = torch.einsum("iac,jbc->iajb", U, W) / ell2
+        K[:, 1:, :, 1:] = (gamma - alpha[:, :, :, None] * beta[:, None, :, :]) * k[:, None, :, None]
+    return K.reshape(n1 * (p1 + 1), n2 * (p2 + 1))
+
+
+def _sq_dist_gpytorch(x1, x2):
+    """gpytorch 1.4.0 Distance._sq_dist as reached from covar_dist(square_dist=True): mean-centred
+    expanded form, diagonal zeroed only if x1 == x2 and neither requires grad, clamp at 0 (Q8)."""
+    same = torch.equal(x1, x2) and not x1.requires_grad and not x2.requires_grad
+    adj = x1.mean(-2, keepdim=True)
+    a, b = x1 - adj, x2 - adj
+    an = a.pow(2).sum(-1, keepdim=True)
+    bn = an if same else b.pow(2).sum(-1, keepdim=True)
+    one_a, one_b = torch.ones_like(an), torch.ones_like(bn)
+    res = torch.cat([-2.0 * a, an, one_a], -1).matmul(torch.cat([b, one_b, bn], -1).transpose(-2, -1))
+    if same:
+        res.diagonal(dim1=-2, dim2=-1).fill_(0)
+    return res.clamp_min_(0)
+
+
+def kernel_reference_structure(x1, x2, v1, v2, ell):
+    """Same matrix as kernel_closed_form, built the way the reference builds it (:57-107): scaled inputs,
+    gpytorch's expanded squared distance, matmuls against the directions, block-contiguous assembly and two
+    gathers into the interleaved order.  Used for the CPU baseline timing and as a second opinion."""
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    p1, p2 = v1.shape[0] // n1, v2.shape[0] // n2
+    assert p1 == p2, "v1 and v2 must contain same number of directions"
+    p = p1
+    u, w = normalize_rows(v1), normalize_rows(v2)
+    a, b = x1 / ell, x2 / ell
+    k = _sq_dist_gpytorch(a, b).div_(-2).exp_()
+    K = x1.new_zeros(n1 * (p + 1), n2 * (p + 1))
+    K[:n1, :n2] = k
+    # value-derivative block, direction-major columns
+    bw = (b.reshape(n2, 1, d) @ w.reshape(n2, p, d).transpose(-2, -1)).flatten()
+    o1 = (a @ w.T - bw)[:, torch.arange(n2 * p).view(n2, p).t().reshape(-1)] / ell
+    K[:n1, n2:] = o1 * k.repeat(1, p)
+    # derivative-value block
+    au = (a.reshape(n1, 1, d) @ u.reshape(n1, p, d).transpose(-2, -1)).flatten()
+    perm1 = torch.arange(n1 * p).view(n1, p).t().reshape(-1)
+    o2 = ((au - b @ u.T)[:, perm1]).t() / ell
+    K[n1:, :n2] = -o2 * k.repeat(p, 1)
+    # derivative-derivative block
+    perm2 = torch.arange(n2 * p).view(n2, p).t().reshape(-1)
+    kp = (u @ w.T / ell.pow(2))[:, perm2][perm1, :]
+    K[n1:, n2:] = (kp - o1.repeat(p, 1) * o2.repeat(1, p)) * k.repeat(p, p)
+    r = torch.arange(n1 * (p + 1)).view(p + 1, n1).t().reshape(-1)
+    c = torch.arange(n2 * (p + 1)).view(p + 1, n2).t().reshape(-1)
+    return K[r, :][:, c]
+
+
+def kernel_diag(n, p, ell, dtype=None):
+    """diag=True branch (:110-119): [1, 1/l^2, ..., 1/l^2] per point."""
+    ell = ell.reshape(())
+    row = torch.cat([torch.ones(1, dtype=ell.dtype), (1.0 / (ell * ell)).expand(p)])
+    return row.repeat(n)
+
+
+def canonical_directions(n, d, p, dtype=torch.float64, idx=None):
+    """eye(d)[idx] repeated for every point -- what train_gp / eval_gp pass (directional_vi.py:87-88,292-293)."""
+    idx = list(range(p)) if idx is None else idx
+    return torch.eye(d, dtype=dtype)[idx].repeat(n, 1)
+
+
+# ------------------------------------------------------------------------------------ transforms
+def lengthscale(P):
+    return softplus(P.raw_ell).reshape(())
+
+
+def outputscale(P):
+    return softplus(P.raw_os).reshape(())
+
+
+def noise(P):
+    return softplus(P.raw_noise).reshape(()) + NOISE_FLOOR
+
+
+def chol_factor_of_q(P):
+    """CholeskyVariationalDistribution.forward: L_s = param * tril-mask (no positivity transform)."""
+    return P.Ls_raw * torch.ones_like(P.Ls_raw).tril(0)
+
+
+def kl_divergence(P):
+    """KL(N(m, L_s L_s^T) || N(0, I)) as gpytorch computes it (SURVEY 8a row KL)."""
+    Ls = chol_factor_of_q(P)
+    Mp = P.m.numel()
+    logdet = Ls.diagonal().pow(2).log().sum()
+    return 0.5 * ((Ls * Ls).sum() + (P.m * P.m).sum() - Mp - logdet)
+
+
+def psd_safe_cholesky(A, jitter=CHOL_RETRY_JITTER, max_tries=3):
+    """gpytorch.utils.cholesky.psd_safe_cholesky semantics."""
+    L, info = torch.linalg.cholesky_ex(A)
+    if not bool(info.any()):
+        return L
+    if torch.isnan(A).any():
+        raise NanError("NaN in the matrix handed to the Cholesky factorisation")
+    Ap, prev = A.clone(), 0.0
+    for i in range(max_tries):
+        new = jitter * (10 ** i)
+        Ap.diagonal().add_(new - prev)
+        prev = new
+        L, info = torch.linalg.cholesky_ex(Ap)
+        if not bool(info.any()):
+            return L
+    raise NotPSDError(f"not positive definite after adding jitter up to {new:.1e}")
+
+
+# ------------------------------------------------------------------------------------------- S, S-df, S-g
+def predictive(P, x, Vx, variant="dsvgp", structure="lean"):
+    """q(f) at the minibatch: returns (mean, variance) of length n' -- variance is the diagonal of the
+    predictive covariance INCLUDING the +1e-4 jitter and EXCLUDING likelihood noise.
+
+    variant  "dsvgp": DirectionalGradVariationalStrategy.forward (DGVS.py:89-208), n' = n(p+1)
+             "dfree": DFreeDirectionalGradVariationalStrategy.forward (:89-195), n' = n (values only)
+             "grad":  GradVariationalStrategy.forward (:87-137), p = d canonical directions on both sides
+    """
+    n, d = x.shape
+    M = P.Z.shape[0]
+    ell, osc = lengthscale(P), outputscale(P)
+    if variant == "grad":
+        Vz = canonical_directions(M, d, d, x.dtype)
+        Vx = canonical_directions(n, d, d, x.dtype)
+    else:
+        Vz = P.Vz
+    p = Vz.shape[0] // M
+    if variant != "grad":
+        assert Vx.shape[0] // n == p, "Need minibatch dim to be same as number of directions for kernel"
+    keep = slice(None, None, p + 1) if variant == "dfree" else slice(None)
+    Ls = chol_factor_of_q(P)
+
+    if structure == "reference":
+        kern = kernel_reference_structure
+        Kzx = (osc * kern(P.Z, x, Vz, Vx, ell))[:, keep]
+        Kxz = (osc * kern(x, P.Z, Vx, Vz, ell))[keep, :]
+        Kzz = osc * kern(P.Z, P.Z, Vz, Vz, ell)
+        Kxx = (osc * kern(x, x, Vx, Vx, ell))[keep, keep]
+        Kzz = Kzz + KZZ_JITTER * torch.eye(Kzz.shape[0], dtype=Kzz.dtype)
+        L = psd_safe_cholesky(Kzz.double())
+        A = torch.linalg.solve_triangular(L, Kzx.double(), upper=False).to(x.dtype)
+        At = torch.linalg.solve_triangular(L, Kxz.transpose(-1, -2).double(), upper=False).to(x.dtype)
+        mean = (At.transpose(-1, -2) @ P.m.unsqueeze(-1)).squeeze(-1) + P.c.expand(At.shape[1])
+        mid_A = Ls @ (Ls.transpose(-1, -2) @ A) - A
+        var = (Kxx + PRED_JITTER * torch.eye(Kxx.shape[0], dtype=Kxx.dtype)).diagonal() \
+            + (At.transpose(-1, -2) * mid_A.transpose(-1, -2)).sum(-1)
+        return mean, var
+
+    v2 = None if variant == "dfree" else Vx
+    Kzx = osc * kernel_closed_form(P.Z, x, Vz, v2, ell)
+    Kzz = osc * kernel_closed_form(P.Z, P.Z, Vz, Vz, ell)
+    Kzz = Kzz + KZZ_JITTER * torch.eye(Kzz.shape[0], dtype=Kzz.dtype)
+    L = psd_safe_cholesky(Kzz.double())
+    A = torch.linalg.solve_triangular(L, Kzx.double(), upper=False).to(x.dtype)
+    mean = A.transpose(-1, -2) @ P.m + P.c.expand(A.shape[1])
+    kd = osc * (torch.ones(n, dtype=x.dtype) if variant == "dfree" else kernel_diag(n, p, ell).to(x.dtype))
+    mid_A = Ls @ (Ls.transpose(-1, -2) @ A) - A
+    var = kd + PRED_JITTER + (A * mid_A).sum(0)
+    return mean, var
+
+
+def clamp_variance(var):
+    """MultivariateNormal.variance clamps at settings.min_variance (1e-6 fp32 / 1e-10 fp64), Q5."""
+    return var.clamp_min(1e-10 if var.dtype == torch.float64 else 1e-6)
+
+
+def predict(P, x, Vx, variant="dsvgp", structure="lean"):
+    """eval_gp's per-batch result (directional_vi.py:296-298): likelihood(model(x)) mean and variance,
+    i.e. the predictive variance INCLUDING likelihood noise."""
+    mean, var = predictive(P, x, Vx, variant, structure)
+    return mean, clamp_variance(var + noise(P))
+
+
+def elbo(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", through_likelihood=True):
+    """VariationalELBO(likelihood, model, num_data)(likelihood(model(x)), y)  (directional_vi.py:245-246).
+
+    through_likelihood=True reproduces Q3: the reference hands likelihood(model(x)) -- not model(x) -- to the
+    ELBO, so expected_log_prob sees var + sigma^2 and the value is the textbook ELBO minus exactly 0.5.
+    """
+    mean, var = predictive(P, x, Vx, variant, structure)
+    s2 = noise(P)
+    if through_likelihood:
+        var = var + s2
+    var = clamp_variance(var)
+    ell_terms = -0.5 * (((y - mean) ** 2 + var) / s2 + torch.log(s2) + math.log(2 * math.pi))
+    return ell_terms.sum() / mean.numel() - kl_divergence(P) / num_data
+
+
+def elbo_and_grads(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", through_likelihood=True):
+    """One training step's forward + backward (loss = -ELBO is what the reference differentiates; this
+    returns the ELBO and dELBO/dparam so signs are unambiguous)."""
+    Q = P.clone().requires_grad_(True)
+    val = elbo(Q, x, Vx, y, num_data, variant, structure, through_likelihood)
+    names = [k for k, t in Q.tensors().items() if not (variant == "grad" and k == "Vz")]
+    grads = torch.autograd.grad(val, [getattr(Q, k) for k in names], allow_unused=True)
+    out = {k: (g if g is not None else torch.zeros_like(getattr(Q, k))) for k, g in zip(names, grads)}
+    return val.detach(), out
+
+
+# ------------------------------------------------------------------------------------ synthetic inputs
+def testfun(x):
+    """tests/testfun.py:4-11: f = sin(2 pi |x|^2) with its analytic gradient, columns [f, df/dx_1..d]."""
+    s = (x * x).sum(1)
+    f = torch.sin(2 * math.pi * s)
+    g = 4 * math.pi * torch.cos(2 * math.pi * s)[:, None] * x
+    return torch.cat([f[:, None], g], 1)
+
+
+def make_problem(n, d, M, p, dtype=torch.float64, seed=0, variant="dsvgp", perturb_dirs=True, N=None):
+    """Seeded synthetic inputs of SURVEY.md section 8d: x, Z ~ U[0,1]^d; V_z = eye(d)[:p] per point
+    (+0.1 N(0,1) so the general-direction path is exercised); V_x canonical; y = [f, grad f . V_x] of
+    tests/testfun.py; raw hypers 0; m = 1e-3 randn; L_s = I + 0.01 tril(randn)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64)
+    Z = torch.rand(M, d, generator=g, dtype=torch.float64)
+    pz = d if variant == "grad" else p
+    Vz = torch.eye(d, dtype=torch.float64)[:pz].repeat(M, 1)
+    if perturb_dirs and variant != "grad":
+        Vz = Vz + 0.1 * torch.randn(Vz.shape, generator=g, dtype=torch.float64)
+    Mp = M * (pz + 1)
+    m = 1e-3 * torch.randn(Mp, generator=g, dtype=torch.float64)
+    Ls = torch.eye(Mp, dtype=torch.float64) + 0.01 * torch.randn(Mp, Mp, generator=g, dtype=torch.float64).tril()
+    # the strictly-upper part of the raw parameter is arbitrary and must be ignored by every implementation
+    Ls = Ls + 0.5 * torch.randn(Mp, Mp, generator=g, dtype=torch.float64).triu(1)
+    Y = testfun(x)
+    if variant == "dfree":
+        y = Y[:, 0].clone()
+        Vx = canonical_directions(n, d, p, torch.float64)
+    elif variant == "grad":
+        y = Y.reshape(-1).clone()
+        Vx = None
+    else:
+        y = Y[:, : p + 1].reshape(-1).clone()
+        Vx = canonical_directions(n, d, p, torch.float64)
+    P = Params(Z=Z, Vz=Vz, m=m, Ls_raw=Ls, c=torch.full((1,), 0.05, dtype=torch.float64),
+               raw_os=torch.tensor(0.1, dtype=torch.float64), raw_ell=torch.full((1, 1), -0.2, dtype=torch.float64),
+               raw_noise=torch.full((1,), -1.0, dtype=torch.float64))
+    num_data = (d + 1) * (N or n) if variant != "grad" else (N or n)
+    cast = lambda t: None if t is None else t.to(dtype)
+    return P.clone(dtype), cast(x), cast(Vx), cast(y), num_data

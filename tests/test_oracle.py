@@ -1,0 +1,154 @@
+"""The oracle against (a) golden vectors produced by the UNMODIFIED reference files (oracle/make_golden.py)
+and (b) the known-answer identities of SURVEY.md section 8c.  CPU only."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import dsvgp_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KCASES = torch.load(os.path.join(GOLD, "kernel_cases.pt"))
+SCASES = torch.load(os.path.join(GOLD, "step_cases.pt"))
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("name", sorted(KCASES))
+def test_kernel_matches_reference_file(name):
+    c = KCASES[name]
+    ell = torch.nn.functional.softplus(c["raw_ell"]).reshape(())
+    tol = 1e-12 if c["K"].dtype == torch.float64 else 2e-6
+    for fn in (O.kernel_closed_form, O.kernel_reference_structure):
+        K = fn(c["x1"], c["x2"], c["v1"], c["v2"], ell)
+        assert K.shape == c["K"].shape
+        assert rel(K, c["K"]) < tol, (fn.__name__, rel(K, c["K"]))
+    if "Kdiag" in c:
+        n, p = c["x1"].shape[0], c["v1"].shape[0] // c["x1"].shape[0]
+        assert rel(O.kernel_diag(n, p, ell), c["Kdiag"]) < tol
+        assert rel(O.kernel_closed_form(c["x1"], c["x1"], c["v1"], c["v1"], ell).diagonal(), c["Kdiag"]) < tol
+
+
+def _case(name):
+    c = SCASES[name]
+    P = O.Params(**{k: v.clone() for k, v in c["params"].items()})
+    return c, P
+
+
+@pytest.mark.parametrize("structure", ["lean", "reference"])
+@pytest.mark.parametrize("name", sorted(SCASES))
+def test_step_matches_reference_files(name, structure):
+    c, P = _case(name)
+    f64 = c["x"].dtype == torch.float64
+    # fp32: the reference's own fp32 arithmetic (expanded distances, fp32 K_zz before the fp64 Cholesky) is only
+    # reproducible to a few 1e-5; the gate north_star states is 1e-4 relative.
+    tol_v, tol_g = (1e-9, 1e-7) if f64 else (1e-4, 1e-4)
+    val, grads = O.elbo_and_grads(P, c["x"], c["Vx"], c["y"], c["num_data"], c["variant"], structure)
+    assert abs(float(val - c["elbo"])) / abs(float(c["elbo"])) < tol_v
+    for k, g in c["grads"].items():
+        assert rel(grads[k].reshape(g.shape), g) < tol_g, (k, rel(grads[k].reshape(g.shape), g))
+    mean, var = O.predict(P, c["x"], c["Vx"], c["variant"], structure)
+    assert rel(mean, c["pred_mean"]) < (1e-9 if f64 else 1e-4)
+    assert rel(var, c["pred_variance"]) < (1e-9 if f64 else 1e-4)
+    assert rel(mean, c["train_mean"]) < (1e-9 if f64 else 1e-4)
+
+
+def test_kernel_is_directional_derivative_of_rbf():
+    """8c(1): K equals value / directional derivatives / mixed second derivative of the scalar RBF by autograd."""
+    torch.manual_seed(0)
+    d, ell = 4, torch.tensor(0.7, dtype=torch.float64)
+    a = torch.rand(d, dtype=torch.float64, requires_grad=True)
+    b = torch.rand(d, dtype=torch.float64, requires_grad=True)
+    u = torch.randn(2, d, dtype=torch.float64)
+    w = torch.randn(2, d, dtype=torch.float64)
+    K = O.kernel_closed_form(a.detach()[None], b.detach()[None], u, w, ell)
+    k = torch.exp(-0.5 * ((a - b) ** 2).sum() / ell ** 2)
+    ga, = torch.autograd.grad(k, a, create_graph=True)
+    gb, = torch.autograd.grad(k, b, create_graph=True)
+    un, wn = O.normalize_rows(u), O.normalize_rows(w)
+    assert abs(float(K[0, 0] - k)) < 1e-14
+    for i in range(2):
+        assert abs(float(K[1 + i, 0] - ga @ un[i])) < 1e-13
+        assert abs(float(K[0, 1 + i] - gb @ wn[i])) < 1e-13
+        for j in range(2):
+            h, = torch.autograd.grad(ga @ un[i], b, retain_graph=True)
+            assert abs(float(K[1 + i, 1 + j] - h @ wn[j])) < 1e-13
+
+
+def test_kernel_transpose_and_psd():
+    """8c(2),(4): K(x2,x1;v2,v1)^T = K(x1,x2;v1,v2); K(x,x;v,v) is symmetric PSD."""
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.rand(6, 3, generator=g, dtype=torch.float64), torch.rand(8, 3, generator=g, dtype=torch.float64)
+    v1, v2 = torch.randn(12, 3, generator=g, dtype=torch.float64), torch.randn(16, 3, generator=g, dtype=torch.float64)
+    ell = torch.tensor(0.5, dtype=torch.float64)
+    assert rel(O.kernel_closed_form(x2, x1, v2, v1, ell).T, O.kernel_closed_form(x1, x2, v1, v2, ell)) < 1e-14
+    K = O.kernel_closed_form(x1, x1, v1, v1, ell)
+    assert rel(K, K.T) < 1e-14
+    assert torch.linalg.eigvalsh(K).min() > -1e-12
+
+
+def test_full_gradient_kernel_is_canonical_special_case():
+    """8c(5): with p = d and v = I the directional kernel is the analytic RBF gradient kernel (RBFKernelGrad)."""
+    g = torch.Generator().manual_seed(4)
+    d = 3
+    x1, x2 = torch.rand(5, d, generator=g, dtype=torch.float64), torch.rand(4, d, generator=g, dtype=torch.float64)
+    ell = torch.tensor(0.6, dtype=torch.float64)
+    K = O.kernel_closed_form(x1, x2, O.canonical_directions(5, d, d), O.canonical_directions(4, d, d), ell)
+    diff = (x1[:, None] - x2[None]) / ell ** 2
+    k = torch.exp(-0.5 * ((x1[:, None] - x2[None]) ** 2).sum(-1) / ell ** 2)
+    Kb = K.reshape(5, d + 1, 4, d + 1)
+    assert rel(Kb[:, 0, :, 0], k) < 1e-14
+    assert rel(Kb[:, 0, :, 1:], diff * k[..., None]) < 1e-14
+    assert rel(Kb[:, 1:, :, 0], (-diff * k[..., None]).permute(0, 2, 1)) < 1e-14
+    H = (torch.eye(d, dtype=torch.float64) / ell ** 2 - diff[..., :, None] * diff[..., None, :]) * k[..., None, None]
+    assert rel(Kb[:, 1:, :, 1:], H.permute(0, 2, 1, 3)) < 1e-14
+
+
+def test_elbo_is_textbook_minus_half():
+    """8c(6) / Q3: the value through likelihood(model(x)) is the textbook ELBO minus exactly 0.5."""
+    P, x, Vx, y, nd = O.make_problem(20, 2, 6, 2, torch.float64, 7)
+    a = O.elbo(P, x, Vx, y, nd, through_likelihood=True)
+    b = O.elbo(P, x, Vx, y, nd, through_likelihood=False)
+    assert abs(float(a - (b - 0.5))) < 1e-12
+
+
+def test_gradients_against_finite_differences():
+    """8c(7): oracle autograd (fp64) against central differences on a few coordinates of every parameter."""
+    P, x, Vx, y, nd = O.make_problem(12, 3, 5, 2, torch.float64, 8)
+    _, grads = O.elbo_and_grads(P, x, Vx, y, nd)
+    h = 1e-6
+    for name, g in grads.items():
+        t = getattr(P, name)
+        flat = t.reshape(-1)
+        idxs = [0, flat.numel() // 2, flat.numel() - 1] if name != "Ls_raw" else [0, t.shape[1] + 1, t.shape[1] * 3 + 1]
+        for i in idxs:
+            old = float(flat[i])
+            flat[i] = old + h
+            fp = float(O.elbo(P, x, Vx, y, nd))
+            flat[i] = old - h
+            fm = float(O.elbo(P, x, Vx, y, nd))
+            flat[i] = old
+            fd = (fp - fm) / (2 * h)
+            assert abs(fd - float(g.reshape(-1)[i])) < 1e-5 * max(1.0, abs(fd)), (name, i, fd, float(g.reshape(-1)[i]))
+
+
+def test_upper_triangle_of_raw_cholesky_parameter_is_ignored():
+    P, x, Vx, y, nd = O.make_problem(10, 2, 4, 1, torch.float64, 9)
+    a = O.elbo(P, x, Vx, y, nd)
+    P.Ls_raw = P.Ls_raw.tril()
+    assert float(a) == float(O.elbo(P, x, Vx, y, nd))
+
+
+def test_cholesky_failure_ladder_and_nan():
+    A = -torch.eye(3, dtype=torch.float64)
+    with pytest.raises(O.NotPSDError):
+        O.psd_safe_cholesky(A)
+    A = torch.eye(3, dtype=torch.float64)
+    A[1, 1] = -5e-7            # rescued by the first 1e-6 rung
+    assert torch.isfinite(O.psd_safe_cholesky(A)).all()
+    A[0, 0] = math.nan
+    with pytest.raises(O.NanError):
+        O.psd_safe_cholesky(A)
