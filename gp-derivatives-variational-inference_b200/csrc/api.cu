@@ -1,0 +1,116 @@
+// extern "C" surface of libdsvgp_b200.so -- see include/dsvgp_b200.h for the contract of every entry point.
+#include "../../include/dsvgp_b200.h"
+#include "chol.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kdir.cuh"
+#include "misc.cuh"
+
+using namespace dsvgp;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int dsvgp_version(void) { return 100; }
+int dsvgp_built_for_sm(void) { return 100; }
+
+int dsvgp_hyp_from_raw_f32(const float* a, const float* b, const float* c, const float* d, double* hyp, dsvgp_stream_t s) { return hyp_from_raw<float>(a, b, c, d, hyp, ST(s)); }
+int dsvgp_hyp_from_raw_f64(const double* a, const double* b, const double* c, const double* d, double* hyp, dsvgp_stream_t s) { return hyp_from_raw<double>(a, b, c, d, hyp, ST(s)); }
+
+int dsvgp_normalize_dirs_f32(const float* v, int rows, int d, float* vh, float* inv, dsvgp_stream_t s) { return normalize_dirs<float, float>(v, rows, d, vh, inv, ST(s)); }
+int dsvgp_normalize_dirs_f64(const double* v, int rows, int d, double* vh, double* inv, dsvgp_stream_t s) { return normalize_dirs<double, double>(v, rows, d, vh, inv, ST(s)); }
+int dsvgp_normalize_dirs_f32f64(const float* v, int rows, int d, double* vh, double* inv, dsvgp_stream_t s) { return normalize_dirs<float, double>(v, rows, d, vh, inv, ST(s)); }
+
+#define KFWD(NAME, T, TK)                                                                                          \
+  int NAME(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,            \
+           const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, dsvgp_stream_t s) {                 \
+    if (!x1 || !x2 || !hyp || !K || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;                     \
+    return kdir_fwd<T, TK>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s));               \
+  }
+KFWD(dsvgp_kdir_fwd_f32, float, float)
+KFWD(dsvgp_kdir_fwd_f64, double, double)
+KFWD(dsvgp_kdir_fwd_f32f64, float, double)
+
+int dsvgp_kdir_diag_f32(int n, int p, const double* hyp, int use_os, float* out, dsvgp_stream_t s) { return kdir_diag<float>(n, p, hyp, use_os, out, ST(s)); }
+int dsvgp_kdir_diag_f64(int n, int p, const double* hyp, int use_os, double* out, dsvgp_stream_t s) { return kdir_diag<double>(n, p, hyp, use_os, out, ST(s)); }
+
+size_t dsvgp_kdir_bwd_workspace_f32(int n1, int p1, int n2, int p2, int d) { return kdir_bwd_workspace<float>(n1, p1, n2, p2, d); }
+size_t dsvgp_kdir_bwd_workspace_f64(int n1, int p1, int n2, int p2, int d) { return kdir_bwd_workspace<double>(n1, p1, n2, p2, d); }
+
+#define KBWD(NAME, T, TK)                                                                                          \
+  int NAME(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2,   \
+           int d, const double* hyp, int use_os, const TK* dK, int64_t lddk, int dk_trans, double scale,           \
+           double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, dsvgp_stream_t s) {                     \
+    if (!x1 || !x2 || !hyp || !dK || !ws || (p1 > 0 && (!u1 || !inv1)) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;  \
+    return kdir_bwd<T, TK>(x1, u1, inv1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, dK, lddk, dk_trans, scale, gx,    \
+                           gv, gsc, ws, ws_bytes, ST(s));                                                          \
+  }
+KBWD(dsvgp_kdir_bwd_f32, float, float)
+KBWD(dsvgp_kdir_bwd_f64, double, double)
+KBWD(dsvgp_kdir_bwd_f32f64, float, double)
+
+void dsvgp_chol_plan(int Mq, int* Mp, int* nb0, int* nlev) { chol_plan(Mq, Mp, nb0, nlev); }
+int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t s) { return pad_identity(A, ld, Mq, Mp, ST(s)); }
+int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0, int nlev, int* info, dsvgp_stream_t s) {
+  return chol_factor_inverse(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, ST(s));
+}
+
+int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, dsvgp_stream_t s) {
+  return gemm<float>(ta != 0, tb != 0, M, N, K, (float)alpha, A, lda, B, ldb, (float)beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd);
+}
+int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, dsvgp_stream_t s) {
+  return gemm<double>(ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd);
+}
+
+int dsvgp_cast_f64_f32(const double* a, int64_t lda, float* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<double, float>(a, lda, b, ldb, r, c, tril, ST(s)); }
+int dsvgp_cast_f32_f64(const float* a, int64_t lda, double* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<float, double>(a, lda, b, ldb, r, c, tril, ST(s)); }
+int dsvgp_cast_f64_f64(const double* a, int64_t lda, double* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<double, double>(a, lda, b, ldb, r, c, tril, ST(s)); }
+int dsvgp_cast_f32_f32(const float* a, int64_t lda, float* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<float, float>(a, lda, b, ldb, r, c, tril, ST(s)); }
+int dsvgp_mirror_lower_f32(float* A, int64_t ld, int n, dsvgp_stream_t s) { return mirror_lower<float>(A, ld, n, ST(s)); }
+int dsvgp_mirror_lower_f64(double* A, int64_t ld, int n, dsvgp_stream_t s) { return mirror_lower<double>(A, ld, n, ST(s)); }
+int dsvgp_add_outer_f32(float* A, int64_t ld, int n, const float* u, const float* v, double alpha, dsvgp_stream_t s) { return add_outer<float>(A, ld, n, u, v, alpha, ST(s)); }
+int dsvgp_add_outer_f64(double* A, int64_t ld, int n, const double* u, const double* v, double alpha, dsvgp_stream_t s) { return add_outer<double>(A, ld, n, u, v, alpha, ST(s)); }
+int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return sym_phi(Y, ldy, P, ldp, n, ST(s)); }
+
+int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
+
+#define PER_T(SUF, T)                                                                                              \
+  int dsvgp_col_dots_##SUF(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm,    \
+                           T* pv, int nslab, dsvgp_stream_t s) {                                                   \
+    if (!A || !m || !pm || !pv) return DSVGP_ERR_ARG;                                                              \
+    return col_dots<T>(A, C, B, ld, rows, nq, m, pm, pv, nslab, ST(s));                                            \
+  }                                                                                                                \
+  int dsvgp_predict_finish_##SUF(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp,           \
+                                 double pred_jitter, int add_noise, double min_var, T* mu, T* var,                 \
+                                 dsvgp_stream_t s) {                                                               \
+    if (!pm || !pv || !hyp || !mu || !var) return DSVGP_ERR_ARG;                                                   \
+    return predict_finish<T>(pm, pv, nslab, nq, p2, hyp, pred_jitter, add_noise, min_var, mu, var, ST(s));         \
+  }                                                                                                                \
+  int dsvgp_elbo_terms_##SUF(const T* mu, const T* var, const T* y, int nq, const double* hyp, double w,           \
+                             double min_var, T* gmu, T* gvar, double* sc, double* ws, dsvgp_stream_t s) {          \
+    if (!mu || !var || !y || !hyp || !gmu || !gvar || !sc || !ws) return DSVGP_ERR_ARG;                            \
+    return elbo_terms<T>(mu, var, y, nq, hyp, w, min_var, gmu, gvar, sc, ws, ST(s));                               \
+  }                                                                                                                \
+  int dsvgp_pred_bwd_scalars_##SUF(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise,  \
+                                   double* gsc, double* ws, dsvgp_stream_t s) {                                    \
+    if (!gmu || !gvar || !hyp || !gsc || !ws) return DSVGP_ERR_ARG;                                                \
+    return pred_bwd_scalars<T>(gmu, gvar, nq, p2, hyp, add_noise, gsc, ws, ST(s));                                 \
+  }                                                                                                                \
+  int dsvgp_dA_##SUF(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu,              \
+                     const T* gvar, T* tp, int nslab, T* t, dsvgp_stream_t s) {                                    \
+    if (!A || !C || !m || !gmu || !gvar || !tp || !t || nslab < 1) return DSVGP_ERR_ARG;                           \
+    return dA_apply<T>(A, C, Ag, ld, rows, nq, m, gmu, gvar, tp, nslab, t, ST(s));                                 \
+  }                                                                                                                \
+  int dsvgp_kl_##SUF(const T* m, const T* Ls, int64_t ld, int Mq, double* out, double* ws, dsvgp_stream_t s) {     \
+    if (!m || !Ls || !out || !ws) return DSVGP_ERR_ARG;                                                            \
+    return kl_divergence<T>(m, Ls, ld, Mq, out, ws, ST(s));                                                        \
+  }                                                                                                                \
+  int dsvgp_var_grads_##SUF(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, const T* m, int Mq,     \
+                            double inv_nd, T* gm, T* gLs, int64_t ldg, dsvgp_stream_t s) {                         \
+    if (!H || !Ls || !t || !m || !gm || !gLs) return DSVGP_ERR_ARG;                                                \
+    return var_grads<T>(H, ldh, Ls, ldl, t, m, Mq, inv_nd, gm, gLs, ldg, ST(s));                                   \
+  }
+PER_T(f32, float)
+PER_T(f64, double)
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+// Blocked fp64 Cholesky + explicit triangular inverse (definitions in chol.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dsvgp {
+
+// Padded size Mp = nb0 << nlev >= Mq with nb0 <= 112, nb0 % 4 == 0.
+void chol_plan(int Mq, int* Mp, int* nb0, int* nlev);
+
+// Awork (Mp x Mp, lower part holds the SPD matrix, identity on the padding) is destroyed.
+// L (lower, diagonal blocks have their upper part zeroed) and W = L^-1 (lower) are written.
+// *info (device): 0 on success, else 1 + index of the first non-positive pivot.
+int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
+                        int nlev, int* info, cudaStream_t st);
+
+}  // namespace dsvgp

@@ -1,0 +1,251 @@
+// Triangle-aware batched GEMM on the legacy warp-level tensor path (mma.sync), fp64 (DMMA m8n8k4) and
+// fp32-accurate 3xTF32 (m16n8k8).  This is the general-shape workhorse for everything around the hot whitening
+// GEMMs: Cholesky panel / trailing updates, the recursive triangular inverse, the replicated M'^3 backward
+// tail, and -- until/unless the tcgen05 kernel in trmm_tc.cu takes a shape -- the whitening products themselves.
+//
+//   C = alpha * op(A) * op(B) + beta * C         op(A): M x K, op(B): K x N, all row-major with leading dims
+//
+// a_tri / b_tri say that op(A) / op(B) is lower (1) or upper (2) triangular *as an operand of the product*:
+// whole k-ranges that multiply structural zeros are skipped and the elements on the wrong side of the diagonal
+// are masked to zero at load time, so a buffer whose other triangle holds garbage (the raw chol_variational_covar
+// parameter, a Cholesky factor written in place) can be passed as is.  c_tri = 1 computes only the tiles that
+// touch the lower triangle of C (SYRK-like results).
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace dsvgp {
+
+constexpr int BM = 64, BN = 64, BK = 16, LDS_ = BK + 4, GEMM_THREADS = 128;
+
+__device__ __forceinline__ void mma_f64(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <typename T>
+struct GemmParams {
+  const T* A; const T* B; T* C; const T* D;   // D: addend scaled by beta (== C unless given)
+  int M, N, K;
+  int64_t lda, ldb, ldc, ldd, sA, sB, sC;
+  T alpha, beta;
+  int a_tri, b_tri, c_tri;
+};
+
+// element (r, k) of op(A) (r in M, k in K) lives at A[r*lda + k] (TA=false) or A[k*lda + r] (TA=true)
+template <typename T, bool TA, bool TB>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_kernel(GemmParams<T> p) {
+  __shared__ __align__(16) T As[2][BM * LDS_];
+  __shared__ __align__(16) T Bs[2][BN * LDS_];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (p.c_tri == 1 && n0 >= m0 + BM) return;     // tile strictly above the diagonal
+  const T* A = p.A + (int64_t)blockIdx.z * p.sA;
+  const T* B = p.B + (int64_t)blockIdx.z * p.sB;
+  T* C = p.C + (int64_t)blockIdx.z * p.sC;
+  const T* D = p.D ? p.D : C;   // an explicit addend is not batched
+  const int64_t ldd = p.D ? p.ldd : p.ldc;
+
+  // k-range that can be non-zero for this tile
+  int kbeg = 0, kend = p.K;
+  if (p.a_tri == 1) kend = min(kend, m0 + BM);          // lower: k <= r
+  if (p.a_tri == 2) kbeg = max(kbeg, m0);               // upper: k >= r
+  if (p.b_tri == 1) kbeg = max(kbeg, n0);               // lower: k >= c
+  if (p.b_tri == 2) kend = min(kend, n0 + BN);          // upper: k <= c
+  kbeg = (kbeg / BK) * BK;
+
+  constexpr int PER = BM * BK / GEMM_THREADS;   // 8 elements of each operand per thread per stage
+  T ra[PER], rb[PER];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int r, k;
+      if (!TA) { r = e / BK; k = e % BK; } else { k = e / BM; r = e % BM; }
+      const int gr = m0 + r, gk = k0 + k;
+      bool ok = gr < p.M && gk < p.K;
+      if (p.a_tri == 1) ok = ok && gk <= gr;
+      if (p.a_tri == 2) ok = ok && gk >= gr;
+      ra[q] = ok ? (TA ? A[(int64_t)gk * p.lda + gr] : A[(int64_t)gr * p.lda + gk]) : T(0);
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int c, k;
+      if (TB) { c = e / BK; k = e % BK; } else { k = e / BN; c = e % BN; }
+      const int gc = n0 + c, gk = k0 + k;
+      bool ok = gc < p.N && gk < p.K;
+      if (p.b_tri == 1) ok = ok && gk >= gc;
+      if (p.b_tri == 2) ok = ok && gk <= gc;
+      rb[q] = ok ? (TB ? B[(int64_t)gc * p.ldb + gk] : B[(int64_t)gk * p.ldb + gc]) : T(0);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int r, k;
+      if (!TA) { r = e / BK; k = e % BK; } else { k = e / BM; r = e % BM; }
+      As[buf][r * LDS_ + k] = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int c, k;
+      if (TB) { c = e / BK; k = e % BK; } else { k = e / BN; c = e % BN; }
+      Bs[buf][c * LDS_ + k] = rb[q];
+    }
+  };
+
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // warp tile origin inside the CTA tile
+  const int g = lane >> 2, t = lane & 3;
+
+  constexpr bool F64 = sizeof(T) == 8;
+  // accumulators: fp64 4x4 m8n8 tiles x 2 ; fp32 2x4 m16n8 tiles x 4
+  double acc64[F64 ? 4 : 1][F64 ? 4 : 1][2];
+  float acc32[F64 ? 1 : 2][F64 ? 1 : 4][4];
+  if constexpr (F64) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc64[i][j][0] = acc64[i][j][1] = 0.0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc32[i][j][q] = 0.f;
+  }
+
+  if (kbeg < kend) {
+    load_tiles(kbeg);
+    store_tiles(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+      const bool more = k0 + BK < kend;
+      if (more) load_tiles(k0 + BK);
+      const T* as = As[buf];
+      const T* bs = Bs[buf];
+      if constexpr (F64) {
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+          double af[4], bf[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) af[i] = as[(wm + 8 * i + g) * LDS_ + kk + t];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bf[j] = bs[(wn + 8 * j + g) * LDS_ + kk + t];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_f64(acc64[i][j], af[i], bf[j]);
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 8) {
+          uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = wm + 16 * i + g;
+            const float v[4] = {(float)as[r * LDS_ + kk + t], (float)as[(r + 8) * LDS_ + kk + t],
+                                (float)as[r * LDS_ + kk + t + 4], (float)as[(r + 8) * LDS_ + kk + t + 4]};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              ah[i][q] = to_tf32(v[q]);
+              al[i][q] = to_tf32(v[q] - __uint_as_float(ah[i][q]));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = wn + 8 * j + g;
+            const float v[2] = {(float)bs[c * LDS_ + kk + t], (float)bs[c * LDS_ + kk + t + 4]};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              bh[j][q] = to_tf32(v[q]);
+              bl[j][q] = to_tf32(v[q] - __uint_as_float(bh[j][q]));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mma_tf32(acc32[i][j], al[i], bh[j]);   // small terms first
+              mma_tf32(acc32[i][j], ah[i], bl[j]);
+              mma_tf32(acc32[i][j], ah[i], bh[j]);
+            }
+        }
+      }
+      if (more) {
+        store_tiles(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+      }
+    }
+  }
+
+  // epilogue
+  auto put = [&](int r, int c, T v) {
+    if (r < p.M && c < p.N) {
+      T* dst = C + (int64_t)r * p.ldc + c;
+      *dst = (p.beta == T(0)) ? p.alpha * v : p.alpha * v + p.beta * D[(int64_t)r * ldd + c];
+    }
+  };
+  if constexpr (F64) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = m0 + wm + 8 * i + g, c = n0 + wn + 8 * j + 2 * t;
+        put(r, c, (T)acc64[i][j][0]);
+        put(r, c + 1, (T)acc64[i][j][1]);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = m0 + wm + 16 * i + g, c = n0 + wn + 8 * j + 2 * t;
+        put(r, c, (T)acc32[i][j][0]);
+        put(r, c + 1, (T)acc32[i][j][1]);
+        put(r + 8, c, (T)acc32[i][j][2]);
+        put(r + 8, c + 1, (T)acc32[i][j][3]);
+      }
+  }
+}
+
+template <typename T>
+int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
+         T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
+         cudaStream_t st, const T* D, int64_t ldd) {
+  if (M <= 0 || N <= 0 || batch <= 0) return DSVGP_OK;
+  if (!A || !B || !C || K < 0) return DSVGP_ERR_ARG;
+  GemmParams<T> p{A, B, C, D, M, N, K, lda, ldb, ldc, ldd, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri};
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
+  if (!ta && !tb) gemm_kernel<T, false, false><<<grid, GEMM_THREADS, 0, st>>>(p);
+  else if (!ta && tb) gemm_kernel<T, false, true><<<grid, GEMM_THREADS, 0, st>>>(p);
+  else if (ta && !tb) gemm_kernel<T, true, false><<<grid, GEMM_THREADS, 0, st>>>(p);
+  else gemm_kernel<T, true, true><<<grid, GEMM_THREADS, 0, st>>>(p);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template int gemm<float>(bool, bool, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*,
+                         int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const float*, int64_t);
+template int gemm<double>(bool, bool, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
+                          double*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const double*, int64_t);
+
+}  // namespace dsvgp

@@ -1,0 +1,23 @@
+// Triangle-aware batched GEMM (definitions in gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dsvgp {
+
+enum { TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
+
+// C = alpha*op(A)*op(B) + beta*C, row-major.  a_tri/b_tri: structure of op(A)/op(B) as product operands.
+// c_tri = 1: only tiles touching the lower triangle of C are computed (the rest of C is left untouched).
+// batch > 1: operand z lives at base + z*stride (element strides sA, sB, sC).
+template <typename T>
+int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
+         T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
+         cudaStream_t st, const T* D = nullptr, int64_t ldd = 0);   // D != null: C = alpha*AB + beta*D
+
+template <typename T>
+inline int gemm1(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+                 T beta, T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, cudaStream_t st) {
+  return gemm<T>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, 1, 0, 0, 0, st);
+}
+
+}  // namespace dsvgp

@@ -1,0 +1,721 @@
+// Fused RBF directional-gradient kernel assembly (forward, backward, diag) for sm_100a.
+//
+// Replaces the ~45 eager ops of the reference's RBFKernelDirectionalGrad.forward
+// (/root/reference/directionalvi/RBFKernelDirectionalGrad.py:41-108) and their autograd backward:
+// with D = x1_i - x2_j, k = os*exp(-|D|^2 / 2l^2), u = v1[i,a-1]/|v1[i,a-1]|, w = v2[j,b-1]/|v2[j,b-1]|,
+//   K[i(p1+1)+a, j(p2+1)+b] = k                                   a=b=0
+//                             k (D.w)/l^2                          a=0,b>0
+//                            -k (D.u)/l^2                          a>0,b=0
+//                             k (u.w/l^2 - (D.u)(D.w)/l^4)         a,b>0
+// written ONCE, directly in the interleaved layout the reference reaches through two full-matrix gathers
+// (:105-107).  Inputs are staged through shared memory in d-chunks; the output tile is staged in shared
+// memory so every global store is a full coalesced row segment.
+//
+// T  = dtype of x (model dtype); TK = dtype of K / dK and of all arithmetic (double for K_zz always, because
+// the reference factorises K_zz in fp64, DirectionalGradVariationalStrategy.py:74).
+#include "common.cuh"
+#include "kdir.cuh"
+
+namespace dsvgp {
+
+// ------------------------------------------------------------------------------------------------ prep
+// One warp per direction row: vhat = v / |v|, inv_norm = 1/|v|   (RBFKernelDirectionalGrad.py:57-58)
+template <typename T, typename TK>
+__global__ void normalize_dirs_kernel(const T* __restrict__ v, int rows, int d, TK* __restrict__ vhat,
+                                      TK* __restrict__ inv_norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  TK s = 0;
+  for (int c = lane; c < d; c += 32) {
+    TK a = (TK)v[(int64_t)row * d + c];
+    s += a * a;
+  }
+  s = warp_sum(s);
+  const TK inv = TK(1) / dsqrt<TK>(s);
+  for (int c = lane; c < d; c += 32) vhat[(int64_t)row * d + c] = (TK)v[(int64_t)row * d + c] * inv;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+// --------------------------------------------------------------------------------------- forward (blocked)
+template <typename TK> struct FwdTile { static constexpr int TI = 32; };
+template <> struct FwdTile<double> { static constexpr int TI = 16; };
+constexpr int FWD_TJ = 32;
+constexpr int FWD_DC = 16;
+constexpr int FWD_LDX = FWD_TJ + 1;   // padded row of the transposed column-side staging
+
+template <typename TK, int P1, int P2>
+constexpr size_t fwd_smem_bytes() {
+  constexpr int TI = FwdTile<TK>::TI;
+  return sizeof(TK) * (size_t)(TI * FWD_DC + TI * P1 * FWD_DC + FWD_DC * FWD_LDX + P2 * FWD_DC * FWD_LDX +
+                               TI * (P1 + 1) * (FWD_TJ * (P2 + 1) + 1));
+}
+
+template <typename T, typename TK, int P1, int P2>
+__global__ void __launch_bounds__(256)
+kdir_fwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, const T* __restrict__ x2,
+                 const TK* __restrict__ w2, int n2, int d, const double* __restrict__ hyp, int use_os,
+                 TK diag_add, TK* __restrict__ K, int64_t ldk) {
+  constexpr int TI = FwdTile<TK>::TI, TJ = FWD_TJ, DC = FWD_DC, RP = TI / 8;
+  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, LDS = TJ * Q2 + 1, LDX = FWD_LDX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TK* x1s = reinterpret_cast<TK*>(smem_raw);      // [TI][DC]
+  TK* u1s = x1s + TI * DC;                        // [TI*P1][DC]
+  TK* x2s = u1s + TI * P1 * DC;                   // [DC][LDX]
+  TK* w2s = x2s + DC * LDX;                       // [P2][DC][LDX]
+  TK* Ks = w2s + P2 * DC * LDX;                    // [TI*Q1][LDS]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+
+  TK r2[RP], al[RP][P1 > 0 ? P1 : 1], be[RP][P2 > 0 ? P2 : 1], ga[RP][P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1];
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    r2[r] = 0;
+#pragma unroll
+    for (int a = 0; a < P1; ++a) al[r][a] = 0;
+#pragma unroll
+    for (int b = 0; b < P2; ++b) be[r][b] = 0;
+#pragma unroll
+    for (int a = 0; a < P1; ++a)
+#pragma unroll
+      for (int b = 0; b < P2; ++b) ga[r][a][b] = 0;
+  }
+
+  for (int c0 = 0; c0 < d; c0 += DC) {
+    __syncthreads();
+    for (int e = tid; e < TI * DC; e += 256) {
+      const int i = e / DC, cc = e % DC;
+      const bool ok = (i0 + i < n1) && (c0 + cc < d);
+      x1s[e] = ok ? (TK)x1[(int64_t)(i0 + i) * d + c0 + cc] : TK(0);
+    }
+    for (int e = tid; e < TI * P1 * DC; e += 256) {
+      const int ia = e / DC, cc = e % DC;
+      const bool ok = (i0 * P1 + ia < n1 * P1) && (c0 + cc < d);
+      u1s[e] = ok ? u1[(int64_t)(i0 * P1 + ia) * d + c0 + cc] : TK(0);
+    }
+    for (int e = tid; e < TJ * DC; e += 256) {
+      const int j = e / DC, cc = e % DC;
+      const bool ok = (j0 + j < n2) && (c0 + cc < d);
+      x2s[cc * LDX + j] = ok ? (TK)x2[(int64_t)(j0 + j) * d + c0 + cc] : TK(0);
+    }
+    for (int e = tid; e < TJ * P2 * DC; e += 256) {
+      const int jb = e / DC, cc = e % DC, j = jb / (P2 > 0 ? P2 : 1), b = jb % (P2 > 0 ? P2 : 1);
+      const bool ok = (j0 + j < n2) && (c0 + cc < d);
+      w2s[(b * DC + cc) * LDX + j] = ok ? w2[(int64_t)((j0 + j) * P2 + b) * d + c0 + cc] : TK(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < DC; ++cc) {
+      const TK xj = x2s[cc * LDX + lane];
+      TK wj[P2 > 0 ? P2 : 1];
+#pragma unroll
+      for (int b = 0; b < P2; ++b) wj[b] = w2s[(b * DC + cc) * LDX + lane];
+#pragma unroll
+      for (int r = 0; r < RP; ++r) {
+        const int i = warp + 8 * r;
+        const TK dl = x1s[i * DC + cc] - xj;
+        r2[r] += dl * dl;
+#pragma unroll
+        for (int b = 0; b < P2; ++b) be[r][b] += dl * wj[b];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+          const TK ui = u1s[(i * P1 + a) * DC + cc];
+          al[r][a] += dl * ui;
+#pragma unroll
+          for (int b = 0; b < P2; ++b) ga[r][a][b] += ui * wj[b];
+        }
+      }
+    }
+  }
+
+  const TK ell = (TK)hyp[0], os = use_os ? (TK)hyp[1] : TK(1);
+  const TK il2 = TK(1) / (ell * ell);
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    const int i = warp + 8 * r;
+    const TK k = os * dexp<TK>(TK(-0.5) * r2[r] * il2);
+    const bool dg = (diag_add != TK(0)) && (i0 + i == j0 + lane);
+    TK* row0 = Ks + (i * Q1) * LDS + lane * Q2;
+    row0[0] = k + (dg ? diag_add : TK(0));
+#pragma unroll
+    for (int b = 0; b < P2; ++b) row0[1 + b] = k * be[r][b] * il2;
+#pragma unroll
+    for (int a = 0; a < P1; ++a) {
+      TK* rowa = row0 + (1 + a) * LDS;
+      const TK aa = al[r][a] * il2;
+      rowa[0] = -k * aa;
+#pragma unroll
+      for (int b = 0; b < P2; ++b)
+        rowa[1 + b] = k * (ga[r][a][b] * il2 - aa * be[r][b] * il2) + ((dg && a == b) ? diag_add : TK(0));
+    }
+  }
+  __syncthreads();
+  // coalesced write-out: each row of the tile is a contiguous TJ*Q2 segment of the output row
+  const int rows = min(TI * Q1, n1 * Q1 - i0 * Q1);
+  const int cols = min(TJ * Q2, n2 * Q2 - j0 * Q2);
+  TK* Kt = K + (int64_t)(i0 * Q1) * ldk + (int64_t)j0 * Q2;
+  for (int e = tid; e < rows * (TJ * Q2); e += 256) {
+    const int rr = e / (TJ * Q2), cc = e % (TJ * Q2);
+    if (cc < cols) Kt[(int64_t)rr * ldk + cc] = Ks[rr * LDS + cc];
+  }
+}
+
+// ------------------------------------------------------------------------------------- forward (runtime p)
+// Fallback for p1 or p2 > DSVGP_MAXP_FAST (e.g. the full-gradient strategy with large d): one thread per
+// point pair, directions read through L1/L2.  Correct for any p <= DSVGP_MAXP; not tuned.
+template <typename T, typename TK>
+__global__ void __launch_bounds__(128)
+kdir_fwd_generic(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, int p1, const T* __restrict__ x2,
+                 const TK* __restrict__ w2, int n2, int p2, int d, const double* __restrict__ hyp, int use_os,
+                 TK diag_add, TK* __restrict__ K, int64_t ldk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n2 || i >= n1) return;
+  TK al[DSVGP_MAXP], be[DSVGP_MAXP];
+  const TK ell = (TK)hyp[0], os = use_os ? (TK)hyp[1] : TK(1), il2 = TK(1) / (ell * ell);
+  TK r2 = 0;
+  for (int a = 0; a < p1; ++a) al[a] = 0;
+  for (int b = 0; b < p2; ++b) be[b] = 0;
+  for (int c = 0; c < d; ++c) {
+    const TK dl = (TK)x1[(int64_t)i * d + c] - (TK)x2[(int64_t)j * d + c];
+    r2 += dl * dl;
+    for (int a = 0; a < p1; ++a) al[a] += dl * u1[(int64_t)(i * p1 + a) * d + c];
+    for (int b = 0; b < p2; ++b) be[b] += dl * w2[(int64_t)(j * p2 + b) * d + c];
+  }
+  const TK k = os * dexp<TK>(TK(-0.5) * r2 * il2);
+  const bool dg = (diag_add != TK(0)) && (i == j);
+  TK* Kb = K + (int64_t)i * (p1 + 1) * ldk + (int64_t)j * (p2 + 1);
+  Kb[0] = k + (dg ? diag_add : TK(0));
+  for (int b = 0; b < p2; ++b) Kb[1 + b] = k * be[b] * il2;
+  for (int a = 0; a < p1; ++a) {
+    TK* Ka = Kb + (int64_t)(1 + a) * ldk;
+    Ka[0] = -k * al[a] * il2;
+    for (int b = 0; b < p2; ++b) {
+      TK g = 0;
+      for (int c = 0; c < d; ++c) g += u1[(int64_t)(i * p1 + a) * d + c] * w2[(int64_t)(j * p2 + b) * d + c];
+      Ka[1 + b] = k * (g * il2 - al[a] * il2 * be[b] * il2) + ((dg && a == b) ? diag_add : TK(0));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ diag=True branch
+// RBFKernelDirectionalGrad.py:110-119: [1, 1/l^2, ..., 1/l^2] per point (times outputscale under ScaleKernel).
+template <typename TK>
+__global__ void kdir_diag_kernel(int n, int p, const double* __restrict__ hyp, int use_os, TK* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * (p + 1)) return;
+  const double ell = hyp[0], os = use_os ? hyp[1] : 1.0;
+  out[e] = (TK)((e % (p + 1)) == 0 ? os : os / (ell * ell));
+}
+
+// --------------------------------------------------------------------------------------- backward (blocked)
+// grid = (column chunks, row tiles).  Per column tile of TJ points:
+//   phase A  one thread per point pair recomputes k, alpha, beta, gamma and turns the upstream block
+//            g = dK[i*,j*] into the coefficient block Cf such that
+//              dx1_i  = sum_j Cf[(i,0),(j,:)] . [x2_j; w_j*]  + x1_i * E0_i + sum_a u_ia * Ea_ia
+//              du_ia  = sum_j Cf[(i,a),(j,:)] . [x2_j; w_j*]  + x1_i * Ea_ia
+//   phase B  the small GEMM Cf (TI*Q1 x TJ*Q2) x Y (TJ*Q2 x d) accumulated in registers across column tiles.
+// Partials per column chunk go to a workspace and are summed (deterministically) by kdir_bwd_reduce.
+constexpr int BWD_TI = 16, BWD_TJ = 32, BWD_MAXACC = 16;
+
+template <typename TK> __host__ __device__ constexpr int bwd_ldy(int d) { return d | 1; }
+
+template <typename TK, int P1, int P2>
+size_t bwd_smem_bytes(int d) {
+  const int ldy = d | 1;
+  return sizeof(TK) * (size_t)(BWD_TI * d + BWD_TI * P1 * d + BWD_TJ * (P2 + 1) * ldy +
+                               BWD_TI * (P1 + 1) * (BWD_TJ * (P2 + 1) + 1) + BWD_TI * (P1 + 1)) + 64 * sizeof(double);
+}
+
+template <typename T, typename TK, int P1, int P2>
+__global__ void __launch_bounds__(256)
+kdir_bwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, const T* __restrict__ x2,
+                 const TK* __restrict__ w2, int n2, int d, const double* __restrict__ hyp, int use_os,
+                 const TK* __restrict__ dK, int64_t lddk, int dk_trans, int chunk_pts,
+                 TK* __restrict__ part, double* __restrict__ part_sc) {
+  constexpr int TI = BWD_TI, TJ = BWD_TJ, Q1 = P1 + 1, Q2 = P2 + 1, LDC = TJ * Q2 + 1, RP = TI / 8;
+  const int ldy = d | 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);            // [64] reduction scratch
+  TK* x1s = reinterpret_cast<TK*>(red + 64);                    // [TI][d]
+  TK* u1s = x1s + TI * d;                                       // [TI*P1][d]
+  TK* Ys = u1s + TI * P1 * d;                                   // [TJ*Q2][ldy]   row (j,0)=x2_j, (j,b)=w_jb
+  TK* Cf = Ys + TJ * Q2 * ldy;                                  // [TI*Q1][LDC]
+  TK* rowsum = Cf + TI * Q1 * LDC;                              // [TI*Q1]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * TI;
+  const int jbeg = blockIdx.x * chunk_pts, jend = min(n2, jbeg + chunk_pts);
+  const TK ell = (TK)hyp[0], os = use_os ? (TK)hyp[1] : TK(1), il2 = TK(1) / (ell * ell);
+
+  for (int e = tid; e < TI * d; e += 256) {
+    const int i = e / d;
+    x1s[e] = (i0 + i < n1) ? (TK)x1[(int64_t)i0 * d + e] : TK(0);
+  }
+  for (int e = tid; e < TI * P1 * d; e += 256) {
+    const int ia = e / d;
+    u1s[e] = (i0 * P1 + ia < n1 * P1) ? u1[(int64_t)i0 * P1 * d + e] : TK(0);
+  }
+  for (int e = tid; e < TI * Q1; e += 256) rowsum[e] = 0;
+
+  const int nout = TI * Q1 * d;
+  TK acc[BWD_MAXACC];
+#pragma unroll
+  for (int q = 0; q < BWD_MAXACC; ++q) acc[q] = 0;
+  double s_ell = 0, s_os = 0;
+
+  for (int j0 = jbeg; j0 < jend; j0 += TJ) {
+    __syncthreads();
+    // stage Y = [x2_j; w_j1..w_jP2] rows and the upstream tile
+    for (int e = tid; e < TJ * d; e += 256) {
+      const int j = e / d, c = e % d;
+      Ys[(j * Q2) * ldy + c] = (j0 + j < jend) ? (TK)x2[(int64_t)(j0 + j) * d + c] : TK(0);
+    }
+    for (int e = tid; e < TJ * P2 * d; e += 256) {
+      const int jb = e / d, c = e % d, j = jb / (P2 > 0 ? P2 : 1), b = jb % (P2 > 0 ? P2 : 1);
+      Ys[(j * Q2 + 1 + b) * ldy + c] = (j0 + j < jend) ? w2[(int64_t)((j0 + j) * P2 + b) * d + c] : TK(0);
+    }
+    {
+      const int rows = min(TI * Q1, (n1 - i0) * Q1), cols = min(TJ * Q2, (jend - j0) * Q2);
+      if (!dk_trans) {
+        for (int e = tid; e < TI * Q1 * TJ * Q2; e += 256) {
+          const int rr = e / (TJ * Q2), cc = e % (TJ * Q2);
+          Cf[rr * LDC + cc] = (rr < rows && cc < cols)
+                                  ? dK[(int64_t)(i0 * Q1 + rr) * lddk + (int64_t)j0 * Q2 + cc] : TK(0);
+        }
+      } else {
+        for (int e = tid; e < TI * Q1 * TJ * Q2; e += 256) {
+          const int cc = e / (TI * Q1), rr = e % (TI * Q1);
+          Cf[rr * LDC + cc] = (rr < rows && cc < cols)
+                                  ? dK[(int64_t)((int64_t)j0 * Q2 + cc) * lddk + (i0 * Q1 + rr)] : TK(0);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase A
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const int i = warp + 8 * r;
+      TK r2 = 0, al[P1 > 0 ? P1 : 1], be[P2 > 0 ? P2 : 1], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1];
+#pragma unroll
+      for (int a = 0; a < P1; ++a) al[a] = 0;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) be[b] = 0;
+#pragma unroll
+      for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P2; ++b) ga[a][b] = 0;
+      const TK* yj = Ys + (lane * Q2) * ldy;
+      for (int c = 0; c < d; ++c) {
+        const TK dl = x1s[i * d + c] - yj[c];
+        r2 += dl * dl;
+        TK wj[P2 > 0 ? P2 : 1];
+#pragma unroll
+        for (int b = 0; b < P2; ++b) {
+          wj[b] = yj[(1 + b) * ldy + c];
+          be[b] += dl * wj[b];
+        }
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+          const TK ui = u1s[(i * P1 + a) * d + c];
+          al[a] += dl * ui;
+#pragma unroll
+          for (int b = 0; b < P2; ++b) ga[a][b] += ui * wj[b];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < P1; ++a) al[a] *= il2;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) be[b] *= il2;
+      const TK k = os * dexp<TK>(TK(-0.5) * r2 * il2);
+      TK* cf = Cf + (i * Q1) * LDC + lane * Q2;
+      const TK g00 = cf[0];
+      TK q = g00, sdd = 0;           // q = dL/dk ; sdd = sum(dalpha*alpha + dbeta*beta + dgamma*gamma)
+      TK dbe[P2 > 0 ? P2 : 1], dal[P1 > 0 ? P1 : 1];
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        dbe[b] = cf[1 + b];
+        q += cf[1 + b] * be[b];
+      }
+#pragma unroll
+      for (int a = 0; a < P1; ++a) {
+        const TK ga0 = cf[(1 + a) * LDC];
+        dal[a] = -ga0;
+        q -= ga0 * al[a];
+#pragma unroll
+        for (int b = 0; b < P2; ++b) {
+          const TK gab = cf[(1 + a) * LDC + 1 + b];
+          const TK gam = ga[a][b] * il2;
+          q += gab * (gam - al[a] * be[b]);
+          dal[a] -= gab * be[b];
+          dbe[b] -= gab * al[a];
+          sdd += k * gab * gam;
+          cf[(1 + a) * LDC + 1 + b] = k * gab * il2;       // dgamma / l^2 : multiplies w_jb in du_ia
+        }
+      }
+      const TK e0 = -q * k * il2;
+      cf[0] = -e0;
+      TK rs0 = e0;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        const TK db = k * dbe[b];
+        sdd += db * be[b];
+        cf[1 + b] = db * il2;
+      }
+      rs0 = warp_sum(rs0);
+      if (lane == 0) rowsum[i * Q1] += rs0;
+#pragma unroll
+      for (int a = 0; a < P1; ++a) {
+        const TK da = k * dal[a];
+        sdd += da * al[a];
+        const TK ea = da * il2;
+        cf[(1 + a) * LDC] = -ea;
+        const TK rsa = warp_sum(ea);
+        if (lane == 0) rowsum[i * Q1 + 1 + a] += rsa;
+      }
+      s_ell += (double)(q * k * r2 * il2 / ell - TK(2) * sdd / ell);
+      s_os += (double)(q * k / os);
+    }
+    __syncthreads();
+    // ---- phase B: acc[(row,c)] += sum_jb Cf[row][jb] * Ys[jb][c]
+#pragma unroll
+    for (int qd = 0; qd < BWD_MAXACC; ++qd) {
+      const int o = tid + 256 * qd;
+      if (o < nout) {
+        const int row = o / d, c = o % d;
+        const TK* cr = Cf + row * LDC;
+        TK s = 0;
+#pragma unroll 4
+        for (int jb = 0; jb < TJ * Q2; ++jb) s += cr[jb] * Ys[jb * ldy + c];
+        acc[qd] += s;
+      }
+    }
+  }
+  __syncthreads();
+  TK* pout = part + ((int64_t)blockIdx.x * n1 * Q1 + (int64_t)i0 * Q1) * d;
+#pragma unroll
+  for (int qd = 0; qd < BWD_MAXACC; ++qd) {
+    const int o = tid + 256 * qd;
+    if (o < nout) {
+      const int row = o / d, c = o % d, i = row / Q1, a = row % Q1;
+      if (i0 + i < n1) {
+        TK v = acc[qd] + x1s[i * d + c] * rowsum[row];
+        if (a == 0) {
+#pragma unroll
+          for (int aa = 0; aa < P1; ++aa) v += u1s[(i * P1 + aa) * d + c] * rowsum[i * Q1 + 1 + aa];
+        }
+        pout[(int64_t)row * d + c] = v;
+      }
+    }
+  }
+  const double t_ell = block_sum<double, 256>(s_ell, red);
+  const double t_os = block_sum<double, 256>(s_os, red + 32);
+  if (tid == 0) {
+    const int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    part_sc[2 * b] = t_ell;
+    part_sc[2 * b + 1] = t_os;
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward (runtime p)
+// One thread per point pair, atomics into double accumulators.  Any p <= DSVGP_MAXP; not tuned.
+template <typename T, typename TK>
+__global__ void __launch_bounds__(128)
+kdir_bwd_generic(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, int p1, const T* __restrict__ x2,
+                 const TK* __restrict__ w2, int n2, int p2, int d, const double* __restrict__ hyp, int use_os,
+                 const TK* __restrict__ dK, int64_t lddk, int dk_trans, double* __restrict__ gx /*[n1][d]*/,
+                 double* __restrict__ gu /*[n1*p1][d]*/, double* __restrict__ gsc /*[2]*/) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  double s_ell = 0, s_os = 0;
+  if (j < n2 && i < n1) {
+    TK al[DSVGP_MAXP], be[DSVGP_MAXP];
+    const TK ell = (TK)hyp[0], os = use_os ? (TK)hyp[1] : TK(1), il2 = TK(1) / (ell * ell);
+    TK r2 = 0;
+    for (int a = 0; a < p1; ++a) al[a] = 0;
+    for (int b = 0; b < p2; ++b) be[b] = 0;
+    for (int c = 0; c < d; ++c) {
+      const TK dl = (TK)x1[(int64_t)i * d + c] - (TK)x2[(int64_t)j * d + c];
+      r2 += dl * dl;
+      for (int a = 0; a < p1; ++a) al[a] += dl * u1[(int64_t)(i * p1 + a) * d + c];
+      for (int b = 0; b < p2; ++b) be[b] += dl * w2[(int64_t)(j * p2 + b) * d + c];
+    }
+    for (int a = 0; a < p1; ++a) al[a] *= il2;
+    for (int b = 0; b < p2; ++b) be[b] *= il2;
+    const TK k = os * dexp<TK>(TK(-0.5) * r2 * il2);
+    auto G = [&](int a, int b) -> TK {
+      const int64_t r = (int64_t)i * (p1 + 1) + a, c = (int64_t)j * (p2 + 1) + b;
+      return dk_trans ? dK[c * lddk + r] : dK[r * lddk + c];
+    };
+    TK q = G(0, 0), sdd = 0;
+    for (int b = 0; b < p2; ++b) q += G(0, 1 + b) * be[b];
+    for (int a = 0; a < p1; ++a) q -= G(1 + a, 0) * al[a];
+    // pass 1 over (a,b): gamma-dependent terms
+    for (int a = 0; a < p1; ++a)
+      for (int b = 0; b < p2; ++b) {
+        TK g = 0;
+        for (int c = 0; c < d; ++c) g += u1[(int64_t)(i * p1 + a) * d + c] * w2[(int64_t)(j * p2 + b) * d + c];
+        g *= il2;
+        const TK gab = G(1 + a, 1 + b);
+        q += gab * (g - al[a] * be[b]);
+        sdd += k * gab * g;
+      }
+    const TK e0 = -q * k * il2;
+    for (int c = 0; c < d; ++c) {
+      const TK dl = (TK)x1[(int64_t)i * d + c] - (TK)x2[(int64_t)j * d + c];
+      TK gxc = e0 * dl;
+      for (int b = 0; b < p2; ++b) {
+        TK db = G(0, 1 + b);
+        for (int a = 0; a < p1; ++a) db -= G(1 + a, 1 + b) * al[a];
+        gxc += k * db * il2 * w2[(int64_t)(j * p2 + b) * d + c];
+      }
+      for (int a = 0; a < p1; ++a) {
+        TK da = -G(1 + a, 0);
+        TK guc = 0;
+        for (int b = 0; b < p2; ++b) {
+          da -= G(1 + a, 1 + b) * be[b];
+          guc += k * G(1 + a, 1 + b) * il2 * w2[(int64_t)(j * p2 + b) * d + c];
+        }
+        const TK ea = k * da * il2;
+        gxc += ea * u1[(int64_t)(i * p1 + a) * d + c];
+        guc += ea * dl;
+        atomicAdd(&gu[(int64_t)(i * p1 + a) * d + c], (double)guc);
+      }
+      atomicAdd(&gx[(int64_t)i * d + c], (double)gxc);
+    }
+    for (int b = 0; b < p2; ++b) {
+      TK db = G(0, 1 + b);
+      for (int a = 0; a < p1; ++a) db -= G(1 + a, 1 + b) * al[a];
+      sdd += k * db * be[b];
+    }
+    for (int a = 0; a < p1; ++a) {
+      TK da = -G(1 + a, 0);
+      for (int b = 0; b < p2; ++b) da -= G(1 + a, 1 + b) * be[b];
+      sdd += k * da * al[a];
+    }
+    s_ell = (double)(q * k * r2 * il2 / ell - TK(2) * sdd / ell);
+    s_os = (double)(q * k / os);
+  }
+  __shared__ double red[64];
+  const double t_ell = block_sum<double, 128>(s_ell, red);
+  const double t_os = block_sum<double, 128>(s_os, red + 32);
+  if (threadIdx.x == 0) {
+    atomicAdd(&gsc[0], t_ell);
+    atomicAdd(&gsc[1], t_os);
+  }
+}
+
+// One warp per output row (i,a'): sums the column-chunk partials, applies the chain rule of the row
+// normalisation (RBFKernelDirectionalGrad.py:57) for direction rows, and ACCUMULATES scale*grad into the
+// double gradient buffers gx (n1,d) / gv (n1*p1,d).
+template <typename TK>
+__global__ void kdir_bwd_reduce_rows(const TK* __restrict__ part, int nchunk, int n1, int p1, int d,
+                                     const TK* __restrict__ u1, const TK* __restrict__ inv_norm, double scale,
+                                     double* __restrict__ gx, double* __restrict__ gv) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int Q1 = p1 + 1;
+  if (row >= n1 * Q1) return;
+  const int i = row / Q1, a = row % Q1;
+  if (a == 0) {
+    if (!gx) return;
+    for (int c = lane; c < d; c += 32) {
+      double s = 0;
+      for (int ch = 0; ch < nchunk; ++ch) s += (double)part[((int64_t)ch * n1 * Q1 + row) * d + c];
+      gx[(int64_t)i * d + c] += scale * s;
+    }
+  } else {
+    if (!gv) return;
+    const int64_t vr = (int64_t)i * p1 + (a - 1);
+    double dot = 0;
+    for (int c = lane; c < d; c += 32) {
+      double s = 0;
+      for (int ch = 0; ch < nchunk; ++ch) s += (double)part[((int64_t)ch * n1 * Q1 + row) * d + c];
+      dot += s * (double)u1[vr * d + c];
+    }
+    dot = warp_sum(dot);
+    const double inv = (double)inv_norm[vr];
+    for (int c = lane; c < d; c += 32) {
+      double s = 0;
+      for (int ch = 0; ch < nchunk; ++ch) s += (double)part[((int64_t)ch * n1 * Q1 + row) * d + c];
+      gv[vr * d + c] += scale * (s - (double)u1[vr * d + c] * dot) * inv;
+    }
+  }
+}
+
+// generic path: gu holds gradients w.r.t. the NORMALISED directions; apply the chain rule into gv
+template <typename TK>
+__global__ void kdir_bwd_chain_generic(const double* __restrict__ gxt, const double* __restrict__ gut, int n1,
+                                       int p1, int d, const TK* __restrict__ u1, const TK* __restrict__ inv_norm,
+                                       double scale, double* __restrict__ gx, double* __restrict__ gv) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row < n1) {
+    if (gx)
+      for (int c = lane; c < d; c += 32) gx[(int64_t)row * d + c] += scale * gxt[(int64_t)row * d + c];
+  } else if (row < n1 + n1 * p1) {
+    if (!gv) return;
+    const int64_t vr = row - n1;
+    double dot = 0;
+    for (int c = lane; c < d; c += 32) dot += gut[vr * d + c] * (double)u1[vr * d + c];
+    dot = warp_sum(dot);
+    const double inv = (double)inv_norm[vr];
+    for (int c = lane; c < d; c += 32)
+      gv[vr * d + c] += scale * (gut[vr * d + c] - (double)u1[vr * d + c] * dot) * inv;
+  }
+}
+
+__global__ void kdir_bwd_reduce_scalars(const double* __restrict__ part_sc, int nblocks, double* __restrict__ gsc) {
+  __shared__ double red[64];
+  double a = 0, b = 0;
+  for (int e = threadIdx.x; e < nblocks; e += 256) {
+    a += part_sc[2 * e];
+    b += part_sc[2 * e + 1];
+  }
+  a = block_sum<double, 256>(a, red);
+  b = block_sum<double, 256>(b, red + 32);
+  if (threadIdx.x == 0) {
+    gsc[0] += a;
+    gsc[1] += b;
+  }
+}
+
+// ================================================================================================ host side
+template <typename T, typename TK>
+int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st) {
+  if (rows <= 0) return DSVGP_OK;
+  normalize_dirs_kernel<T, TK><<<ceil_div(rows, 8), 256, 0, st>>>(v, rows, d, vhat, inv_norm);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T, typename TK, int P1, int P2>
+static int launch_fwd_blocked(const T* x1, const TK* u1, int n1, const T* x2, const TK* w2, int n2, int d,
+                              const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st) {
+  constexpr size_t smem = fwd_smem_bytes<TK, P1, P2>();
+  auto kern = kdir_fwd_blocked<T, TK, P1, P2>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(ceil_div(n2, FWD_TJ), ceil_div(n1, FwdTile<TK>::TI));
+  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, (TK)diag_add, K, ldk);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T, typename TK>
+int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
+             const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
+  if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
+#define FWD_CASE(A, B)                                                                                         \
+  if (p1 == A && p2 == B)                                                                                      \
+    return launch_fwd_blocked<T, TK, A, B>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, diag_add, K, ldk, st);
+  FWD_CASE(0, 0) FWD_CASE(1, 1) FWD_CASE(2, 2) FWD_CASE(3, 3) FWD_CASE(1, 0) FWD_CASE(2, 0) FWD_CASE(3, 0)
+#undef FWD_CASE
+  dim3 grid(ceil_div(n2, 128), n1);
+  kdir_fwd_generic<T, TK><<<grid, 128, 0, st>>>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, (TK)diag_add, K, ldk);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename TK>
+int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t st) {
+  const int64_t tot = (int64_t)n * (p + 1);
+  if (tot <= 0) return DSVGP_OK;
+  kdir_diag_kernel<TK><<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(n, p, hyp, use_os, out);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+// workspace (bytes) the backward needs for an (n1,p1) x (n2,p2) call
+template <typename TK>
+size_t kdir_bwd_workspace(int n1, int p1, int n2, int p2, int d) {
+  const bool fast = (p1 <= DSVGP_MAXP_FAST && (p2 == p1 || p2 == 0) && BWD_TI * (p1 + 1) * d <= 256 * BWD_MAXACC);
+  if (!fast) return sizeof(double) * ((size_t)n1 * d + (size_t)n1 * p1 * d) + 256;
+  const int rt = ceil_div(n1, BWD_TI);
+  int nchunk = bwd_num_chunks(n1, n2);
+  return sizeof(TK) * (size_t)nchunk * n1 * (p1 + 1) * d + sizeof(double) * 2 * (size_t)rt * nchunk + 256;
+}
+
+int bwd_num_chunks(int n1, int n2) {
+  const int rt = ceil_div(n1, BWD_TI);
+  const int tiles = ceil_div(n2, BWD_TJ);
+  int want = ceil_div(148 * 4, rt);            // ~4 CTAs per SM across the grid
+  if (want < 1) want = 1;
+  if (want > tiles) want = tiles;
+  const int tiles_per_chunk = ceil_div(tiles, want);
+  return ceil_div(tiles, tiles_per_chunk);
+}
+
+template <typename T, typename TK, int P1, int P2>
+static int launch_bwd_blocked(const T* x1, const TK* u1, const TK* inv1, int n1, const T* x2, const TK* w2, int n2,
+                              int d, const double* hyp, int use_os, const TK* dK, int64_t lddk, int dk_trans,
+                              double scale, double* gx, double* gv, double* gsc, void* ws, cudaStream_t st) {
+  const int rt = ceil_div(n1, BWD_TI);
+  const int nchunk = bwd_num_chunks(n1, n2);
+  const int tiles = ceil_div(n2, BWD_TJ);
+  const int chunk_pts = ceil_div(tiles, nchunk) * BWD_TJ;
+  TK* part = reinterpret_cast<TK*>(ws);
+  size_t part_bytes = round_up64(sizeof(TK) * (size_t)nchunk * n1 * (P1 + 1) * d, 16);
+  double* part_sc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + part_bytes);
+  const size_t smem = bwd_smem_bytes<TK, P1, P2>(d);
+  if (smem > 227 * 1024) return DSVGP_ERR_ARG;
+  auto kern = kdir_bwd_blocked<T, TK, P1, P2>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(nchunk, rt);
+  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, dK, lddk, dk_trans, chunk_pts, part, part_sc);
+  CHECK_LAUNCH();
+  kdir_bwd_reduce_rows<TK><<<ceil_div(n1 * (P1 + 1), 8), 256, 0, st>>>(part, nchunk, n1, P1, d, u1, inv1, scale, gx, gv);
+  CHECK_LAUNCH();
+  if (gsc) {
+    kdir_bwd_reduce_scalars<<<1, 256, 0, st>>>(part_sc, rt * nchunk, gsc);
+    CHECK_LAUNCH();
+  }
+  return DSVGP_OK;
+}
+
+// Accumulates  scale * dL/dx1 into gx (n1,d),  scale * dL/dv1 into gv (n1*p1,d)  (either may be null) and the
+// UNSCALED dL/d ell, dL/d outputscale into gsc[0], gsc[1] (may be null).  All three are double buffers.
+template <typename T, typename TK>
+int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2,
+             int d, const double* hyp, int use_os, const TK* dK, int64_t lddk, int dk_trans, double scale,
+             double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
+  if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
+  if (ws_bytes < kdir_bwd_workspace<TK>(n1, p1, n2, p2, d)) return DSVGP_ERR_WORKSPACE;
+  const bool fast = (p1 <= DSVGP_MAXP_FAST && (p2 == p1 || p2 == 0) && BWD_TI * (p1 + 1) * d <= 256 * BWD_MAXACC);
+  if (fast) {
+#define BWD_CASE(A, B)                                                                                         \
+  if (p1 == A && p2 == B)                                                                                      \
+    return launch_bwd_blocked<T, TK, A, B>(x1, u1, inv1, n1, x2, w2, n2, d, hyp, use_os, dK, lddk, dk_trans,  \
+                                           scale, gx, gv, gsc, ws, st);
+    BWD_CASE(0, 0) BWD_CASE(1, 1) BWD_CASE(2, 2) BWD_CASE(3, 3) BWD_CASE(1, 0) BWD_CASE(2, 0) BWD_CASE(3, 0)
+#undef BWD_CASE
+  }
+  double* gxt = reinterpret_cast<double*>(ws);
+  double* gut = gxt + (size_t)n1 * d;
+  cudaMemsetAsync(ws, 0, sizeof(double) * ((size_t)n1 * d + (size_t)n1 * p1 * d + 2), st);
+  double* gsc_t = gsc ? gsc : gut + (size_t)n1 * p1 * d;   // scalars accumulate directly (or into scratch)
+  dim3 grid(ceil_div(n2, 128), n1);
+  kdir_bwd_generic<T, TK><<<grid, 128, 0, st>>>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, dK, lddk, dk_trans,
+                                                gxt, gut, gsc_t);
+  CHECK_LAUNCH();
+  kdir_bwd_chain_generic<TK><<<ceil_div(n1 * (p1 + 1), 8), 256, 0, st>>>(gxt, gut, n1, p1, d, u1, inv1, scale, gx, gv);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+// explicit instantiations: (T, TK) in {(f32,f32), (f64,f64), (f32,f64)}
+#define INST(T, TK)                                                                                             \
+  template int normalize_dirs<T, TK>(const T*, int, int, TK*, TK*, cudaStream_t);                               \
+  template int kdir_fwd<T, TK>(const T*, const TK*, int, int, const T*, const TK*, int, int, int, const double*, \
+                               int, double, TK*, int64_t, cudaStream_t);                                        \
+  template int kdir_bwd<T, TK>(const T*, const TK*, const TK*, int, int, const T*, const TK*, int, int, int,    \
+                               const double*, int, const TK*, int64_t, int, double, double*, double*, double*,  \
+                               void*, size_t, cudaStream_t);
+INST(float, float)
+INST(double, double)
+INST(float, double)
+#undef INST
+template int kdir_diag<float>(int, int, const double*, int, float*, cudaStream_t);
+template int kdir_diag<double>(int, int, const double*, int, double*, cudaStream_t);
+template size_t kdir_bwd_workspace<float>(int, int, int, int, int);
+template size_t kdir_bwd_workspace<double>(int, int, int, int, int);
+
+}  // namespace dsvgp

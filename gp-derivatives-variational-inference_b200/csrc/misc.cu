@@ -1,0 +1,491 @@
+// Small fused elementwise / reduction kernels around the whitening products:
+// positivity transforms, predictive mean / diagonal variance, Gaussian expected log-likelihood, KL, and the
+// pieces of their backward that are not GEMMs.  All HBM-bound; warp-shuffle + shared-memory reductions, partial
+// sums written per CTA and summed by a second tiny kernel (deterministic, no float atomics).
+//
+// Reference semantics (file:line are under /root/reference/directionalvi unless noted; [GPT] = gpytorch 1.4.0):
+//   mean     = A^T m + c on every output incl. derivative outputs   DirectionalGradVariationalStrategy.py:126,188
+//   variance = diag(K_xx) + 1e-4 + diag(A^T (S - I) A)              :192-205, via MatmulLazyTensor.diag [GPT]
+//   likelihood(dist) adds sigma^2, sigma^2 = softplus(raw)+1e-4     [GPT] GaussianLikelihood
+//   expected_log_prob = -0.5*(((y-mu)^2 + var)/sigma^2 + log sigma^2 + log 2pi)   [GPT]
+//   KL(q||N(0,I)) = 0.5*(|tril(Ls)|_F^2 + m.m - M' - sum log Ls_ii^2)             [GPT]
+#include "common.cuh"
+#include "misc.cuh"
+
+namespace dsvgp {
+
+// hyp = {ell, os, noise, c, sigmoid(raw_ell), sigmoid(raw_os), sigmoid(raw_noise), 0}
+template <typename T>
+__global__ void hyp_from_raw_kernel(const T* raw_ell, const T* raw_os, const T* raw_noise, const T* c, double* hyp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double re = (double)raw_ell[0];
+  hyp[0] = softplus_d(re);
+  hyp[4] = sigmoid_d(re);
+  const double ro = raw_os ? (double)raw_os[0] : 0.0;
+  hyp[1] = raw_os ? softplus_d(ro) : 1.0;
+  hyp[5] = raw_os ? sigmoid_d(ro) : 0.0;
+  const double rn = raw_noise ? (double)raw_noise[0] : 0.0;
+  hyp[2] = raw_noise ? softplus_d(rn) + 1e-4 : 0.0;
+  hyp[6] = raw_noise ? sigmoid_d(rn) : 0.0;
+  hyp[3] = c ? (double)c[0] : 0.0;
+  hyp[7] = 0.0;
+}
+
+__global__ void pad_identity_kernel(double* A, int64_t ld, int Mq, int Mp) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int i = (int)(e / Mp), j = (int)(e % Mp);
+  if (i >= Mq || j >= Mq) A[(int64_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+}
+
+template <typename S, typename D>
+__global__ void cast2d_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int rows,
+                              int cols, int tril) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= cols || i >= rows) return;
+  dst[(int64_t)i * ldd + j] = (tril && j > i) ? D(0) : (D)src[(int64_t)i * lds + j];
+}
+
+// fill the strictly-upper triangle from the lower one
+template <typename T>
+__global__ void mirror_lower_kernel(T* A, int64_t ld, int n) {
+  __shared__ T tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? A[(int64_t)i * ld + j] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;      // transposed block position
+    if (i < n && j < n && j > i) A[(int64_t)i * ld + j] = tile[tx][r];
+  }
+}
+
+template <typename T>
+__global__ void add_outer_kernel(T* A, int64_t ld, int n, const T* __restrict__ u, const T* __restrict__ v, T alpha) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n || i >= n) return;
+  A[(int64_t)i * ld + j] += alpha * u[i] * v[j];
+}
+
+// Psi = 0.5*(Phi + Phi^T), Phi = tril(Y) with halved diagonal  (symmetrised Cholesky-backward middle factor)
+__global__ void sym_phi_kernel(const double* __restrict__ Y, int64_t ldy, double* __restrict__ P, int64_t ldp, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n || i >= n) return;
+  const int a = max(i, j), b = min(i, j);
+  P[(int64_t)i * ldp + j] = 0.5 * Y[(int64_t)a * ldy + b];
+}
+
+// --------------------------------------------------------------------------------- predictive mean / variance
+// partial column sums over a slab of rows:  pm[s][j] = sum_i A_ij m_i ,  pv[s][j] = sum_i A_ij C_ij
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_dots_kernel(const T* __restrict__ A, const T* __restrict__ C, int64_t ld, int rows, int nq,
+                const T* __restrict__ m, int rows_per_slab, T* __restrict__ pm, T* __restrict__ pv) {
+  __shared__ T sm[4][64], sv[4][64];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + cl;
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
+  T am = 0, av = 0;
+  if (j < nq) {
+    int i = r0 + rl;
+    for (; i + 12 < r1; i += 16) {
+      T a[4], c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = A[(int64_t)(i + 4 * q) * ld + j];
+        c[q] = C ? C[(int64_t)(i + 4 * q) * ld + j] : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        am += a[q] * m[i + 4 * q];
+        av += a[q] * c[q];
+      }
+    }
+    for (; i < r1; i += 4) {
+      const T a = A[(int64_t)i * ld + j];
+      am += a * m[i];
+      if (C) av += a * C[(int64_t)i * ld + j];
+    }
+  }
+  sm[rl][cl] = am;
+  sv[rl][cl] = av;
+  __syncthreads();
+  if (rl == 0 && j < nq) {
+    pm[(int64_t)blockIdx.y * nq + j] = sm[0][cl] + sm[1][cl] + sm[2][cl] + sm[3][cl];
+    pv[(int64_t)blockIdx.y * nq + j] = sv[0][cl] + sv[1][cl] + sv[2][cl] + sv[3][cl];
+  }
+}
+
+// partial column sums  pq[s][j] = sum_i (B_ij^2 - A_ij^2)  (prediction path: no backward, so C is never formed)
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_sqdiff_kernel(const T* __restrict__ A, const T* __restrict__ B, int64_t ld, int rows, int nq,
+                  const T* __restrict__ m, int rows_per_slab, T* __restrict__ pm, T* __restrict__ pv) {
+  __shared__ T sm[4][64], sv[4][64];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + cl;
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
+  T am = 0, av = 0;
+  if (j < nq) {
+    for (int i = r0 + rl; i < r1; i += 4) {
+      const T a = A[(int64_t)i * ld + j], b = B[(int64_t)i * ld + j];
+      am += a * m[i];
+      av += (b - a) * (b + a);
+    }
+  }
+  sm[rl][cl] = am;
+  sv[rl][cl] = av;
+  __syncthreads();
+  if (rl == 0 && j < nq) {
+    pm[(int64_t)blockIdx.y * nq + j] = sm[0][cl] + sm[1][cl] + sm[2][cl] + sm[3][cl];
+    pv[(int64_t)blockIdx.y * nq + j] = sv[0][cl] + sv[1][cl] + sv[2][cl] + sv[3][cl];
+  }
+}
+
+template <typename T>
+__global__ void predict_finish_kernel(const T* __restrict__ pm, const T* __restrict__ pv, int nslab, int nq, int p2,
+                                      const double* __restrict__ hyp, double pred_jitter, int add_noise,
+                                      double min_var, T* __restrict__ mu, T* __restrict__ var) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nq) return;
+  double sm = 0, sv = 0;
+  for (int s = 0; s < nslab; ++s) {
+    sm += (double)pm[(int64_t)s * nq + j];
+    sv += (double)pv[(int64_t)s * nq + j];
+  }
+  const double ell = hyp[0], os = hyp[1];
+  const double kd = (j % (p2 + 1)) == 0 ? os : os / (ell * ell);
+  double v = kd + pred_jitter + sv + (add_noise ? hyp[2] : 0.0);
+  if (v < min_var) v = min_var;
+  mu[j] = (T)(sm + hyp[3]);
+  var[j] = (T)v;
+}
+
+// ------------------------------------------------------------------------------------------ ELBO data term
+// sc_part[b] = {sum_j term_j * w, explicit d/dsigma^2}, gmu_j = dELBO/dmu_j, gvar_j = dELBO/dvar_j
+template <typename T>
+__global__ void __launch_bounds__(256)
+elbo_terms_kernel(const T* __restrict__ mu, const T* __restrict__ var, const T* __restrict__ y, int nq,
+                  const double* __restrict__ hyp, double w, double min_var, T* __restrict__ gmu,
+                  T* __restrict__ gvar, double* __restrict__ sc_part) {
+  __shared__ double red[64];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const double s2 = hyp[2];
+  double term = 0, ds2 = 0;
+  if (j < nq) {
+    const double r = (double)y[j] - (double)mu[j], v = (double)var[j];
+    const double quad = r * r + v;
+    term = -0.5 * (quad / s2 + log(s2) + 1.8378770664093453) * w;
+    ds2 = 0.5 * (quad / (s2 * s2) - 1.0 / s2) * w;
+    gmu[j] = (T)(w * r / s2);
+    gvar[j] = (T)((v > min_var) ? -0.5 * w / s2 : 0.0);
+  }
+  const double a = block_sum<double, 256>(term, red);
+  const double b = block_sum<double, 256>(ds2, red + 32);
+  if (threadIdx.x == 0) {
+    sc_part[2 * blockIdx.x] = a;
+    sc_part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// out[k] += sum_b part[b*stride + k], k < width   (one CTA)
+__global__ void sum_scalar_parts_kernel(const double* __restrict__ part, int nparts, int stride, int width,
+                                        double* __restrict__ out) {
+  __shared__ double red[32];
+  for (int k = 0; k < width; ++k) {
+    double s = 0;
+    for (int b = threadIdx.x; b < nparts; b += 256) s += part[(int64_t)b * stride + k];
+    s = block_sum<double, 256>(s, red);
+    if (threadIdx.x == 0) out[k] += s;
+    __syncthreads();
+  }
+}
+
+// gsc += {d ell, d os, d sigma^2, d c} contributions that flow through mean (+c) and the K_xx diagonal
+template <typename T>
+__global__ void __launch_bounds__(256)
+pred_bwd_scalars_kernel(const T* __restrict__ gmu, const T* __restrict__ gvar, int nq, int p2,
+                        const double* __restrict__ hyp, int add_noise, double* __restrict__ part) {
+  __shared__ double red[32];
+  const double ell = hyp[0], os = hyp[1];
+  double d_ell = 0, d_os = 0, d_s2 = 0, d_c = 0;
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < nq; j += gridDim.x * 256) {
+    const double gv = (double)gvar[j];
+    const bool val = (j % (p2 + 1)) == 0;
+    d_os += gv * (val ? 1.0 : 1.0 / (ell * ell));
+    d_ell += val ? 0.0 : gv * (-2.0 * os / (ell * ell * ell));
+    d_s2 += add_noise ? gv : 0.0;
+    d_c += (double)gmu[j];
+  }
+  double v[4] = {d_ell, d_os, d_s2, d_c};
+  for (int k = 0; k < 4; ++k) {
+    const double s = block_sum<double, 256>(v[k], red);
+    if (threadIdx.x == 0) part[4 * blockIdx.x + k] = s;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ backward through mean / variance
+// In place  C_ij <- m_i*gmu_j + 2*gvar_j*C_ij  (= dELBO/dA),  Ag_ij <- A_ij*gvar_j  (left factor of the weighted
+// SYRK G = A diag(gvar) A^T),  tp[s][i] = sum_{j in slab s} A_ij*gmu_j  (= dELBO/dm and the rank-one part of dL).
+template <typename T>
+__global__ void __launch_bounds__(256)
+dA_kernel(const T* __restrict__ A, T* __restrict__ C, T* __restrict__ Ag, int64_t ld, int rows, int nq,
+          const T* __restrict__ m, const T* __restrict__ gmu, const T* __restrict__ gvar, int cols_per_slab,
+          T* __restrict__ tp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= rows) return;
+  const int c0 = blockIdx.y * cols_per_slab, c1 = min(nq, c0 + cols_per_slab);
+  const T mi = m[i];
+  T t = 0;
+  for (int j = c0 + lane; j < c1; j += 32) {
+    const int64_t o = (int64_t)i * ld + j;
+    const T a = A[o], gm = gmu[j], gv = gvar[j];
+    t += a * gm;
+    C[o] = mi * gm + T(2) * gv * C[o];
+    if (Ag) Ag[o] = a * gv;
+  }
+  t = warp_sum(t);
+  if (lane == 0) tp[(int64_t)blockIdx.y * rows + i] = t;
+}
+
+template <typename T>
+__global__ void sum_parts_kernel(const T* __restrict__ part, int nparts, int len, T* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0;
+  for (int b = 0; b < nparts; ++b) s += (double)part[(int64_t)b * len + i];
+  out[i] = (T)s;
+}
+
+// ------------------------------------------------------------------------------------------------------ KL
+template <typename T>
+__global__ void __launch_bounds__(256)
+kl_kernel(const T* __restrict__ m, const T* __restrict__ Ls, int64_t ld, int Mq, double* __restrict__ part) {
+  __shared__ double red[32];
+  double s = 0;
+  const int64_t tot = (int64_t)Mq * Mq;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < tot; e += (int64_t)gridDim.x * 256) {
+    const int i = (int)(e / Mq), j = (int)(e % Mq);
+    if (j <= i) {
+      const double v = (double)Ls[(int64_t)i * ld + j];
+      s += 0.5 * v * v;
+      if (i == j) s += 0.5 * ((double)m[i] * (double)m[i] - 1.0 - log(v * v));
+    }
+  }
+  s = block_sum<double, 256>(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// gm_i = t_i - m_i/num_data ;  gLs_ij = 2*H[j][i] - (Ls_ij - [i==j]/Ls_ii)/num_data for j <= i, 0 above
+template <typename T>
+__global__ void var_grads_kernel(const T* __restrict__ H, int64_t ldh, const T* __restrict__ Ls, int64_t ldl,
+                                 const T* __restrict__ t, const T* __restrict__ m, int Mq, double inv_nd,
+                                 T* __restrict__ gm, T* __restrict__ gLs, int64_t ldg) {
+  __shared__ T tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x, tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  // tile of H^T: rows bi*32.., cols bj*32..  = H[bj*32 + c][bi*32 + r]
+  for (int r = ty; r < 32; r += 8) {
+    const int hi = bj * 32 + r, hj = bi * 32 + tx;
+    tile[r][tx] = (hi < Mq && hj < Mq) ? H[(int64_t)hi * ldh + hj] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < Mq && j < Mq) {
+      T g = 0;
+      if (j <= i) {
+        double gg = 2.0 * (double)tile[tx][r];
+        if (inv_nd != 0.0) {
+          const double l = (double)Ls[(int64_t)i * ldl + j];
+          gg -= inv_nd * (l - (i == j ? 1.0 / l : 0.0));
+        }
+        g = (T)gg;
+      }
+      gLs[(int64_t)i * ldg + j] = g;
+    }
+  }
+  if (bj == 0 && ty == 0) {
+    const int i = bi * 32 + tx;
+    if (i < Mq) gm[i] = (T)((double)t[i] - inv_nd * (double)m[i]);
+  }
+}
+
+// ================================================================================================ host side
+template <typename T>
+int hyp_from_raw(const T* raw_ell, const T* raw_os, const T* raw_noise, const T* c, double* hyp, cudaStream_t st) {
+  if (!raw_ell || !hyp) return DSVGP_ERR_ARG;
+  hyp_from_raw_kernel<T><<<1, 32, 0, st>>>(raw_ell, raw_os, raw_noise, c, hyp);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int pad_identity(double* A, int64_t ld, int Mq, int Mp, cudaStream_t st) {
+  if (Mp <= Mq) return DSVGP_OK;
+  pad_identity_kernel<<<(unsigned)ceil_div64((int64_t)Mp * Mp, 256), 256, 0, st>>>(A, ld, Mq, Mp);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename S, typename D>
+int cast2d(const S* src, int64_t lds, D* dst, int64_t ldd, int rows, int cols, int tril, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(cols, 256), rows);
+  cast2d_kernel<S, D><<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols, tril);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T>
+int mirror_lower(T* A, int64_t ld, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 32), ceil_div(n, 32)), block(32, 8);
+  mirror_lower_kernel<T><<<grid, block, 0, st>>>(A, ld, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T>
+int add_outer(T* A, int64_t ld, int n, const T* u, const T* v, double alpha, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 256), n);
+  add_outer_kernel<T><<<grid, 256, 0, st>>>(A, ld, n, u, v, (T)alpha);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 256), n);
+  sym_phi_kernel<<<grid, 256, 0, st>>>(Y, ldy, P, ldp, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int reduce_slabs(int rows, int cols) {
+  // enough row slabs that (column blocks x slabs) covers ~4 CTAs per SM
+  const int cb = ceil_div(cols, 64);
+  int s = ceil_div(148 * 4, cb);
+  if (s < 1) s = 1;
+  const int maxs = ceil_div(rows, 64);
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+template <typename T>
+int col_dots(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm, T* pv, int nslab,
+             cudaStream_t st) {
+  if (rows <= 0 || nq <= 0) return DSVGP_OK;
+  if (nslab < 1) return DSVGP_ERR_ARG;
+  const int rps = ceil_div(rows, nslab);
+  dim3 grid(ceil_div(nq, 64), nslab);
+  if (B) col_sqdiff_kernel<T><<<grid, 256, 0, st>>>(A, B, ld, rows, nq, m, rps, pm, pv);
+  else col_dots_kernel<T><<<grid, 256, 0, st>>>(A, C, ld, rows, nq, m, rps, pm, pv);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T>
+int predict_finish(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter,
+                   int add_noise, double min_var, T* mu, T* var, cudaStream_t st) {
+  if (nq <= 0) return DSVGP_OK;
+  predict_finish_kernel<T><<<ceil_div(nq, 256), 256, 0, st>>>(pm, pv, nslab, nq, p2, hyp, pred_jitter, add_noise,
+                                                              min_var, mu, var);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+// sc[0] += data term, sc[1] += explicit dELBO/dsigma^2 ; ws: 2*ceil(nq/256) doubles
+template <typename T>
+int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp, double w, double min_var, T* gmu,
+               T* gvar, double* sc, double* ws, cudaStream_t st) {
+  if (nq <= 0) return DSVGP_OK;
+  const int nb = ceil_div(nq, 256);
+  elbo_terms_kernel<T><<<nb, 256, 0, st>>>(mu, var, y, nq, hyp, w, min_var, gmu, gvar, ws);
+  CHECK_LAUNCH();
+  sum_scalar_parts_kernel<<<1, 256, 0, st>>>(ws, nb, 2, 2, sc);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+// gsc[0..3] += {d ell, d os, d sigma^2, d c} ; ws: 4*blocks doubles (blocks <= 296)
+template <typename T>
+int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc,
+                     double* ws, cudaStream_t st) {
+  if (nq <= 0) return DSVGP_OK;
+  int nb = ceil_div(nq, 256);
+  if (nb > 296) nb = 296;
+  pred_bwd_scalars_kernel<T><<<nb, 256, 0, st>>>(gmu, gvar, nq, p2, hyp, add_noise, ws);
+  CHECK_LAUNCH();
+  sum_scalar_parts_kernel<<<1, 256, 0, st>>>(ws, nb, 4, 4, gsc);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T>
+int dA_apply(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu, const T* gvar, T* tp,
+             int nslab, T* t, cudaStream_t st) {
+  if (rows <= 0 || nq <= 0) return DSVGP_OK;
+  const int cps = ceil_div(ceil_div(nq, nslab), 32) * 32;
+  const int ns = ceil_div(nq, cps);
+  dim3 grid(ceil_div(rows, 8), ns);
+  dA_kernel<T><<<grid, 256, 0, st>>>(A, C, Ag, ld, rows, nq, m, gmu, gvar, cps, tp);
+  CHECK_LAUNCH();
+  sum_parts_kernel<T><<<ceil_div(rows, 256), 256, 0, st>>>(tp, ns, rows, t);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+// out[0] += KL ; ws: 296 doubles
+template <typename T>
+int kl_divergence(const T* m, const T* Ls, int64_t ld, int Mq, double* out, double* ws, cudaStream_t st) {
+  if (Mq <= 0) return DSVGP_OK;
+  int nb = (int)ceil_div64((int64_t)Mq * Mq, 256 * 8);
+  if (nb > 296) nb = 296;
+  kl_kernel<T><<<nb, 256, 0, st>>>(m, Ls, ld, Mq, ws);
+  CHECK_LAUNCH();
+  sum_scalar_parts_kernel<<<1, 256, 0, st>>>(ws, nb, 1, 1, out);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename T>
+int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, const T* m, int Mq, double inv_nd, T* gm,
+              T* gLs, int64_t ldg, cudaStream_t st) {
+  if (Mq <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(Mq, 32), ceil_div(Mq, 32)), block(32, 8);
+  var_grads_kernel<T><<<grid, block, 0, st>>>(H, ldh, Ls, ldl, t, m, Mq, inv_nd, gm, gLs, ldg);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+#define INST(T)                                                                                                    \
+  template int hyp_from_raw<T>(const T*, const T*, const T*, const T*, double*, cudaStream_t);                     \
+  template int mirror_lower<T>(T*, int64_t, int, cudaStream_t);                                                    \
+  template int add_outer<T>(T*, int64_t, int, const T*, const T*, double, cudaStream_t);                           \
+  template int col_dots<T>(const T*, const T*, const T*, int64_t, int, int, const T*, T*, T*, int, cudaStream_t);  \
+  template int predict_finish<T>(const T*, const T*, int, int, int, const double*, double, int, double, T*, T*,    \
+                                 cudaStream_t);                                                                    \
+  template int elbo_terms<T>(const T*, const T*, const T*, int, const double*, double, double, T*, T*, double*,    \
+                             double*, cudaStream_t);                                                               \
+  template int pred_bwd_scalars<T>(const T*, const T*, int, int, const double*, int, double*, double*,             \
+                                   cudaStream_t);                                                                  \
+  template int dA_apply<T>(const T*, T*, T*, int64_t, int, int, const T*, const T*, const T*, T*, int, T*,         \
+                           cudaStream_t);                                                                          \
+  template int kl_divergence<T>(const T*, const T*, int64_t, int, double*, double*, cudaStream_t);                 \
+  template int var_grads<T>(const T*, int64_t, const T*, int64_t, const T*, const T*, int, double, T*, T*,         \
+                            int64_t, cudaStream_t);
+INST(float)
+INST(double)
+#undef INST
+template int cast2d<double, float>(const double*, int64_t, float*, int64_t, int, int, int, cudaStream_t);
+template int cast2d<float, double>(const float*, int64_t, double*, int64_t, int, int, int, cudaStream_t);
+template int cast2d<double, double>(const double*, int64_t, double*, int64_t, int, int, int, cudaStream_t);
+template int cast2d<float, float>(const float*, int64_t, float*, int64_t, int, int, int, cudaStream_t);
+
+}  // namespace dsvgp

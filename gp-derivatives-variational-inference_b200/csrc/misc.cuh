@@ -1,0 +1,37 @@
+// Elementwise / reduction kernels (definitions in misc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dsvgp {
+
+template <typename T>
+int hyp_from_raw(const T* raw_ell, const T* raw_os, const T* raw_noise, const T* c, double* hyp, cudaStream_t st);
+int pad_identity(double* A, int64_t ld, int Mq, int Mp, cudaStream_t st);
+template <typename S, typename D>
+int cast2d(const S* src, int64_t lds, D* dst, int64_t ldd, int rows, int cols, int tril, cudaStream_t st);
+template <typename T> int mirror_lower(T* A, int64_t ld, int n, cudaStream_t st);
+template <typename T> int add_outer(T* A, int64_t ld, int n, const T* u, const T* v, double alpha, cudaStream_t st);
+int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st);
+int reduce_slabs(int rows, int cols);
+template <typename T>
+int col_dots(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm, T* pv, int nslab,
+             cudaStream_t st);
+template <typename T>
+int predict_finish(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter,
+                   int add_noise, double min_var, T* mu, T* var, cudaStream_t st);
+template <typename T>
+int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp, double w, double min_var, T* gmu,
+               T* gvar, double* sc, double* ws, cudaStream_t st);
+template <typename T>
+int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc,
+                     double* ws, cudaStream_t st);
+template <typename T>
+int dA_apply(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu, const T* gvar, T* tp,
+             int nslab, T* t, cudaStream_t st);
+template <typename T>
+int kl_divergence(const T* m, const T* Ls, int64_t ld, int Mq, double* out, double* ws, cudaStream_t st);
+template <typename T>
+int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, const T* m, int Mq, double inv_nd, T* gm,
+              T* gLs, int64_t ldg, cudaStream_t st);
+
+}  // namespace dsvgp

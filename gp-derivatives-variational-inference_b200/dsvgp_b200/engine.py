@@ -1,0 +1,288 @@
+"""The DSVGP minibatch step on one GPU: kernel launches in the order the data flows, no host synchronisation
+except the single Cholesky-status read at the end of a step.
+
+What the reference does per step (DirectionalGradVariationalStrategy.forward, DGVS.py:89-208, plus the gpytorch
+likelihood / ELBO / KL and their autograd backward) and what happens here instead:
+
+  reference                                         here (all on torch's current stream)
+  ------------------------------------------------  ---------------------------------------------------------
+  K_zx, K_xz, K_zz, full K_xx (4 kernel calls)      K_zz (fp64) and K_zx only; K_xx diagonal in closed form
+  psd_safe_cholesky(K_zz.double())                  blocked fp64 Cholesky + explicit W = L^-1
+  two fp64 triangular solves                        one triangular product A = W K_zx (tensor cores)
+  (S - I) A through two dense L_s products          B = L_s^T A, C = L_s B - A (triangular products)
+  mean, diag via MatmulLazyTensor.diag              column reductions of A.m and A*C
+  likelihood + ELBO + KL elementwise ops            one fused kernel each
+  autograd through everything (fp64 Cholesky bwd)   hand-derived backward: dA in place, dK_zx = W^T dA,
+                                                    G = A diag(g) A^T, and a replicated M'^3 fp64 tail
+                                                    (dL, Phi, W^T Psi W) feeding the assembly backward
+
+Multi-GPU (distributed.py): everything up to and including G is local to a minibatch shard; `reduce_hook` is
+called once with the two buffers that have to be summed over ranks before the replicated tail runs.
+"""
+import torch
+
+from . import ops
+from .ops import F32, F64, TRI_LOWER, TRI_UPPER
+
+KZZ_JITTER = 1e-3          # add_jitter() default            DGVS.py:144
+PRED_JITTER = 1e-4         # data_data_covar.add_jitter(1e-4) DGVS.py:198,203
+CHOL_RETRY = (1e-6, 1e-5, 1e-4)   # psd_safe_cholesky(jitter=1e-6): 1e-6 * 10**i, i < 3   DGVS.py:74
+
+
+class NanError(RuntimeError):
+    """gpytorch.utils.errors.NanError equivalent."""
+
+
+class NotPSDError(RuntimeError):
+    """gpytorch.utils.errors.NotPSDError equivalent."""
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class Factor:
+    """Everything that depends on the parameters only (not on the minibatch): transformed hyper-parameters,
+    normalised inducing directions, the fp64 Cholesky factor L of K_zz + jitter*I and W = L^-1.
+    Recomputed every training step, memoised across batches in eval mode (DGVS.py:72 `@cached`)."""
+
+    def __init__(self, device, dtype, d, M, p):
+        self.key = (str(device), dtype, d, M, p)
+        self.d, self.M, self.p = d, M, p
+        self.Mq = M * (p + 1)
+        self.Mp, self.nb0, self.nlev = ops.chol_plan(self.Mq)
+        e = lambda *s, dt=F64: torch.empty(*s, dtype=dt, device=device)
+        self.hyp = e(8)
+        self.info = torch.zeros(1, dtype=torch.int32, device=device)
+        self.Kzz, self.L, self.W = e(self.Mp, self.Mp), e(self.Mp, self.Mp), e(self.Mp, self.Mp)
+        self.Wt = e(self.Mq, self.Mq, dt=dtype) if dtype == F32 else self.W      # W in the model dtype
+        self.uzT = self.invzT = self.uz64 = self.invz64 = None
+        self.valid = False
+
+
+class Workspace:
+    """Every minibatch-sized buffer one (dtype, n, d, M, p, p2) problem needs, allocated once, reused per step."""
+
+    def __init__(self, device, dtype, n, d, M, p, p2):
+        T = dtype
+        self.n, self.d, self.M, self.p, self.p2 = n, d, M, p, p2
+        self.Mq, self.nq = M * (p + 1), n * (p2 + 1)
+        Mq, nq = self.Mq, self.nq
+        self.ldn = _round_up(max(nq, 1), 8)
+        e = lambda *s, dt=T: torch.empty(*s, dtype=dt, device=device)
+        self.Kzx, self.A, self.B, self.C = (e(Mq, self.ldn) for _ in range(4))
+        self.nslab = max(1, ops.reduce_slabs(Mq, nq))
+        self.pm, self.pv = e(self.nslab, nq), e(self.nslab, nq)
+        self.mu, self.var, self.gmu, self.gvar = e(nq), e(nq), e(nq), e(nq)
+        self.tp = e(max(1, min(64, nq // 2048)), Mq)
+        # [G | t] (model dtype) and [scalars(8) | gZ | gVz] (double) are the two buffers summed over ranks.
+        # scalars: 0 data term, 1 explicit dELBO/dnoise, 4 d ell, 5 d outputscale, 6 d noise via variance, 7 d c
+        self.big = e(Mq * Mq + Mq)
+        self.G, self.t = self.big[: Mq * Mq].view(Mq, Mq), self.big[Mq * Mq:]
+        self.small = torch.zeros(8 + M * d + M * p * d, dtype=F64, device=device)
+        self.sc = self.small[:8]
+        self.gZ = self.small[8: 8 + M * d].view(M, d)
+        self.gVz = self.small[8 + M * d:].view(M * p, d) if p else None
+        self.kl = torch.zeros(1, dtype=F64, device=device)
+        self.scratch = e(8192, dt=F64)
+        self.H, self.X = e(Mq, Mq), e(Mq, Mq)
+        self.Xd = e(Mq, Mq, dt=F64) if T == F32 else self.X
+        self.dL, self.Y, self.Psi, self.S = (e(Mq, Mq, dt=F64) for _ in range(4))
+        self.gm, self.gLs = e(Mq), e(Mq, Mq)
+        self.wx = None
+
+
+class Engine:
+    def __init__(self):
+        self._ws, self._fac = {}, {}
+        self.reduce_hook = None     # callable(big_or_None, small) summing the buffers over ranks, or None
+
+    def workspace(self, device, dtype, n, d, M, p, p2):
+        key = (str(device), dtype, n, d, M, p, p2)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 3:          # eval batches of many sizes: do not hoard HBM
+                self._ws.clear()
+            ws = self._ws[key] = Workspace(device, dtype, n, d, M, p, p2)
+        return ws
+
+    def factor(self, device, dtype, d, M, p):
+        key = (str(device), dtype, d, M, p)
+        f = self._fac.get(key)
+        if f is None:
+            if len(self._fac) > 3:
+                self._fac.clear()
+            f = self._fac[key] = Factor(device, dtype, d, M, p)
+        return f
+
+    # ------------------------------------------------------------------------------------------ factorisation
+    @staticmethod
+    def _factorise(f, P, T, extra_jitter):
+        """hyper-parameter transforms, direction normalisation, K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+        ops.hyp_from_raw(P.raw_ell.reshape(-1), P.raw_os.reshape(-1),
+                         None if P.raw_noise is None else P.raw_noise.reshape(-1), P.c.reshape(-1), out=f.hyp)
+        if f.p:
+            f.uzT, f.invzT = ops.normalize_dirs(P.Vz, T)
+            f.uz64, f.invz64 = (f.uzT, f.invzT) if T == F64 else ops.normalize_dirs(P.Vz, F64)
+        if f.Mp > f.Mq:
+            ops.pad_identity(f.Kzz, f.Mq)
+        ops.kdir_fwd(P.Z, f.uz64, f.p, P.Z, f.uz64, f.p, f.hyp, f.Kzz, diag_add=KZZ_JITTER + extra_jitter)
+        ops.cholesky_inverse(f.Kzz, f.L, f.W, f.nb0, f.nlev, f.info)
+        if T == F32:
+            ops.cast2d(f.W, f.Wt, f.Mq, f.Mq, tril=True)
+
+    @staticmethod
+    def _check(f, P):
+        info = int(f.info.item())          # the one host sync of a step
+        if info == 0:
+            return True
+        for name in ("Z", "Vz", "raw_ell", "raw_os"):
+            t = getattr(P, name, None)
+            if t is not None and not bool(torch.isfinite(t).all()):
+                raise NanError(f"NaN/inf in `{name}` reached the Cholesky factorisation of K_zz")
+        return False
+
+    # ------------------------------------------------------------------------------------------------ forward
+    @staticmethod
+    def _forward(ws, f, P, x, wx, add_noise, need_C):
+        Mq, nq = ws.Mq, ws.nq
+        Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
+        ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx)
+        ops.gemm(f.Wt, Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)                        # A = L^-1 K_zx
+        ops.gemm(P.Ls_raw, A, B, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)             # B = L_s^T A
+        if need_C:
+            ops.gemm(P.Ls_raw, B, C, a_tri=TRI_LOWER, beta=-1.0, D=A, M=Mq, N=nq, K=Mq)  # C = (S - I) A
+            ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C)
+        else:
+            ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, B=B)                              # sum_i B^2 - A^2
+        ops.predict_finish(ws.pm, ws.pv, nq, ws.p2, f.hyp, ws.mu, ws.var, add_noise, PRED_JITTER)
+
+    # ----------------------------------------------------------------------------------------------- backward
+    def _backward(self, ws, f, P, x, wx, gmu, gvar, add_noise, inv_num_data):
+        """Gradients of a scalar whose derivatives w.r.t. (mean, variance) are (gmu, gvar), plus the KL gradient
+        scaled by -inv_num_data.  Results: ws.gm, ws.gLs (model dtype), ws.small (double)."""
+        T, Mq, nq = x.dtype, ws.Mq, ws.nq
+        A, Ag, C, dKzx = ws.A, ws.B, ws.C, ws.Kzx
+        ops.pred_bwd_scalars(gmu, gvar, ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)
+        ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t)                      # C <- dA ; Ag ; t = A gmu
+        ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)              # dK_zx = L^-T dA
+        ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
+        ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)                        # G = A diag(gvar) A^T
+        ops.mirror_lower(ws.G, Mq)
+        if self.reduce_hook is not None:
+            self.reduce_hook(ws.big, ws.small)
+        # ---- replicated tail: O(M'^3), identical on every rank
+        W, L = f.W, f.L
+        ops.gemm(P.Ls_raw, ws.G, ws.H, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq)       # H = L_s^T G
+        ops.gemm(P.Ls_raw, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=-2.0, D=ws.G, M=Mq, N=Mq, K=Mq)
+        ops.add_outer(ws.X, P.m, ws.t, 1.0)                                              # X = dA A^T
+        if T == F32:
+            ops.cast2d(ws.X, ws.Xd)
+        ops.gemm(W, ws.Xd, ws.dL, ta=True, a_tri=TRI_UPPER, alpha=-1.0, c_tri=1, M=Mq, N=Mq, K=Mq)     # -tril(W^T X)
+        ops.gemm(L, ws.dL, ws.Y, ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, c_tri=1, M=Mq, N=Mq, K=Mq)  # L^T dL
+        ops.sym_phi(ws.Y, ws.Psi, Mq)                                                    # Psi = sym(Phi(Y))
+        ops.gemm(W, ws.Psi, ws.Y, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq)            # Y <- W^T Psi
+        ops.gemm(ws.Y, W, ws.S, b_tri=TRI_LOWER, c_tri=1, M=Mq, N=Mq, K=Mq)              # dK_zz = W^T Psi W
+        ops.mirror_lower(ws.S, Mq)
+        ops.kdir_bwd(P.Z, f.uz64, f.invz64, ws.p, P.Z, f.uz64, ws.p, f.hyp, ws.S, ws.gZ, ws.gVz, ws.sc[4:6],
+                     scale=2.0)
+        ops.var_grads(ws.H, P.Ls_raw, ws.t, P.m, inv_num_data, ws.gm, ws.gLs)
+
+    @staticmethod
+    def _collect(ws, f, P, T, noise_terms):
+        """dict of gradients shaped like the parameters (device ops only, no sync)."""
+        hyp, sc = f.hyp, ws.sc
+        g = {"Z": ws.gZ.to(T), "m": ws.gm.clone(), "Ls_raw": ws.gLs.clone(),
+             "c": sc[7].to(T).reshape(P.c.shape), "raw_os": (sc[5] * hyp[5]).to(T).reshape(P.raw_os.shape),
+             "raw_ell": (sc[4] * hyp[4]).to(T).reshape(P.raw_ell.shape)}
+        if ws.gVz is not None:
+            g["Vz"] = ws.gVz.to(T)
+        if P.raw_noise is not None:
+            g["raw_noise"] = (noise_terms * hyp[6]).to(T).reshape(P.raw_noise.shape)
+        return g
+
+    # ------------------------------------------------------------------------------------------ public: train
+    def elbo_step(self, P, x, Vx, y, num_data, p, p2, through_likelihood=True, n_global=None, want_grads=True):
+        """One fused forward(+backward) of VariationalELBO(likelihood, model, num_data)(likelihood(model(x)), y).
+
+        Returns (elbo [0-dim float64 tensor], grads dict or None, mean, variance).  `variance` includes likelihood
+        noise iff through_likelihood (directional_vi.py:245 feeds likelihood(model(x)) to the ELBO, Q3)."""
+        T, dev = x.dtype, x.device
+        n, d = x.shape
+        M = P.Z.shape[0]
+        ws = self.workspace(dev, T, n, d, M, p, p2)
+        f = self.factor(dev, T, d, M, p)
+        f.valid = False
+        nq_global = (n_global if n_global is not None else n) * (p2 + 1)
+        wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        for extra in (0.0,) + CHOL_RETRY:
+            self._factorise(f, P, T, extra)
+            self._forward(ws, f, P, x, wx, through_likelihood, need_C=True)
+            ws.small.zero_()
+            ws.kl.zero_()
+            ops.elbo_terms(ws.mu, ws.var, y, f.hyp, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
+            ops.kl_divergence(P.m, P.Ls_raw, ws.kl, ws.scratch)
+            if want_grads:
+                self._backward(ws, f, P, x, wx, ws.gmu, ws.gvar, through_likelihood, 1.0 / num_data)
+            elif self.reduce_hook is not None:
+                self.reduce_hook(None, ws.small)
+            if self._check(f, P):
+                break
+        else:
+            raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4 (psd_safe_cholesky ladder)")
+        elbo = ws.sc[0] - ws.kl[0] / num_data
+        grads = self._collect(ws, f, P, T, ws.sc[1] + ws.sc[6]) if want_grads else None
+        return elbo, grads, ws.mu.clone(), ws.var.clone()
+
+    # --------------------------------------------------------------------------- public: differentiable q(f)
+    def predictive_forward(self, P, x, Vx, p, p2, add_noise):
+        """mean, variance of q(f) (+ noise), keeping A and C for predictive_backward (generic autograd path)."""
+        T = x.dtype
+        n, d = x.shape
+        ws = self.workspace(x.device, T, n, d, P.Z.shape[0], p, p2)
+        f = self.factor(x.device, T, d, P.Z.shape[0], p)
+        f.valid = False
+        ws.wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        for extra in (0.0,) + CHOL_RETRY:
+            self._factorise(f, P, T, extra)
+            self._forward(ws, f, P, x, ws.wx, add_noise, need_C=True)
+            if self._check(f, P):
+                return (ws, f), ws.mu.clone(), ws.var.clone()
+        raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4 (psd_safe_cholesky ladder)")
+
+    def predictive_backward(self, ctx, P, x, gmu, gvar, add_noise):
+        ws, f = ctx
+        ws.small.zero_()
+        min_var = 1e-10 if x.dtype == F64 else 1e-6
+        gvar = torch.where(ws.var > min_var, gvar, torch.zeros_like(gvar)).contiguous()
+        self._backward(ws, f, P, x, ws.wx, gmu.contiguous(), gvar, add_noise, 0.0)
+        return self._collect(ws, f, P, x.dtype, ws.sc[6])
+
+    # ------------------------------------------------------------------------------------------ public: eval
+    def predict(self, P, x, Vx, p, p2, add_noise, reuse_factor=False):
+        """eval_gp's per-batch prediction (directional_vi.py:296-298).  reuse_factor: eval-mode memoisation of
+        the Cholesky factor (DGVS.py:72) -- K_zz is factorised once and reused until the strategy invalidates it."""
+        T = x.dtype
+        n, d = x.shape
+        M = P.Z.shape[0]
+        ws = self.workspace(x.device, T, n, d, M, p, p2)
+        f = self.factor(x.device, T, d, M, p)
+        if not (reuse_factor and f.valid):
+            f.valid = False
+            for extra in (0.0,) + CHOL_RETRY:
+                self._factorise(f, P, T, extra)
+                if self._check(f, P):
+                    break
+            else:
+                raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4")
+            f.valid = reuse_factor
+        wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        self._forward(ws, f, P, x, wx, add_noise, need_C=False)
+        return ws.mu.clone(), ws.var.clone()
+
+    def invalidate(self):
+        for f in self._fac.values():
+            f.valid = False
+
+
+ENGINE = Engine()

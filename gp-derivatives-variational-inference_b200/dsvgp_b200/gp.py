@@ -1,0 +1,604 @@
+"""Host-side mirror of the reference's Python API for the DSVGP hot path (no gpytorch import).
+
+The reference's boundary IS its Python class API: GPModel(gpytorch.models.ApproximateGP),
+ScaleKernel(RBFKernelDirectionalGrad()), ConstantMean, CholeskyVariationalDistribution, the three variational
+strategies, GaussianLikelihood and VariationalELBO.  This module provides those names with the same constructor
+arguments, attributes, state-dict keys and error behaviour, backed by the CUDA engine (engine.py) instead of
+eager gpytorch/ATen ops.  What a strategy call returns is a lazy `PredictiveDistribution`; handing it to
+VariationalELBO runs ONE fused forward+backward on the GPU and hooks the result into autograd, so
+`loss = -mll(likelihood(model(x, **kw)), y); loss.backward()` works unchanged (directional_vi.py:245-249).
+"""
+import math
+import types
+import warnings
+
+import torch
+from torch.nn import Parameter
+from torch.nn.functional import softplus
+
+from . import ops
+from .engine import ENGINE, NanError, NotPSDError  # noqa: F401  (re-exported)
+
+
+class OldVersionWarning(UserWarning):
+    pass
+
+
+def _inv_softplus(v):
+    return v + torch.log(-torch.expm1(-v))
+
+
+# ------------------------------------------------------------------------------------------------- modules
+class Module(torch.nn.Module):
+    """gpytorch.Module subset: hyperparameters() / variational_parameters() split used by the two optimisers
+    (directional_vi.py:186-199)."""
+
+    def named_hyperparameters(self):
+        for prefix, mod in self.named_modules():
+            if not isinstance(mod, _VariationalDistribution):
+                yield from mod.named_parameters(prefix=prefix, recurse=False)
+
+    def named_variational_parameters(self):
+        for prefix, mod in self.named_modules():
+            if isinstance(mod, _VariationalDistribution):
+                yield from mod.named_parameters(prefix=prefix, recurse=False)
+
+    def hyperparameters(self):
+        for _, p in self.named_hyperparameters():
+            yield p
+
+    def variational_parameters(self):
+        for _, p in self.named_variational_parameters():
+            yield p
+
+
+class ConstantMean(Module):
+    """gpytorch.means.ConstantMean: state-dict key `constant`, shape (1,)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("constant", Parameter(torch.zeros(1)))
+
+    def forward(self, x):
+        return self.constant.expand(x.shape[:-1])
+
+
+class MultivariateNormal:
+    """Dense (mean, covariance) pair -- what model.forward(x) returns on the prior path."""
+
+    def __init__(self, mean, covariance_matrix):
+        self.loc = mean
+        self.covariance_matrix = covariance_matrix
+
+    @property
+    def mean(self):
+        return self.loc
+
+    @property
+    def lazy_covariance_matrix(self):
+        return self.covariance_matrix
+
+    @property
+    def variance(self):
+        var = self.covariance_matrix.diagonal(dim1=-2, dim2=-1)
+        return var.clamp_min(1e-10 if var.dtype == torch.float64 else 1e-6)
+
+    @property
+    def stddev(self):
+        return self.variance.sqrt()
+
+    @property
+    def event_shape(self):
+        return self.loc.shape[-1:]
+
+
+# --------------------------------------------------------------------------------------------- kernel modules
+class _KDir(torch.autograd.Function):
+    """K = RBFKernelDirectionalGrad(x1, x2; v1, v2, lengthscale) with the fused backward."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, v1, v2, raw_ell, p1, p2):
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        hyp = ops.hyp_from_raw(raw_ell.reshape(-1))
+        u1, inv1 = ops.normalize_dirs(v1) if p1 else (None, None)
+        w2, inv2 = ops.normalize_dirs(v2) if p2 else (None, None)
+        K = torch.empty(x1.shape[0] * (p1 + 1), x2.shape[0] * (p2 + 1), dtype=x1.dtype, device=x1.device)
+        ops.kdir_fwd(x1c, u1, p1, x2c, w2, p2, hyp, K, use_os=False)
+        ctx.save_for_backward(x1c, x2c, u1, inv1, w2, inv2, hyp)
+        ctx.p = (p1, p2)
+        ctx.raw_shape = raw_ell.shape
+        return K
+
+    @staticmethod
+    def backward(ctx, dK):
+        x1, x2, u1, inv1, w2, inv2, hyp = ctx.saved_tensors
+        p1, p2 = ctx.p
+        dK = dK.contiguous()
+        T, dev = x1.dtype, x1.device
+        need = ctx.needs_input_grad
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
+        gsc = z(2)
+        gx1 = gv1 = gx2 = gv2 = None
+        if need[0] or need[2] or need[4]:
+            gx1, gv1 = z(*x1.shape), (z(x1.shape[0] * p1, x1.shape[1]) if p1 else None)
+            ops.kdir_bwd(x1, u1, inv1, p1, x2, w2, p2, hyp, dK, gx1, gv1, gsc, use_os=False)
+        if need[1] or need[3]:
+            gx2, gv2 = z(*x2.shape), (z(x2.shape[0] * p2, x2.shape[1]) if p2 else None)
+            ops.kdir_bwd(x2, w2, inv2, p2, x1, u1, p1, hyp, dK, gx2, gv2, None, use_os=False, dk_trans=True)
+        cast = lambda g, ok: g.to(T) if (g is not None and ok) else None
+        g_raw = (gsc[0] * hyp[4]).to(T).reshape(ctx.raw_shape) if need[4] else None
+        return cast(gx1, need[0]), cast(gx2, need[1]), cast(gv1, need[2]), cast(gv2, need[3]), g_raw, None, None
+
+
+class RBFKernelDirectionalGrad(Module):
+    """Drop-in for the reference class of the same name (RBFKernelDirectionalGrad.py:8-125).
+
+    forward(x1, x2, diag=False, v1=..., v2=...) returns the dense interleaved
+    (n1(p+1), n2(p+1)) block covariance of (value, p directional derivatives); directions are point-major and
+    are normalised inside the call; isotropic lengthscale of shape (1,1) under softplus."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.register_parameter("raw_lengthscale", Parameter(torch.zeros(1, 1)))
+        self.n_dir1 = 0
+
+    @property
+    def lengthscale(self):
+        return softplus(self.raw_lengthscale)
+
+    @lengthscale.setter
+    def lengthscale(self, value):
+        value = torch.as_tensor(value, dtype=self.raw_lengthscale.dtype, device=self.raw_lengthscale.device)
+        self.raw_lengthscale.data.copy_(_inv_softplus(value).expand(1, 1))
+
+    def set_num_directions(self, num_directions):
+        self.n_dir1 = num_directions
+
+    def num_outputs_per_input(self, x1, x2):
+        return self.n_dir1 + 1
+
+    def forward(self, x1, x2, diag=False, **params):
+        n1, n2 = x1.shape[-2], x2.shape[-2]
+        v1, v2 = params["v1"], params["v2"]
+        n_dir1, n_dir2 = int(v1.shape[-2] / n1), int(v2.shape[-2] / n2)
+        assert n_dir1 == n_dir2, "v1 and v2 must contain same number of directions"
+        self.set_num_directions(n_dir1)
+        if diag:
+            if not (n1 == n2 and torch.eq(x1, x2).all() and torch.eq(v1, v2).all()):
+                raise RuntimeError("diag=True only works when x1 == x2 and v1 == v2")
+            hyp = ops.hyp_from_raw(self.raw_lengthscale.reshape(-1))
+            return ops.kdir_diag(n2, n_dir2, hyp, x1.dtype, use_os=False)
+        return _KDir.apply(x1, x2, v1.to(x1.device), v2.to(x1.device), self.raw_lengthscale, n_dir1, n_dir2)
+
+    def __call__(self, x1, x2=None, diag=False, **params):
+        return self.forward(x1, x1 if x2 is None else x2, diag=diag, **params)
+
+
+class RBFKernelGrad(RBFKernelDirectionalGrad):
+    """gpytorch.kernels.RBFKernelGrad as used by grad_svgp.py:34: the same kernel with the d canonical
+    directions at every point (RBFKernelDirectionalGrad.py:156-161 states the equivalence)."""
+
+    def forward(self, x1, x2, diag=False, **params):
+        d = x1.shape[-1]
+        eye = torch.eye(d, dtype=x1.dtype, device=x1.device)
+        return super().forward(x1, x2, diag=diag, v1=eye.repeat(x1.shape[-2], 1), v2=eye.repeat(x2.shape[-2], 1))
+
+    def num_outputs_per_input(self, x1, x2):
+        return x1.size(-1) + 1
+
+
+class ScaleKernel(Module):
+    """gpytorch.kernels.ScaleKernel: keys `raw_outputscale` (0-dim) and `base_kernel.*`."""
+
+    def __init__(self, base_kernel):
+        super().__init__()
+        self.base_kernel = base_kernel
+        self.register_parameter("raw_outputscale", Parameter(torch.tensor(0.0)))
+
+    @property
+    def outputscale(self):
+        return softplus(self.raw_outputscale)
+
+    @outputscale.setter
+    def outputscale(self, value):
+        value = torch.as_tensor(value, dtype=self.raw_outputscale.dtype, device=self.raw_outputscale.device)
+        self.raw_outputscale.data.copy_(_inv_softplus(value).reshape(()))
+
+    def num_outputs_per_input(self, x1, x2):
+        return self.base_kernel.num_outputs_per_input(x1, x2)
+
+    def forward(self, x1, x2, diag=False, **params):
+        return self.base_kernel.forward(x1, x2, diag=diag, **params) * self.outputscale
+
+    def __call__(self, x1, x2=None, diag=False, **params):
+        return self.forward(x1, x1 if x2 is None else x2, diag=diag, **params)
+
+
+# ------------------------------------------------------------------------------------- variational distribution
+class _VariationalDistribution(Module):
+    pass
+
+
+class CholeskyVariationalDistribution(_VariationalDistribution):
+    """gpytorch.variational.CholeskyVariationalDistribution: keys `variational_mean` (M') and
+    `chol_variational_covar` (M', M'); q(u) = N(m, L L^T) with L = tril(param) (no positivity transform)."""
+
+    def __init__(self, num_inducing_points, batch_shape=torch.Size([]), mean_init_std=1e-3, **kwargs):
+        super().__init__()
+        self.num_inducing_points = num_inducing_points
+        self.mean_init_std = mean_init_std
+        self.register_parameter("variational_mean", Parameter(torch.zeros(num_inducing_points)))
+        self.register_parameter("chol_variational_covar", Parameter(torch.eye(num_inducing_points)))
+
+    def shape(self):
+        return torch.Size([self.num_inducing_points])
+
+    def initialize_from_prior(self):
+        """First-call initialisation against the whitened prior N(0, I): m <- 1e-3 * randn, L <- I."""
+        with torch.no_grad():
+            self.variational_mean.zero_().add_(torch.randn_like(self.variational_mean), alpha=self.mean_init_std)
+            self.chol_variational_covar.copy_(torch.eye(self.num_inducing_points, dtype=self.chol_variational_covar.dtype,
+                                                        device=self.chol_variational_covar.device))
+
+
+# ------------------------------------------------------------------------------------------------- likelihood
+class _HomoskedasticNoise(Module):
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_noise", Parameter(torch.zeros(1)))
+
+    @property
+    def noise(self):
+        return softplus(self.raw_noise) + 1e-4          # GreaterThan(1e-4)
+
+
+class GaussianLikelihood(Module):
+    """gpytorch.likelihoods.GaussianLikelihood: key `noise_covar.raw_noise`; likelihood(dist) adds the noise."""
+
+    def __init__(self):
+        super().__init__()
+        self.noise_covar = _HomoskedasticNoise()
+
+    @property
+    def noise(self):
+        return self.noise_covar.noise
+
+    @property
+    def raw_noise(self):
+        return self.noise_covar.raw_noise
+
+    def __call__(self, dist, *args, **kwargs):
+        if isinstance(dist, PredictiveDistribution):
+            return dist._with_likelihood(self)
+        if isinstance(dist, MultivariateNormal):
+            n = dist.mean.shape[-1]
+            eye = torch.eye(n, dtype=dist.mean.dtype, device=dist.mean.device)
+            return MultivariateNormal(dist.mean, dist.covariance_matrix + self.noise * eye)
+        raise TypeError("GaussianLikelihood expects the distribution returned by the model")
+
+
+# ------------------------------------------------------------------------------------- autograd entry points
+_PARAM_ORDER = ("Z", "Vz", "m", "Ls_raw", "c", "raw_os", "raw_ell", "raw_noise")
+
+
+class _ElboStep(torch.autograd.Function):
+    """value = ELBO; the gradients w.r.t. every parameter are computed by the same fused GPU pass and handed
+    to autograd in backward (scaled by the incoming gradient)."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, Vx, y, *params):
+        P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
+        want = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params)
+        elbo, grads, mean, var = ENGINE.elbo_step(P, x, Vx, y, cfg["num_data"], cfg["p"], cfg["p2"],
+                                                  cfg["through_likelihood"], cfg.get("n_global"), want_grads=want)
+        ctx.grads = grads
+        ctx.mark_non_differentiable(mean, var)
+        return elbo.to(x.dtype), mean, var
+
+    @staticmethod
+    def backward(ctx, g_elbo, _gm, _gv):
+        grads = ctx.grads
+        if grads is None:
+            raise RuntimeError("the ELBO was evaluated without gradients (torch.no_grad / no parameter requires grad)")
+        out = []
+        for name, need in zip(_PARAM_ORDER, ctx.needs_input_grad[4:]):
+            g = grads.get(name)
+            out.append(g * g_elbo.to(g.dtype) if (need and g is not None) else None)
+        return (None, None, None, None, *out)
+
+
+class _Predictive(torch.autograd.Function):
+    """(mean, variance) of q(f) [+ noise] as differentiable tensors -- the generic path behind
+    PredictiveDistribution.mean / .variance when they are used outside VariationalELBO."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, Vx, *params):
+        P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
+        ectx, mean, var = ENGINE.predictive_forward(P, x, Vx, cfg["p"], cfg["p2"], cfg["add_noise"])
+        ctx.ectx, ctx.P, ctx.x, ctx.cfg = ectx, P, x, cfg
+        ectx[0].generation = getattr(ectx[0], "generation", 0) + 1
+        ctx.generation = ectx[0].generation
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, gmu, gvar):
+        if ctx.ectx[0].generation != ctx.generation:
+            raise RuntimeError("dsvgp_b200: the predictive workspace was overwritten by a later forward pass before "
+                               "backward ran; call backward before evaluating the model again on the same shape")
+        grads = ENGINE.predictive_backward(ctx.ectx, ctx.P, ctx.x, gmu, gvar, ctx.cfg["add_noise"])
+        out = []
+        for name, need in zip(_PARAM_ORDER, ctx.needs_input_grad[3:]):
+            g = grads.get(name)
+            out.append(g if (need and g is not None) else None)
+        return (None, None, None, *out)
+
+
+class PredictiveDistribution:
+    """Lazy q(f(X)) returned by a variational strategy (stands in for gpytorch's MultivariateNormal with a lazy
+    covariance).  Only what the reference's callers consume is offered: .mean / .loc, .variance, .stddev
+    (directional_vi.py:256-257, :297-298).  The full predictive covariance is SURVEY.md section 8f rank 4."""
+
+    def __init__(self, strategy, x, Vx, likelihood=None):
+        self._strategy, self._x, self._Vx, self._likelihood = strategy, x, Vx, likelihood
+        self._cache = None
+
+    def _with_likelihood(self, likelihood):
+        return PredictiveDistribution(self._strategy, self._x, self._Vx, likelihood)
+
+    @property
+    def event_shape(self):
+        return torch.Size([self._x.shape[0] * (self._strategy._p2() + 1)])
+
+    def _params(self):
+        return self._strategy._param_list(self._likelihood)
+
+    def _evaluate(self):
+        if self._cache is None:
+            st = self._strategy
+            cfg = dict(p=st._p(), p2=st._p2(), add_noise=self._likelihood is not None)
+            params = self._params()
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params):
+                self._cache = _Predictive.apply(cfg, self._x, self._Vx, *params)
+            else:
+                P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
+                self._cache = ENGINE.predict(P, self._x, self._Vx, cfg["p"], cfg["p2"], cfg["add_noise"],
+                                             reuse_factor=not st.training)
+        return self._cache
+
+    @property
+    def mean(self):
+        return self._evaluate()[0]
+
+    loc = mean
+
+    @property
+    def variance(self):
+        return self._evaluate()[1]
+
+    @property
+    def stddev(self):
+        return self.variance.sqrt()
+
+    @property
+    def lazy_covariance_matrix(self):
+        raise NotImplementedError("only the predictive mean and diagonal variance are on the B200 hot path")
+
+    covariance_matrix = lazy_covariance_matrix
+
+
+# ------------------------------------------------------------------------------------------------ objectives
+class VariationalELBO(Module):
+    """gpytorch.mlls.VariationalELBO(likelihood, model, num_data): (dist, target) -> scalar
+    (1/n') sum_j E_q[log p(y_j | f_j)] - KL(q(u) || p(u)) / num_data."""
+
+    def __init__(self, likelihood, model, num_data, beta=1.0, combine_terms=True):
+        super().__init__()
+        self.likelihood, self.model, self.num_data, self.beta = likelihood, model, num_data, beta
+        if not combine_terms:
+            raise NotImplementedError("combine_terms=False is not used on the hot path")
+
+    def forward(self, dist, target, **kwargs):
+        if not isinstance(dist, PredictiveDistribution):
+            raise TypeError("VariationalELBO expects the distribution returned by model(x, ...) or likelihood(model(x, ...))")
+        st = dist._strategy
+        cfg = dict(p=st._p(), p2=st._p2(), num_data=float(self.num_data) / float(self.beta),
+                   through_likelihood=dist._likelihood is not None, n_global=st._n_global)
+        params = st._param_list(self.likelihood)
+        elbo, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, target.contiguous(), *params)
+        dist._cache = (mean, var)      # train loops print output.mean / output.variance (directional_vi.py:256-257)
+        return elbo
+
+
+class PredictiveLogLikelihood(Module):
+    """gpytorch.mlls.PredictiveLogLikelihood (mll_type="PLL", directional_vi.py:218-219): log N(y; mu, var + noise)
+    summed with weight 1/n', minus KL/num_data.  Uses the differentiable mean / variance path."""
+
+    def __init__(self, likelihood, model, num_data, beta=1.0):
+        super().__init__()
+        self.likelihood, self.model, self.num_data, self.beta = likelihood, model, num_data, beta
+
+    def forward(self, dist, target, **kwargs):
+        marginal = self.likelihood(dist)
+        mean, var = marginal.mean, marginal.variance
+        ll = -0.5 * ((target - mean) ** 2 / var + var.log() + math.log(2 * math.pi))
+        kl = self.model.variational_strategy.kl_divergence()
+        return ll.sum(-1) / mean.shape[-1] - kl / (self.num_data / self.beta)
+
+
+# ---------------------------------------------------------------------------------------------------- models
+class ApproximateGP(Module):
+    """gpytorch.models.ApproximateGP: model(x, **kwargs) -> variational_strategy(x, **kwargs)."""
+
+    def __init__(self, variational_strategy):
+        super().__init__()
+        self.variational_strategy = variational_strategy
+
+    def forward(self, x, **kwargs):
+        raise NotImplementedError
+
+    def __call__(self, inputs, prior=False, **kwargs):
+        if inputs.dim() == 1:
+            inputs = inputs.unsqueeze(-1)
+        return self.variational_strategy(inputs, prior=prior, **kwargs)
+
+
+def _ensure_updated_strategy_flag_set(module, state_dict, prefix, *args):
+    """load_state_dict pre-hook of the reference strategies (DGVS.py:17-29): checkpoints from before the whitened
+    parameterisation lack `updated_strategy`; they get False, which triggers the one-off re-whitening."""
+    if prefix + "updated_strategy" not in state_dict:
+        device = state_dict[list(state_dict.keys())[0]].device
+        state_dict[prefix + "updated_strategy"] = torch.tensor(False, device=device)
+        warnings.warn("You have loaded a variational GP model from a version that used un-whitened parameters; "
+                      "they are converted on the first call. Re-save the model.", OldVersionWarning)
+
+
+class _DirectionalStrategyBase(Module):
+    """Shared machinery of the three strategies (gpytorch _VariationalStrategy + DGVS.py:65-69)."""
+
+    def __init__(self, model, inducing_points, variational_distribution, learn_inducing_locations=True):
+        super().__init__()
+        object.__setattr__(self, "model", model)
+        inducing_points = inducing_points.clone()
+        if inducing_points.dim() == 1:
+            inducing_points = inducing_points.unsqueeze(-1)
+        if learn_inducing_locations:
+            self.register_parameter("inducing_points", Parameter(inducing_points))
+        else:
+            self.register_buffer("inducing_points", inducing_points)
+        self._variational_distribution = variational_distribution
+        self.register_buffer("variational_params_initialized", torch.tensor(0))
+        self.register_buffer("updated_strategy", torch.tensor(True))
+        self._register_load_state_dict_pre_hook(_ensure_updated_strategy_flag_set, with_module=True)
+        self._n_global = None          # set by distributed.shard(): global minibatch size of a sharded step
+
+    # ---- shape helpers
+    def _p(self):
+        raise NotImplementedError
+
+    def _p2(self):
+        return self._p()
+
+    def _directions(self):
+        raise NotImplementedError
+
+    def _param_list(self, likelihood):
+        vd, model = self._variational_distribution, self.model
+        raw_noise = likelihood.noise_covar.raw_noise if likelihood is not None else None
+        return (self.inducing_points, self._directions(), vd.variational_mean, vd.chol_variational_covar,
+                model.mean_module.constant, model.covar_module.raw_outputscale,
+                model.covar_module.base_kernel.raw_lengthscale, raw_noise)
+
+    def train(self, mode=True):
+        ENGINE.invalidate()                 # eval-mode memoisation of the Cholesky factor ends here (DGVS.py:72)
+        return super().train(mode)
+
+    def kl_divergence(self):
+        """KL(q(u) || N(0, I)) of the whitened parameterisation (differentiable, small: plain torch on device)."""
+        vd = self._variational_distribution
+        Ls = vd.chol_variational_covar.tril()
+        m = vd.variational_mean
+        return 0.5 * ((Ls * Ls).sum() + (m * m).sum() - m.numel() - Ls.diagonal().pow(2).log().sum())
+
+    def _data_directions(self, x, kwargs):
+        raise NotImplementedError
+
+    def forward(self, x, inducing_points, inducing_values, variational_inducing_covar=None, **kwargs):
+        """Same signature as the reference forward (DGVS.py:89); the inducing arguments are the module's own
+        parameters and are read from the module."""
+        Vx = self._data_directions(x, kwargs)
+        return PredictiveDistribution(self, x.contiguous(), Vx)
+
+    def _rewhiten_legacy_parameters(self):
+        """One-off conversion of un-whitened variational parameters (reference __call__, DGVS.py:211-238):
+        m <- L^-1 (m - c),  L_s <- L^-1 L_s  with L = chol(K_zz + 1e-3 I)."""
+        vd = self._variational_distribution
+        params = self._param_list(None)
+        P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
+        T, dev = P.Z.dtype, P.Z.device
+        f = ENGINE.factor(dev, T, P.Z.shape[1], P.Z.shape[0], self._p())
+        ENGINE._factorise(f, P, T, 0.0)
+        if not ENGINE._check(f, P):
+            raise NotPSDError("K_zz is not positive definite")
+        with torch.no_grad():
+            Mq = f.Mq
+            rhs = torch.empty(Mq, Mq + 8, dtype=T, device=dev)
+            rhs[:, :Mq] = vd.chol_variational_covar.tril()
+            rhs[:, Mq] = vd.variational_mean - self.model.mean_module.constant
+            out = torch.empty_like(rhs)
+            ops.gemm(f.Wt, rhs, out, a_tri=ops.TRI_LOWER, M=Mq, N=Mq + 1, K=Mq)
+            root = out[:, :Mq].tril()
+            sign = torch.where(root.diagonal() < 0, -1.0, 1.0).to(T)
+            vd.chol_variational_covar.copy_(root * sign)
+            vd.variational_mean.copy_(out[:, Mq])
+        ENGINE.invalidate()
+        self.updated_strategy.fill_(True)
+
+    def __call__(self, x, prior=False, **kwargs):
+        if prior:
+            return self.model.forward(x, **kwargs)
+        if not self.updated_strategy.item():
+            self._rewhiten_legacy_parameters()
+        if not self.variational_params_initialized.item():
+            self._variational_distribution.initialize_from_prior()
+            self.variational_params_initialized.fill_(1)
+        vd = self._variational_distribution
+        return self.forward(x, self.inducing_points, vd.variational_mean, None, **kwargs)
+
+
+class DirectionalGradVariationalStrategy(_DirectionalStrategyBase):
+    """Drop-in for directionalvi/DirectionalGradVariationalStrategy.py:32-240: whitened SVGP over function values
+    and p learned directional derivatives per inducing point.  `kwargs['derivative_directions']` (n*p, d) gives the
+    data-side directions."""
+
+    def __init__(self, model, inducing_points, inducing_directions, variational_distribution,
+                 learn_inducing_locations=True):
+        super().__init__(model, inducing_points, variational_distribution, learn_inducing_locations)
+        self.register_parameter(name="inducing_directions", param=Parameter(inducing_directions.clone()))
+
+    def _p(self):
+        return int(self.inducing_directions.size(-2) / self.inducing_points.size(-2))
+
+    def _directions(self):
+        return self.inducing_directions
+
+    def _data_directions(self, x, kwargs):
+        derivative_directions = kwargs["derivative_directions"]
+        num_derivative_directions = int(derivative_directions.size(-2) / x.size(-2))
+        assert num_derivative_directions == self._p(), "Need minibatch dim to be same as number of directions for kernel"
+        self.model.covar_module.base_kernel.set_num_directions(self._p())
+        return derivative_directions.to(device=x.device, dtype=x.dtype).contiguous()
+
+
+class DFreeDirectionalGradVariationalStrategy(DirectionalGradVariationalStrategy):
+    """Drop-in for directionalvi/DFreeDirectionalGradVariationalStrategy.py:32-227: same inducing structure, but the
+    data carry no derivative labels -- only the function-value rows/columns of the data side are kept
+    (:112,:118,:123,:136), so outputs have length n and the data-side directions influence nothing."""
+
+    def _p2(self):
+        return 0
+
+
+class GradVariationalStrategy(_DirectionalStrategyBase):
+    """Drop-in for directionalvi/GradVariationalStrategy.py:32-169: full-gradient inducing variables, i.e. the
+    directional strategy with the d canonical directions at every inducing and data point (gpytorch RBFKernelGrad)."""
+
+    def __init__(self, model, inducing_points, variational_distribution, learn_inducing_locations=True):
+        super().__init__(model, inducing_points, variational_distribution, learn_inducing_locations)
+        self._canon = None
+
+    def _p(self):
+        return self.inducing_points.size(-1)
+
+    def _canonical(self, n, like):
+        d = like.shape[-1]
+        return torch.eye(d, dtype=like.dtype, device=like.device).repeat(n, 1)
+
+    def _directions(self):
+        Z = self.inducing_points
+        if self._canon is None or self._canon.shape[0] != Z.shape[0] * Z.shape[1] or self._canon.device != Z.device \
+                or self._canon.dtype != Z.dtype:
+            self._canon = self._canonical(Z.shape[0], Z)
+        return self._canon
+
+    def _data_directions(self, x, kwargs):
+        return self._canonical(x.shape[0], x)

@@ -1,0 +1,168 @@
+"""Tensor-level wrappers over the C ABI (one Python function per kernel family).
+
+Every function takes CUDA tensors, enqueues work on torch's current stream and returns without synchronising.
+Matrices are row-major; a 2-D tensor must have unit stride in its last dimension, its first stride is the
+leading dimension.  These are the building blocks of engine.py and of the autograd Functions in functions.py.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, call_raw, suffix
+
+TRI_NONE, TRI_LOWER, TRI_UPPER = 0, 1, 2
+F32, F64 = torch.float32, torch.float64
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "matrix operands must be row-major with unit inner stride"
+    return t.stride(0)
+
+
+def _pair_suffix(t_in, t_k):
+    if t_in == t_k:
+        return suffix(t_in)
+    if t_in == F32 and t_k == F64:
+        return "f32f64"
+    raise _lib.DsvgpError(f"unsupported dtype pair {t_in}/{t_k}")
+
+
+def hyp_from_raw(raw_ell, raw_os=None, raw_noise=None, c=None, out=None):
+    """-> device double[8] {ell, os, noise, c, sigmoid(raw_ell), sigmoid(raw_os), sigmoid(raw_noise), 0}."""
+    out = torch.empty(8, dtype=F64, device=raw_ell.device) if out is None else out
+    call("dsvgp_hyp_from_raw_" + suffix(raw_ell.dtype), raw_ell, raw_os, raw_noise, c, out)
+    return out
+
+
+def normalize_dirs(v, k_dtype=None):
+    """Row-normalised directions and 1/|v| in k_dtype (RBFKernelDirectionalGrad.py:57-58)."""
+    k_dtype = k_dtype or v.dtype
+    v = v.contiguous()
+    vhat = torch.empty(v.shape, dtype=k_dtype, device=v.device)
+    inv = torch.empty(v.shape[0], dtype=k_dtype, device=v.device)
+    call("dsvgp_normalize_dirs_" + _pair_suffix(v.dtype, k_dtype), v, v.shape[0], v.shape[1], vhat, inv)
+    return vhat, inv
+
+
+def kdir_fwd(x1, u1, p1, x2, w2, p2, hyp, out, use_os=True, diag_add=0.0):
+    """out[:n1(p1+1), :n2(p2+1)] = [os*] K(x1, x2; u1, w2) (+ diag_add on the diagonal)."""
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    assert out.shape[0] >= n1 * (p1 + 1) and out.shape[1] >= n2 * (p2 + 1)
+    call("dsvgp_kdir_fwd_" + _pair_suffix(x1.dtype, out.dtype), x1, u1 if p1 else None, n1, p1, x2,
+         w2 if p2 else None, n2, p2, d, hyp, int(use_os), float(diag_add), out, _ld(out))
+    return out
+
+
+def kdir_diag(n, p, hyp, dtype, use_os=True):
+    out = torch.empty(n * (p + 1), dtype=dtype, device=hyp.device)
+    call("dsvgp_kdir_diag_" + suffix(dtype), n, p, hyp, int(use_os), out)
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    key = (tag, device)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def kdir_bwd(x1, u1, inv1, p1, x2, w2, p2, hyp, dK, gx, gv, gsc, use_os=True, dk_trans=False, scale=1.0):
+    """Accumulate scale*dL/dx1 into gx, scale*dL/dv1 into gv and dL/d(ell, os) into gsc[0:2] (all float64)."""
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    nbytes = call_raw("dsvgp_kdir_bwd_workspace_" + suffix(dK.dtype), n1, p1, n2, p2, d)
+    ws = _workspace(nbytes, x1.device, "kdir_bwd")
+    call("dsvgp_kdir_bwd_" + _pair_suffix(x1.dtype, dK.dtype), x1, u1 if p1 else None, inv1 if p1 else None, n1, p1,
+         x2, w2 if p2 else None, n2, p2, d, hyp, int(use_os), dK, _ld(dK), int(dk_trans), float(scale), gx,
+         gv if p1 else None, gsc, ws, ws.numel())
+
+
+def gemm(A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, a_tri=TRI_NONE, b_tri=TRI_NONE, c_tri=0, D=None,
+         M=None, N=None, K=None):
+    """C[:M,:N] = alpha*op(A)[:M,:K] @ op(B)[:K,:N] + beta*(D or C).  Triangle flags: see include/dsvgp_b200.h."""
+    if M is None:
+        M = A.shape[1] if ta else A.shape[0]
+    if K is None:
+        K = A.shape[0] if ta else A.shape[1]
+    if N is None:
+        N = B.shape[0] if tb else B.shape[1]
+    call("dsvgp_gemm_" + suffix(C.dtype), int(ta), int(tb), M, N, K, float(alpha), A, _ld(A), B, _ld(B), float(beta),
+         C, _ld(C), a_tri, b_tri, c_tri, 1, 0, 0, 0, D, _ld(D) if D is not None else 0)
+    return C
+
+
+def chol_plan(Mq):
+    return _lib.chol_plan(Mq)
+
+
+def pad_identity(A, Mq):
+    call("dsvgp_pad_identity_f64", A, _ld(A), Mq, A.shape[0])
+
+
+def cholesky_inverse(Awork, L, W, nb0, nlev, info):
+    """Awork (Mp x Mp fp64, destroyed) -> L, W = L^-1; info: device int32[1]."""
+    call("dsvgp_chol_f64", Awork, _ld(Awork), L, _ld(L), W, _ld(W), Awork.shape[0], nb0, nlev, info)
+
+
+def cast2d(src, dst, rows=None, cols=None, tril=False):
+    rows = src.shape[0] if rows is None else rows
+    cols = src.shape[1] if cols is None else cols
+    call(f"dsvgp_cast_{suffix(src.dtype)}_{suffix(dst.dtype)}", src, _ld(src), dst, _ld(dst), rows, cols, int(tril))
+    return dst
+
+
+def mirror_lower(A, n=None):
+    call("dsvgp_mirror_lower_" + suffix(A.dtype), A, _ld(A), A.shape[0] if n is None else n)
+    return A
+
+
+def add_outer(A, u, v, alpha=1.0, n=None):
+    call("dsvgp_add_outer_" + suffix(A.dtype), A, _ld(A), A.shape[0] if n is None else n, u, v, float(alpha))
+    return A
+
+
+def sym_phi(Y, P, n):
+    call("dsvgp_sym_phi_f64", Y, _ld(Y), P, _ld(P), n)
+    return P
+
+
+def reduce_slabs(rows, cols):
+    return call_raw("dsvgp_reduce_slabs", rows, cols)
+
+
+def col_dots(A, m, pm, pv, rows, nq, C=None, B=None):
+    nslab = pm.shape[0]
+    call("dsvgp_col_dots_" + suffix(A.dtype), A, C, B, _ld(A), rows, nq, m, pm, pv, nslab)
+
+
+def predict_finish(pm, pv, nq, p2, hyp, mu, var, add_noise, pred_jitter=1e-4):
+    min_var = 1e-10 if mu.dtype == F64 else 1e-6      # gpytorch settings.min_variance
+    call("dsvgp_predict_finish_" + suffix(mu.dtype), pm, pv, pm.shape[0], nq, p2, hyp, float(pred_jitter),
+         int(add_noise), min_var, mu, var)
+
+
+def elbo_terms(mu, var, y, hyp, w, gmu, gvar, sc, ws):
+    min_var = 1e-10 if mu.dtype == F64 else 1e-6
+    call("dsvgp_elbo_terms_" + suffix(mu.dtype), mu, var, y, mu.numel(), hyp, float(w), min_var, gmu, gvar, sc, ws)
+
+
+def pred_bwd_scalars(gmu, gvar, p2, hyp, add_noise, gsc, ws):
+    call("dsvgp_pred_bwd_scalars_" + suffix(gmu.dtype), gmu, gvar, gmu.numel(), p2, hyp, int(add_noise), gsc, ws)
+
+
+def dA_apply(A, C, Ag, rows, nq, m, gmu, gvar, tp, t):
+    call("dsvgp_dA_" + suffix(A.dtype), A, C, Ag, _ld(A), rows, nq, m, gmu, gvar, tp, tp.shape[0], t)
+
+
+def kl_divergence(m, Ls_raw, out, ws):
+    call("dsvgp_kl_" + suffix(m.dtype), m, Ls_raw, _ld(Ls_raw), m.numel(), out, ws)
+
+
+def var_grads(H, Ls_raw, t, m, inv_num_data, gm, gLs):
+    call("dsvgp_var_grads_" + suffix(m.dtype), H, _ld(H), Ls_raw, _ld(Ls_raw), t, m, m.numel(), float(inv_num_data),
+         gm, gLs, _ld(gLs))

@@ -1,0 +1,145 @@
+/* dsvgp_b200 -- C ABI of the B200-native DSVGP hot path (libdsvgp_b200.so, sm_100a only).
+ *
+ * The reference (mishapadidar/GP-Derivatives-Variational-Inference) has no FFI: its boundary is the Python
+ * class API.  These entry points are what a Python binding of that API calls underneath; each one says which
+ * reference code it replaces (paths are under directionalvi/ of the reference).  The ctypes stubs a maintainer
+ * would add are in INTEGRATION.md and, in full, in gp-derivatives-variational-inference_b200/dsvgp_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; matrices are row-major with an explicit
+ *     leading dimension (in elements); the caller owns every buffer (the library never allocates user-visible
+ *     memory); scratch comes in through a workspace pointer whose size a *_workspace() function reports;
+ *   - all work is enqueued on the cudaStream_t given (pass torch.cuda.current_stream().cuda_stream); there is
+ *     no hidden synchronisation, so every call is CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = DSVGP_ERR_* ; nothing throws;
+ *   - suffixes: _f32 / _f64 = dtype of the model tensors; _f32f64 = fp32 inputs, fp64 matrix (K_zz of an fp32
+ *     model is assembled and factorised in fp64, DirectionalGradVariationalStrategy.py:74);
+ *   - `hyp` is a device double[8]: {lengthscale, outputscale, noise, mean constant,
+ *     sigmoid(raw_lengthscale), sigmoid(raw_outputscale), sigmoid(raw_noise), 0}  (dsvgp_hyp_from_raw_*).
+ *   - directions are passed ALREADY NORMALISED (dsvgp_normalize_dirs_*), point-major: p consecutive rows per
+ *     point (RBFKernelDirectionalGrad.py:10-13).
+ */
+#ifndef DSVGP_B200_H
+#define DSVGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dsvgp_stream_t; /* cudaStream_t */
+
+#define DSVGP_OK 0
+#define DSVGP_ERR_ARG -1
+#define DSVGP_ERR_LAUNCH -2
+#define DSVGP_ERR_WORKSPACE -3
+
+#define DSVGP_TRI_NONE 0
+#define DSVGP_TRI_LOWER 1
+#define DSVGP_TRI_UPPER 2
+
+/* library version (major*10000 + minor*100 + patch) and the compute capability it was built for (100) */
+int dsvgp_version(void);
+int dsvgp_built_for_sm(void);
+
+/* Positive()/GreaterThan(1e-4) transforms of gpytorch that the reference reaches through
+ * self.lengthscale (RBFKernelDirectionalGrad.py:67), ScaleKernel.outputscale (directional_vi.py:56) and
+ * GaussianLikelihood.noise (directional_vi.py:172).  raw_os / raw_noise / c may be NULL. */
+int dsvgp_hyp_from_raw_f32(const float* raw_ell, const float* raw_os, const float* raw_noise, const float* c, double* hyp, dsvgp_stream_t s);
+int dsvgp_hyp_from_raw_f64(const double* raw_ell, const double* raw_os, const double* raw_noise, const double* c, double* hyp, dsvgp_stream_t s);
+
+/* v / |v| row-wise and 1/|v|  -- RBFKernelDirectionalGrad.py:57-58 */
+int dsvgp_normalize_dirs_f32(const float* v, int rows, int d, float* vhat, float* inv_norm, dsvgp_stream_t s);
+int dsvgp_normalize_dirs_f64(const double* v, int rows, int d, double* vhat, double* inv_norm, dsvgp_stream_t s);
+int dsvgp_normalize_dirs_f32f64(const float* v, int rows, int d, double* vhat, double* inv_norm, dsvgp_stream_t s);
+
+/* K (n1(p1+1) x n2(p2+1), interleaved) = [outputscale *] RBFKernelDirectionalGrad.forward(x1, x2, v1=.., v2=..)
+ * -- RBFKernelDirectionalGrad.py:41-108 (+ ScaleKernel).  p2 = 0 gives the value-only columns the DFree strategy
+ * keeps (DFreeDirectionalGradVariationalStrategy.py:118).  diag_add is added to the diagonal (add_jitter,
+ * DirectionalGradVariationalStrategy.py:144) and is only meaningful for x1 == x2. */
+int dsvgp_kdir_fwd_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, dsvgp_stream_t s);
+int dsvgp_kdir_fwd_f64(const double* x1, const double* u1, int n1, int p1, const double* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, double* K, int64_t ldk, dsvgp_stream_t s);
+int dsvgp_kdir_fwd_f32f64(const float* x1, const double* u1, int n1, int p1, const float* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, double* K, int64_t ldk, dsvgp_stream_t s);
+
+/* diag=True branch -- RBFKernelDirectionalGrad.py:110-119 */
+int dsvgp_kdir_diag_f32(int n, int p, const double* hyp, int use_os, float* out, dsvgp_stream_t s);
+int dsvgp_kdir_diag_f64(int n, int p, const double* hyp, int use_os, double* out, dsvgp_stream_t s);
+
+/* Backward of dsvgp_kdir_fwd_* (autograd of RBFKernelDirectionalGrad.py:57-107): given dK, ACCUMULATES
+ *   gx   (n1,d)      += scale * dL/dx1         (NULL to skip)
+ *   gv   (n1*p1,d)   += scale * dL/dv1 (chain rule through the normalisation included; NULL to skip)
+ *   gsc[0] += dL/dlengthscale, gsc[1] += dL/doutputscale   (NULL to skip)
+ * all double.  dk_trans != 0 reads dK transposed (gradients for the second argument: swap the roles).
+ * K is recomputed, never re-read. */
+size_t dsvgp_kdir_bwd_workspace_f32(int n1, int p1, int n2, int p2, int d);
+size_t dsvgp_kdir_bwd_workspace_f64(int n1, int p1, int n2, int p2, int d);
+int dsvgp_kdir_bwd_f32(const float* x1, const float* u1, const float* inv1, int n1, int p1, const float* x2, const float* w2, int n2, int p2, int d, const double* hyp, int use_os, const float* dK, int64_t lddk, int dk_trans, double scale, double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, dsvgp_stream_t s);
+int dsvgp_kdir_bwd_f64(const double* x1, const double* u1, const double* inv1, int n1, int p1, const double* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, const double* dK, int64_t lddk, int dk_trans, double scale, double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, dsvgp_stream_t s);
+int dsvgp_kdir_bwd_f32f64(const float* x1, const double* u1, const double* inv1, int n1, int p1, const float* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, const double* dK, int64_t lddk, int dk_trans, double scale, double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, dsvgp_stream_t s);
+
+/* Cholesky of the jittered K_zz and the inverse factor -- _cholesky_factor / psd_safe_cholesky
+ * (DirectionalGradVariationalStrategy.py:72-75) and TriangularLazyTensor.inv_matmul (:181,:183).
+ * dsvgp_chol_plan: padded size Mp = nb0 << nlev for an Mq x Mq matrix.  dsvgp_pad_identity_f64 writes the identity
+ * padding.  dsvgp_chol_f64: Awork (destroyed) -> L (lower), W = L^-1 (lower); *info (device int) = 0 or
+ * 1 + index of the first non-positive pivot. */
+void dsvgp_chol_plan(int Mq, int* Mp_host, int* nb0_host, int* nlev_host);
+int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t s);
+int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0, int nlev, int* info, dsvgp_stream_t s);
+
+/* C = alpha*op(A)*op(B) + beta*C, triangle-aware, batched -- every dense product of the strategy
+ * (DirectionalGradVariationalStrategy.py:181-205) and of its backward.  fp32 uses 3xTF32 (fp32-accurate).
+ * D != NULL: C = alpha*op(A)*op(B) + beta*D (D not batched); D == NULL: the addend is C itself. */
+int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, dsvgp_stream_t s);
+int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, dsvgp_stream_t s);
+
+/* helpers on M' x M' matrices of the replicated tail */
+int dsvgp_cast_f64_f32(const double* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
+int dsvgp_cast_f32_f64(const float* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
+int dsvgp_cast_f64_f64(const double* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
+int dsvgp_cast_f32_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
+int dsvgp_mirror_lower_f32(float* A, int64_t ld, int n, dsvgp_stream_t s);
+int dsvgp_mirror_lower_f64(double* A, int64_t ld, int n, dsvgp_stream_t s);
+int dsvgp_add_outer_f32(float* A, int64_t ld, int n, const float* u, const float* v, double alpha, dsvgp_stream_t s);
+int dsvgp_add_outer_f64(double* A, int64_t ld, int n, const double* u, const double* v, double alpha, dsvgp_stream_t s);
+int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s);
+
+/* predictive mean / diagonal variance (DirectionalGradVariationalStrategy.py:188,:192-205):
+ *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or  sum (B_ij^2 - A_ij^2)  (B given)
+ *   mu_j = sum_s pm + c ; var_j = kdiag_j + pred_jitter + sum_s pv [+ noise], clamped at min_var. */
+int dsvgp_reduce_slabs(int rows, int cols);
+int dsvgp_col_dots_f32(const float* A, const float* C, const float* B, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, dsvgp_stream_t s);
+int dsvgp_col_dots_f64(const double* A, const double* C, const double* B, int64_t ld, int rows, int nq, const double* m, double* pm, double* pv, int nslab, dsvgp_stream_t s);
+int dsvgp_predict_finish_f32(const float* pm, const float* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter, int add_noise, double min_var, float* mu, float* var, dsvgp_stream_t s);
+int dsvgp_predict_finish_f64(const double* pm, const double* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter, int add_noise, double min_var, double* mu, double* var, dsvgp_stream_t s);
+
+/* Gaussian expected log-likelihood summed with weight w (= 1/n') and its gradient w.r.t. mu, var
+ * (gpytorch GaussianLikelihood.expected_log_prob / VariationalELBO, directional_vi.py:217,246).
+ * sc[0] += sum_j term_j*w ; sc[1] += explicit d/dnoise.  ws: 2*ceil(nq/256) doubles. */
+int dsvgp_elbo_terms_f32(const float* mu, const float* var, const float* y, int nq, const double* hyp, double w, double min_var, float* gmu, float* gvar, double* sc, double* ws, dsvgp_stream_t s);
+int dsvgp_elbo_terms_f64(const double* mu, const double* var, const double* y, int nq, const double* hyp, double w, double min_var, double* gmu, double* gvar, double* sc, double* ws, dsvgp_stream_t s);
+
+/* gsc[0..3] += {d lengthscale, d outputscale, d noise, d constant} flowing through +c and the K_xx diagonal.
+ * ws: 4*296 doubles. */
+int dsvgp_pred_bwd_scalars_f32(const float* gmu, const float* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc, double* ws, dsvgp_stream_t s);
+int dsvgp_pred_bwd_scalars_f64(const double* gmu, const double* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc, double* ws, dsvgp_stream_t s);
+
+/* In place C <- m gmu^T + 2 C diag(gvar) (= dL/dA); Ag <- A diag(gvar) (NULL to skip); t = A gmu.
+ * tp: nslab*rows scratch. */
+int dsvgp_dA_f32(const float* A, float* C, float* Ag, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, dsvgp_stream_t s);
+int dsvgp_dA_f64(const double* A, double* C, double* Ag, int64_t ld, int rows, int nq, const double* m, const double* gmu, const double* gvar, double* tp, int nslab, double* t, dsvgp_stream_t s);
+
+/* KL(N(m, Ls Ls^T) || N(0, I)) with Ls = tril(raw) (_VariationalStrategy.kl_divergence, gpytorch);
+ * out[0] += KL.  ws: 296 doubles. */
+int dsvgp_kl_f32(const float* m, const float* Ls_raw, int64_t ld, int Mq, double* out, double* ws, dsvgp_stream_t s);
+int dsvgp_kl_f64(const double* m, const double* Ls_raw, int64_t ld, int Mq, double* out, double* ws, dsvgp_stream_t s);
+
+/* gm = t - m/num_data ; gLs = tril(2 H^T) - (tril(Ls) - diag(1/Ls_ii))/num_data  (H = Ls^T G) */
+int dsvgp_var_grads_f32(const float* H, int64_t ldh, const float* Ls_raw, int64_t ldl, const float* t, const float* m, int Mq, double inv_num_data, float* gm, float* gLs, int64_t ldg, dsvgp_stream_t s);
+int dsvgp_var_grads_f64(const double* H, int64_t ldh, const double* Ls_raw, int64_t ldl, const double* t, const double* m, int Mq, double inv_num_data, double* gm, double* gLs, int64_t ldg, dsvgp_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSVGP_B200_H */
