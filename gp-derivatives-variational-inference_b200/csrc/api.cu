@@ -9,9 +9,12 @@
 using namespace dsvgp;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+namespace dsvgp { unsigned long long g_launch_count = 0; }
+
 extern "C" {
 
 int dsvgp_version(void) { return 100; }
+int64_t dsvgp_launch_count(void) { return (int64_t)dsvgp::g_launch_count; }
 int dsvgp_built_for_sm(void) { return 100; }
 
 int dsvgp_hyp_from_raw_f32(const float* a, const float* b, const float* c, const float* d, double* hyp, dsvgp_stream_t s) { return hyp_from_raw<float>(a, b, c, d, hyp, ST(s)); }
@@ -55,11 +58,11 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
   return chol_factor_inverse(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, ST(s));
 }
 
-int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, dsvgp_stream_t s) {
-  return gemm<float>(ta != 0, tb != 0, M, N, K, (float)alpha, A, lda, B, ldb, (float)beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd);
+int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s) {
+  return gemm<float>(ta != 0, tb != 0, M, N, K, (float)alpha, A, lda, B, ldb, (float)beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd, C2, ldc2, D2, ldd2);
 }
-int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, dsvgp_stream_t s) {
-  return gemm<double>(ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd);
+int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, double* C2, int64_t ldc2, const double* D2, int64_t ldd2, dsvgp_stream_t s) {
+  return gemm<double>(ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd, C2, ldc2, D2, ldd2);
 }
 
 int dsvgp_cast_f64_f32(const double* a, int64_t lda, float* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<double, float>(a, lda, b, ldb, r, c, tril, ST(s)); }
@@ -70,6 +73,8 @@ int dsvgp_mirror_lower_f32(float* A, int64_t ld, int n, dsvgp_stream_t s) { retu
 int dsvgp_mirror_lower_f64(double* A, int64_t ld, int n, dsvgp_stream_t s) { return mirror_lower<double>(A, ld, n, ST(s)); }
 int dsvgp_add_outer_f32(float* A, int64_t ld, int n, const float* u, const float* v, double alpha, dsvgp_stream_t s) { return add_outer<float>(A, ld, n, u, v, alpha, ST(s)); }
 int dsvgp_add_outer_f64(double* A, int64_t ld, int n, const double* u, const double* v, double alpha, dsvgp_stream_t s) { return add_outer<double>(A, ld, n, u, v, alpha, ST(s)); }
+int dsvgp_tril_minus_eye_f32(const float* Ls, int64_t ldl, float* E, int64_t lde, int n, dsvgp_stream_t s) { return tril_minus_eye<float>(Ls, ldl, E, lde, n, ST(s)); }
+int dsvgp_tril_minus_eye_f64(const double* Ls, int64_t ldl, double* E, int64_t lde, int n, dsvgp_stream_t s) { return tril_minus_eye<double>(Ls, ldl, E, lde, n, ST(s)); }
 int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return sym_phi(Y, ldy, P, ldp, n, ST(s)); }
 
 int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }

@@ -11,8 +11,11 @@
 #define DSVGP_MAXP_FAST 3     // compile-time direction counts of the blocked assembly kernels
 #define DSVGP_MAXP 64         // runtime-p fallback limit
 
+// every kernel launch of the library goes through CHECK_LAUNCH, which also counts it (dsvgp_launch_count)
+namespace dsvgp { extern unsigned long long g_launch_count; }
 #define CHECK_LAUNCH()                                      \
   do {                                                      \
+    ++::dsvgp::g_launch_count;                              \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return DSVGP_ERR_LAUNCH;        \
   } while (0)

@@ -37,8 +37,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 template <typename T>
 struct GemmParams {
   const T* A; const T* B; T* C; const T* D;   // D: addend scaled by beta (== C unless given)
+  T* C2; const T* D2;                          // optional second output C2 = C + D2 (not batched)
   int M, N, K;
-  int64_t lda, ldb, ldc, ldd, sA, sB, sC;
+  int64_t lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC;
   T alpha, beta;
   int a_tri, b_tri, c_tri;
 };
@@ -115,7 +116,11 @@ gemm_kernel(GemmParams<T> p) {
 
   constexpr bool F64 = sizeof(T) == 8;
   // accumulators: fp64 4x4 m8n8 tiles x 2 ; fp32 2x4 m16n8 tiles x 4
-  double acc64[F64 ? 4 : 1][F64 ? 4 : 1][2];
+  // fp32 path: the tensor-core accumulation chain is kept to ONE k-tile (2 mma steps); the running sum lives in
+  // fp64 registers.  A long fp32 tensor-core chain loses ~1e-6 of |A||B| (measured, K = 3072), which the
+  // ill-conditioned whitening product W*K_zx amplifies ~400x; with the fp64 master sum the error is set by the
+  // 3xTF32 products alone.
+  double acc64[F64 ? 4 : 2][4][F64 ? 2 : 4];
   float acc32[F64 ? 1 : 2][F64 ? 1 : 4][4];
   if constexpr (F64) {
 #pragma unroll
@@ -128,7 +133,7 @@ gemm_kernel(GemmParams<T> p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc32[i][j][q] = 0.f;
+        for (int q = 0; q < 4; ++q) acc64[i][j][q] = 0.0;
   }
 
   if (kbeg < kend) {
@@ -155,6 +160,12 @@ gemm_kernel(GemmParams<T> p) {
             for (int j = 0; j < 4; ++j) mma_f64(acc64[i][j], af[i], bf[j]);
         }
       } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc32[i][j][q] = 0.f;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 8) {
           uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
@@ -188,6 +199,12 @@ gemm_kernel(GemmParams<T> p) {
               mma_tf32(acc32[i][j], ah[i], bh[j]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc64[i][j][q] += (double)acc32[i][j][q];
       }
       if (more) {
         store_tiles(buf ^ 1);
@@ -201,7 +218,9 @@ gemm_kernel(GemmParams<T> p) {
   auto put = [&](int r, int c, T v) {
     if (r < p.M && c < p.N) {
       T* dst = C + (int64_t)r * p.ldc + c;
-      *dst = (p.beta == T(0)) ? p.alpha * v : p.alpha * v + p.beta * D[(int64_t)r * ldd + c];
+      const T res = (p.beta == T(0)) ? p.alpha * v : p.alpha * v + p.beta * D[(int64_t)r * ldd + c];
+      *dst = res;
+      if (p.C2) p.C2[(int64_t)r * p.ldc2 + c] = res + p.D2[(int64_t)r * p.ldd2 + c];
     }
   };
   if constexpr (F64) {
@@ -219,10 +238,10 @@ gemm_kernel(GemmParams<T> p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = m0 + wm + 16 * i + g, c = n0 + wn + 8 * j + 2 * t;
-        put(r, c, (T)acc32[i][j][0]);
-        put(r, c + 1, (T)acc32[i][j][1]);
-        put(r + 8, c, (T)acc32[i][j][2]);
-        put(r + 8, c + 1, (T)acc32[i][j][3]);
+        put(r, c, (T)acc64[i][j][0]);
+        put(r, c + 1, (T)acc64[i][j][1]);
+        put(r + 8, c, (T)acc64[i][j][2]);
+        put(r + 8, c + 1, (T)acc64[i][j][3]);
       }
   }
 }
@@ -230,10 +249,10 @@ gemm_kernel(GemmParams<T> p) {
 template <typename T>
 int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
          T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
-         cudaStream_t st, const T* D, int64_t ldd) {
+         cudaStream_t st, const T* D, int64_t ldd, T* C2, int64_t ldc2, const T* D2, int64_t ldd2) {
   if (M <= 0 || N <= 0 || batch <= 0) return DSVGP_OK;
-  if (!A || !B || !C || K < 0) return DSVGP_ERR_ARG;
-  GemmParams<T> p{A, B, C, D, M, N, K, lda, ldb, ldc, ldd, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri};
+  if (!A || !B || !C || K < 0 || (C2 && !D2)) return DSVGP_ERR_ARG;
+  GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
   if (!ta && !tb) gemm_kernel<T, false, false><<<grid, GEMM_THREADS, 0, st>>>(p);
   else if (!ta && tb) gemm_kernel<T, false, true><<<grid, GEMM_THREADS, 0, st>>>(p);
@@ -244,8 +263,10 @@ int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda
 }
 
 template int gemm<float>(bool, bool, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*,
-                         int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const float*, int64_t);
+                         int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const float*, int64_t, float*, int64_t,
+                         const float*, int64_t);
 template int gemm<double>(bool, bool, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
-                          double*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const double*, int64_t);
+                          double*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const double*, int64_t,
+                          double*, int64_t, const double*, int64_t);
 
 }  // namespace dsvgp

@@ -71,6 +71,13 @@ __global__ void add_outer_kernel(T* A, int64_t ld, int n, const T* __restrict__ 
   A[(int64_t)i * ld + j] += alpha * u[i] * v[j];
 }
 
+template <typename T>
+__global__ void tril_minus_eye_kernel(const T* __restrict__ Ls, int64_t ldl, T* __restrict__ E, int64_t lde, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n || i >= n) return;
+  E[(int64_t)i * lde + j] = (j > i) ? T(0) : Ls[(int64_t)i * ldl + j] - (i == j ? T(1) : T(0));
+}
+
 // Psi = 0.5*(Phi + Phi^T), Phi = tril(Y) with halved diagonal  (symmetrised Cholesky-backward middle factor)
 __global__ void sym_phi_kernel(const double* __restrict__ Y, int64_t ldy, double* __restrict__ P, int64_t ldp, int n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -120,7 +127,8 @@ col_dots_kernel(const T* __restrict__ A, const T* __restrict__ C, int64_t ld, in
   }
 }
 
-// partial column sums  pq[s][j] = sum_i (B_ij^2 - A_ij^2)  (prediction path: no backward, so C is never formed)
+// partial column sums  pv[s][j] = sum_i B'_ij (2 A_ij + B'_ij) = sum_i (B_ij^2 - A_ij^2) with B' = B - A
+// (prediction path: no backward, so C is never formed)
 template <typename T>
 __global__ void __launch_bounds__(256)
 col_sqdiff_kernel(const T* __restrict__ A, const T* __restrict__ B, int64_t ld, int rows, int nq,
@@ -132,9 +140,9 @@ col_sqdiff_kernel(const T* __restrict__ A, const T* __restrict__ B, int64_t ld, 
   T am = 0, av = 0;
   if (j < nq) {
     for (int i = r0 + rl; i < r1; i += 4) {
-      const T a = A[(int64_t)i * ld + j], b = B[(int64_t)i * ld + j];
+      const T a = A[(int64_t)i * ld + j], bp = B[(int64_t)i * ld + j];    // bp = B' = (L_s^T - I) A
       am += a * m[i];
-      av += (b - a) * (b + a);
+      av += bp * (a + a + bp);
     }
   }
   sm[rl][cl] = am;
@@ -359,6 +367,15 @@ int add_outer(T* A, int64_t ld, int n, const T* u, const T* v, double alpha, cud
   return DSVGP_OK;
 }
 
+template <typename T>
+int tril_minus_eye(const T* Ls, int64_t ldl, T* E, int64_t lde, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 256), n);
+  tril_minus_eye_kernel<T><<<grid, 256, 0, st>>>(Ls, ldl, E, lde, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
 int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st) {
   if (n <= 0) return DSVGP_OK;
   dim3 grid(ceil_div(n, 256), n);
@@ -467,6 +484,7 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
 #define INST(T)                                                                                                    \
   template int hyp_from_raw<T>(const T*, const T*, const T*, const T*, double*, cudaStream_t);                     \
   template int mirror_lower<T>(T*, int64_t, int, cudaStream_t);                                                    \
+  template int tril_minus_eye<T>(const T*, int64_t, T*, int64_t, int, cudaStream_t);                                                    \
   template int add_outer<T>(T*, int64_t, int, const T*, const T*, double, cudaStream_t);                           \
   template int col_dots<T>(const T*, const T*, const T*, int64_t, int, int, const T*, T*, T*, int, cudaStream_t);  \
   template int predict_finish<T>(const T*, const T*, int, int, int, const double*, double, int, double, T*, T*,    \

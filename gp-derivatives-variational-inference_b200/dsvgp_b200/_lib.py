@@ -16,7 +16,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "dsvgp
 
 _CTYPES = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
            "dsvgp_stream_t": ctypes.c_void_p, "void": None}
-_PROTO = re.compile(r"^(int|void|size_t)\s+(dsvgp_\w+)\s*\(([^;]*)\)\s*;", re.M)
+_PROTO = re.compile(r"^(int|void|size_t|int64_t)\s+(dsvgp_\w+)\s*\(([^;]*)\)\s*;", re.M)
 
 ERRORS = {-1: "DSVGP_ERR_ARG (bad argument)", -2: "DSVGP_ERR_LAUNCH (CUDA launch failed)",
           -3: "DSVGP_ERR_WORKSPACE (workspace too small)"}
@@ -100,3 +100,8 @@ def chol_plan(Mq):
 
 def version():
     return _lib.dsvgp_version()
+
+
+def launch_count():
+    """CUDA kernels launched by the library so far in this process."""
+    return int(_lib.dsvgp_launch_count())

@@ -1,0 +1,53 @@
+"""Data-parallel DSVGP step: one process per GPU, the minibatch sharded over ranks, ONE exchange per step.
+
+The reference has no distributed code; this is the only parallelism the hot path needs
+(section 8e).  Rank r takes a contiguous shard of the minibatch.  Everything of size proportional to n (K_zx, A, B, C,
+mean, variance, residuals, and their backward up to the weighted Gram matrix G = A diag(g) A^T) is local.  What is
+summed over ranks, once per step, are two buffers the engine lays out contiguously for exactly this purpose:
+
+    big   = [ G (M'^2) | t (M') ]                         model dtype
+    small = [ scalars (8) | dZ (M d) | dV_z (M p d) ]     float64   (data term, d noise, d c, and the K_zx-backward
+                                                                     contributions to Z, V_z, lengthscale, outputscale)
+
+after which every rank runs the identical O(M'^3) tail (Cholesky backward is linear in its upstream gradient, so
+reduce-then-tail equals tail-then-reduce) and ends with identical parameter gradients -- no second collective.
+The data term is normalised by the GLOBAL n' (the reference divides by the batch's event size, VariationalELBO).
+"""
+import torch
+import torch.distributed as dist
+
+from .engine import ENGINE
+
+
+def shard_bounds(n, rank, world_size):
+    """Contiguous, balanced [lo, hi) of a length-n minibatch for `rank` (first n % world ranks get one extra)."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_reduce_payload(big, small, group=None):
+    """Sum the two engine buffers over `group`.  `big` may be None (forward-only evaluation of the ELBO)."""
+    if big is not None:
+        dist.all_reduce(big, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
+
+
+def enable(model, n_global, group=None):
+    """Make every subsequent ELBO step of `model` a shard of a global minibatch of `n_global` points."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    model.variational_strategy._n_global = int(n_global)
+    ENGINE.reduce_hook = lambda big, small: all_reduce_payload(big, small, group)
+
+
+def disable(model):
+    model.variational_strategy._n_global = None
+    ENGINE.reduce_hook = None
+
+
+def broadcast_parameters(model, likelihood, src=0, group=None):
+    """Replicas must start from identical parameters (they stay identical because gradients are)."""
+    with torch.no_grad():
+        for t in list(model.state_dict().values()) + list(likelihood.state_dict().values()):
+            dist.broadcast(t, src=src, group=group)

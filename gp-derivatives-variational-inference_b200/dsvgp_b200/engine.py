@@ -70,7 +70,8 @@ class Workspace:
         Mq, nq = self.Mq, self.nq
         self.ldn = _round_up(max(nq, 1), 8)
         e = lambda *s, dt=T: torch.empty(*s, dtype=dt, device=device)
-        self.Kzx, self.A, self.B, self.C = (e(Mq, self.ldn) for _ in range(4))
+        self.Kzx, self.A, self.B, self.Bp, self.C = (e(Mq, self.ldn) for _ in range(5))
+        self.E, self.Hp = e(Mq, Mq), e(Mq, Mq)
         self.nslab = max(1, ops.reduce_slabs(Mq, nq))
         self.pm, self.pv = e(self.nslab, nq), e(self.nslab, nq)
         self.mu, self.var, self.gmu, self.gvar = e(nq), e(nq), e(nq), e(nq)
@@ -149,12 +150,15 @@ class Engine:
         Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
         ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx)
         ops.gemm(f.Wt, Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)                        # A = L^-1 K_zx
-        ops.gemm(P.Ls_raw, A, B, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)             # B = L_s^T A
+        # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
+        ops.tril_minus_eye(P.Ls_raw, ws.E)
+        ops.gemm(ws.E, A, ws.Bp, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq, C2=B if need_C else None,
+                 D2=A if need_C else None)
         if need_C:
-            ops.gemm(P.Ls_raw, B, C, a_tri=TRI_LOWER, beta=-1.0, D=A, M=Mq, N=nq, K=Mq)  # C = (S - I) A
+            ops.gemm(ws.E, B, C, a_tri=TRI_LOWER, beta=1.0, D=ws.Bp, M=Mq, N=nq, K=Mq)
             ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C)
         else:
-            ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, B=B)                              # sum_i B^2 - A^2
+            ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, Bp=ws.Bp)                         # sum_i B^2 - A^2
         ops.predict_finish(ws.pm, ws.pv, nq, ws.p2, f.hyp, ws.mu, ws.var, add_noise, PRED_JITTER)
 
     # ----------------------------------------------------------------------------------------------- backward
@@ -173,8 +177,8 @@ class Engine:
             self.reduce_hook(ws.big, ws.small)
         # ---- replicated tail: O(M'^3), identical on every rank
         W, L = f.W, f.L
-        ops.gemm(P.Ls_raw, ws.G, ws.H, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq)       # H = L_s^T G
-        ops.gemm(P.Ls_raw, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=-2.0, D=ws.G, M=Mq, N=Mq, K=Mq)
+        ops.gemm(ws.E, ws.G, ws.Hp, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq, C2=ws.H, D2=ws.G)   # H = L_s^T G
+        ops.gemm(ws.E, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=2.0, D=ws.Hp, M=Mq, N=Mq, K=Mq)  # 2 (S - I) G
         ops.add_outer(ws.X, P.m, ws.t, 1.0)                                              # X = dA A^T
         if T == F32:
             ops.cast2d(ws.X, ws.Xd)

@@ -288,7 +288,7 @@ class _ElboStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, x, Vx, y, *params):
         P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
-        want = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params)
+        want = any(ctx.needs_input_grad[4:])      # (grad mode is off inside forward; this is the reliable signal)
         elbo, grads, mean, var = ENGINE.elbo_step(P, x, Vx, y, cfg["num_data"], cfg["p"], cfg["p2"],
                                                   cfg["through_likelihood"], cfg.get("n_global"), want_grads=want)
         ctx.grads = grads

@@ -83,8 +83,9 @@ def kdir_bwd(x1, u1, inv1, p1, x2, w2, p2, hyp, dK, gx, gv, gsc, use_os=True, dk
 
 
 def gemm(A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, a_tri=TRI_NONE, b_tri=TRI_NONE, c_tri=0, D=None,
-         M=None, N=None, K=None):
-    """C[:M,:N] = alpha*op(A)[:M,:K] @ op(B)[:K,:N] + beta*(D or C).  Triangle flags: see include/dsvgp_b200.h."""
+         M=None, N=None, K=None, C2=None, D2=None):
+    """C[:M,:N] = alpha*op(A)[:M,:K] @ op(B)[:K,:N] + beta*(D or C); optionally also C2 = C + D2.
+    Triangle flags: see include/dsvgp_b200.h."""
     if M is None:
         M = A.shape[1] if ta else A.shape[0]
     if K is None:
@@ -92,7 +93,8 @@ def gemm(A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, a_tri=TRI_NONE, b_tri
     if N is None:
         N = B.shape[0] if tb else B.shape[1]
     call("dsvgp_gemm_" + suffix(C.dtype), int(ta), int(tb), M, N, K, float(alpha), A, _ld(A), B, _ld(B), float(beta),
-         C, _ld(C), a_tri, b_tri, c_tri, 1, 0, 0, 0, D, _ld(D) if D is not None else 0)
+         C, _ld(C), a_tri, b_tri, c_tri, 1, 0, 0, 0, D, _ld(D) if D is not None else 0,
+         C2, _ld(C2) if C2 is not None else 0, D2, _ld(D2) if D2 is not None else 0)
     return C
 
 
@@ -126,6 +128,12 @@ def add_outer(A, u, v, alpha=1.0, n=None):
     return A
 
 
+def tril_minus_eye(Ls_raw, E):
+    """E = tril(Ls_raw) - I."""
+    call("dsvgp_tril_minus_eye_" + suffix(E.dtype), Ls_raw, _ld(Ls_raw), E, _ld(E), E.shape[0])
+    return E
+
+
 def sym_phi(Y, P, n):
     call("dsvgp_sym_phi_f64", Y, _ld(Y), P, _ld(P), n)
     return P
@@ -135,7 +143,9 @@ def reduce_slabs(rows, cols):
     return call_raw("dsvgp_reduce_slabs", rows, cols)
 
 
-def col_dots(A, m, pm, pv, rows, nq, C=None, B=None):
+def col_dots(A, m, pm, pv, rows, nq, C=None, Bp=None):
+    """pm = A^T m partials; pv = sum A*C (C given) or sum Bp*(2A + Bp) (Bp = B - A given)."""
+    B = Bp
     nslab = pm.shape[0]
     call("dsvgp_col_dots_" + suffix(A.dtype), A, C, B, _ld(A), rows, nq, m, pm, pv, nslab)
 

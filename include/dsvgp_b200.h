@@ -43,6 +43,8 @@ typedef void* dsvgp_stream_t; /* cudaStream_t */
 /* library version (major*10000 + minor*100 + patch) and the compute capability it was built for (100) */
 int dsvgp_version(void);
 int dsvgp_built_for_sm(void);
+/* number of CUDA kernels this library has launched in this process (host-side counter) */
+int64_t dsvgp_launch_count(void);
 
 /* Positive()/GreaterThan(1e-4) transforms of gpytorch that the reference reaches through
  * self.lengthscale (RBFKernelDirectionalGrad.py:67), ScaleKernel.outputscale (directional_vi.py:56) and
@@ -90,9 +92,10 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 
 /* C = alpha*op(A)*op(B) + beta*C, triangle-aware, batched -- every dense product of the strategy
  * (DirectionalGradVariationalStrategy.py:181-205) and of its backward.  fp32 uses 3xTF32 (fp32-accurate).
- * D != NULL: C = alpha*op(A)*op(B) + beta*D (D not batched); D == NULL: the addend is C itself. */
-int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, dsvgp_stream_t s);
-int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, dsvgp_stream_t s);
+ * D != NULL: C = alpha*op(A)*op(B) + beta*D (D not batched); D == NULL: the addend is C itself.
+ * C2 != NULL: a second output C2 = C + D2 is written by the same epilogue (used for B' = E^T A, B = A + B'). */
+int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s);
+int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, double* C2, int64_t ldc2, const double* D2, int64_t ldd2, dsvgp_stream_t s);
 
 /* helpers on M' x M' matrices of the replicated tail */
 int dsvgp_cast_f64_f32(const double* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
@@ -103,10 +106,15 @@ int dsvgp_mirror_lower_f32(float* A, int64_t ld, int n, dsvgp_stream_t s);
 int dsvgp_mirror_lower_f64(double* A, int64_t ld, int n, dsvgp_stream_t s);
 int dsvgp_add_outer_f32(float* A, int64_t ld, int n, const float* u, const float* v, double alpha, dsvgp_stream_t s);
 int dsvgp_add_outer_f64(double* A, int64_t ld, int n, const double* u, const double* v, double alpha, dsvgp_stream_t s);
+/* E = tril(Ls_raw) - I: the variational factor enters every product as I + E so that (S - I) A = E B + E^T A is
+ * formed without the cancellation of Ls (Ls^T A) - A  (S = Ls Ls^T, B = A + E^T A). */
+int dsvgp_tril_minus_eye_f32(const float* Ls, int64_t ldl, float* E, int64_t lde, int n, dsvgp_stream_t s);
+int dsvgp_tril_minus_eye_f64(const double* Ls, int64_t ldl, double* E, int64_t lde, int n, dsvgp_stream_t s);
 int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s);
 
 /* predictive mean / diagonal variance (DirectionalGradVariationalStrategy.py:188,:192-205):
- *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or  sum (B_ij^2 - A_ij^2)  (B given)
+ *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or, with B' = B - A given in
+ *   the `B` slot, sum B'_ij (2 A_ij + B'_ij) = sum (B_ij^2 - A_ij^2)
  *   mu_j = sum_s pm + c ; var_j = kdiag_j + pred_jitter + sum_s pv [+ noise], clamped at min_var. */
 int dsvgp_reduce_slabs(int rows, int cols);
 int dsvgp_col_dots_f32(const float* A, const float* C, const float* B, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, dsvgp_stream_t s);
