@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the DSVGP minibatch hot path (BASELINE.json metric: DSVGP train points/s, ELBO fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C4|C5|C1] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A step is ONE ELBO forward+backward over one minibatch through the reference-facing API
+(`loss = -mll(likelihood(model(x, derivative_directions=V)), y); loss.backward()`), including the gradient
+all-reduce when N > 1, excluding the optimiser step and data loading.  Weak scaling: every
+rank owns `n_per_gpu` minibatch points; the data term is normalised by the global minibatch.
+
+One JSON line is printed by rank 0.  `value`: inputs already resident in HBM.  `e2e`: the same step with x, y, V
+copied from pinned host memory and the loss read back every step.  `roofline`: the dominant kernel (the whitening
+product A = L^-1 K_zx) timed alone with CUDA events, algorithmic flops M'^2 n' (triangular) against the 3xTF32
+useful peak = measured bf16 dense / 2 (TF32) / 3 (passes); `roofline_assembly`: the fused kernel-assembly kernel
+against measured HBM bandwidth.  `cpu_baseline` (rank 0, N = 1): the oracle's reference-structured step (four
+kernel evaluations incl. the full K_xx, fp64 Cholesky + two triangular solves, autograd backward) on the host cores
+for a bounded sample -- the reference's own minibatch size.  `--impl reference` times only that arm.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gp-derivatives-variational-inference_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {  # name: variant, d, M, p, dtype, N (dataset size), default per-GPU minibatch, reference minibatch
+    "C1": dict(variant="dsvgp", d=2, M=20, p=2, dtype="f32", N=600, n=200, n_ref=200,
+               desc="tests/test_dsvgp.py as shipped"),
+    "C2": dict(variant="dsvgp", d=3, M=512, p=1, dtype="f64", N=35000, n=4096, n_ref=500, desc="bunny-shaped"),
+    "C3": dict(variant="dsvgp", d=10, M=1024, p=2, dtype="f32", N=1000000, n=16384, n_ref=512,
+               desc="synthetic1-shaped, 1M points"),
+    "C4": dict(variant="dsvgp", d=60, M=800, p=3, dtype="f32", N=2048, n=2048, n_ref=512, desc="rover-shaped"),
+    "C5": dict(variant="dfree", d=18, M=1024, p=2, dtype="f32", N=500000, n=16384, n_ref=512, desc="uci_dfree-shaped"),
+}
+METRIC = "DSVGP train points/s (ELBO fwd+bwd)"
+
+
+def synth_batch(n, d, p, variant, dtype, device, seed):
+    """x ~ U[0,1]^d, canonical data directions, y = [f, df/dx_1..p] of f = sum_k sin(2 pi x_k^2) (O(1) values)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64)
+    f = torch.sin(2 * math.pi * x * x).sum(1, keepdim=True)
+    grad = 4 * math.pi * x * torch.cos(2 * math.pi * x * x)
+    if variant == "dfree":
+        y = f.reshape(-1)
+    elif variant == "grad":
+        y = torch.cat([f, grad], 1).reshape(-1)
+    else:
+        y = torch.cat([f, grad[:, :p]], 1).reshape(-1)
+    V = torch.eye(d, dtype=torch.float64)[:p].repeat(n, 1)
+    return x.to(dtype), V.to(dtype), y.to(dtype)
+
+
+def synth_params(d, M, p, dtype, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Z = torch.rand(M, d, generator=g, dtype=torch.float64)
+    Vz = torch.eye(d, dtype=torch.float64)[:p].repeat(M, 1) + 0.1 * torch.randn(M * p, d, generator=g, dtype=torch.float64)
+    Mq = M * (p + 1)
+    m = 1e-3 * torch.randn(Mq, generator=g, dtype=torch.float64)
+    Ls = torch.eye(Mq, dtype=torch.float64) + 0.01 * torch.randn(Mq, Mq, generator=g, dtype=torch.float64).tril()
+    return dict(Z=Z.to(dtype), Vz=Vz.to(dtype), m=m.to(dtype), Ls_raw=Ls.to(dtype))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/dsvgp_clocks_{os.getpid()}.csv"
+
+    def __enter__(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.proc.wait()
+            self.f.close()
+
+    def summary(self):
+        rows = []
+        try:
+            for line in open(self.path):
+                c = [t.strip() for t in line.split(",")]
+                if len(c) >= 9:
+                    rows.append(c)
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), bf16_burst=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    except (OSError, KeyError, ValueError):
+        return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the named kernel from the committed ncu summary of this round, if present."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except (OSError, ValueError):
+        return None
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(wl, steps, warmup):
+    """The reference's algorithm on the host cores: oracle, reference op structure, fwd + autograd bwd."""
+    from oracle import dsvgp_oracle as O            # the one place bench.py executes oracle/
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dtype = torch.float64 if wl["dtype"] == "f64" else torch.float32
+    n = wl["n_ref"]
+    x, V, y = synth_batch(n, wl["d"], wl["p"], wl["variant"], dtype, "cpu", 123)
+    sp = synth_params(wl["d"], wl["M"], wl["p"], dtype)
+    z = lambda *s: torch.zeros(*s, dtype=dtype)
+    P = O.Params(Z=sp["Z"], Vz=sp["Vz"], m=sp["m"], Ls_raw=sp["Ls_raw"], c=z(1), raw_os=z(()), raw_ell=z(1, 1), raw_noise=z(1))
+    num_data = (wl["d"] + 1) * wl["N"]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.elbo_and_grads(P, x, V, y, num_data, wl["variant"], structure="reference")
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return dict(value=n / t, unit="points/s", cores=cores, kind="port", ms_per_step=1e3 * t,
+                sample=f"reference-structured oracle step (4 kernel evaluations incl. full K_xx, fp64 Cholesky + 2 triangular "
+                       f"solves, autograd backward) at the reference's minibatch n={n}, same d/M/p/dtype; median of {steps} "
+                       f"after {warmup} warm-up; torch {torch.__version__} CPU, {cores} threads")
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def build_model(wl, dtype, device):
+    import dfree_directional_vi
+    import directional_vi
+    from dsvgp_b200 import gp
+    sp = synth_params(wl["d"], wl["M"], wl["p"], dtype)
+    cls = dfree_directional_vi.GPModel if wl["variant"] == "dfree" else directional_vi.GPModel
+    model = cls(sp["Z"], sp["Vz"], wl["d"]).to(device=device, dtype=dtype)
+    lik = gp.GaussianLikelihood().to(device=device, dtype=dtype)
+    vs = model.variational_strategy
+    with torch.no_grad():
+        vs._variational_distribution.variational_mean.copy_(sp["m"])
+        vs._variational_distribution.chol_variational_covar.copy_(sp["Ls_raw"])
+        vs.variational_params_initialized.fill_(1)
+    model.train(), lik.train()
+    return model, lik
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-per-gpu", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.n_per_gpu:
+        wl["n"] = args.n_per_gpu
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    config = {"workload": f"{args.workload} {wl['desc']}: d={wl['d']} M={wl['M']} p={wl['p']} M'={wl['M'] * (wl['p'] + 1)} "
+                          f"{wl['dtype']} N={wl['N']}", "n_per_gpu": wl["n"], "global_batch": wl["n"] * world,
+              "variant": wl["variant"], "parallelism": f"dp{world}", "l2_policy": "inputs_exceed_l2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_arm(wl, args.steps, args.warmup)
+        config["n_per_gpu"] = config["global_batch"] = wl["n_ref"]
+        config["parallelism"] = "cpu"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"],
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the hot path has no CPU implementation")
+    import torch.distributed as dist
+    from dsvgp_b200 import _lib, distributed, gp, ops
+    from dsvgp_b200.engine import ENGINE
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    dtype = torch.float64 if wl["dtype"] == "f64" else torch.float32
+    n, d, M, p = wl["n"], wl["d"], wl["M"], wl["p"]
+    p2 = 0 if wl["variant"] == "dfree" else p
+    model, lik = build_model(wl, dtype, device)
+    if world > 1:
+        distributed.broadcast_parameters(model, lik)
+        distributed.enable(model, n * world)
+    mll = gp.VariationalELBO(lik, model, num_data=(d + 1) * wl["N"])
+    xh, Vh, yh = (t.pin_memory() for t in synth_batch(n, d, p, wl["variant"], dtype, "cpu", 1000 + rank))
+    x, V, y = xh.to(device), Vh.to(device), yh.to(device)
+    params = list(model.parameters()) + list(lik.parameters())
+
+    def step(xb, Vb, yb):
+        for q in params:
+            q.grad = None
+        loss = -mll(lik(model(xb, derivative_directions=Vb)), yb)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / k
+
+    for _ in range(warmup):
+        step(x, V, y)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_step = timed(lambda: step(x, V, y), args.steps)
+    launches = _lib.launch_count() - launches0
+
+    def e2e_step():
+        xb, Vb, yb = xh.to(device, non_blocking=True), Vh.to(device, non_blocking=True), yh.to(device, non_blocking=True)
+        return float(step(xb, Vb, yb).item())            # device -> host read of the step's loss
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(t.numel() * t.element_size() for t in (xh, Vh, yh))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    Mq, nq = M * (p + 1), n * (p2 + 1)
+    ws = ENGINE.workspace(device, dtype, n, d, M, p, p2)
+    fac = ENGINE.factor(device, dtype, d, M, p)
+    # dominant kernel alone: A = W K_zx (lower-triangular W), algorithmic flops M'^2 n'
+    wx = ops.normalize_dirs(V, dtype)[0] if p2 else None
+    P_Z = model.variational_strategy.inducing_points.detach()
+    ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx)
+    reps = 5
+
+    def timed_local(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+    ms_gemm = timed_local(lambda: ops.gemm(fac.Wt, ws.Kzx, ws.A, a_tri=ops.TRI_LOWER, M=Mq, N=nq, K=Mq), reps)
+    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
+    s = 8 if dtype == torch.float64 else 4
+    gemm_flops = float(Mq) * Mq * nq
+    if dtype == torch.float64:
+        tensor_peak, peak_note = 40.0, "nominal B200 fp64 (DMMA) 40 TFLOP/s -- no measured fp64 peak in MEASURED_PEAKS.json"
+    else:
+        tensor_peak = pk["bf16_sustained"] / 2 / 3
+        peak_note = f"{pk['src']} bf16 dense sustained {pk['bf16_sustained']} TFLOP/s / 2 (TF32 rate) / 3 (3xTF32 passes)"
+    asm_bytes = s * (float(Mq) * nq + (M + n) * d + (M * p + n * p2) * d)
+    out = {
+        "metric": METRIC, "value": n * world / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": wl["dtype"], "data": "synthetic", "config": config, "impl": "b200",
+        "e2e": {"value": n * world / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4 + (8 if dtype == torch.float64 else 4)},
+        "gpu_launches": launches, "launches_per_step": launches / args.steps,
+        "clocks": clk.summary(),
+        "roofline": {"kernel": "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)" if dtype != torch.float64
+                     else "gemm_kernel (A = L^-1 K_zx, fp64 DMMA)", "bound": "tensor",
+                     "achieved": gemm_flops / (ms_gemm * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": gemm_flops / (ms_gemm * 1e-3) / 1e12 / tensor_peak, "traffic": ncu_traffic("gemm_whiten"),
+                     "ms": ms_gemm, "flops_per_launch": gemm_flops, "peak_note": peak_note},
+        "roofline_assembly": {"kernel": "kdir_fwd_blocked (K_zx)", "bound": "hbm", "achieved": asm_bytes / (ms_asm * 1e-3) / 1e9,
+                              "peak": pk["hbm"], "unit": "GB/s", "frac": asm_bytes / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
+                              "traffic": ncu_traffic("kdir_fwd"), "ms": ms_asm, "bytes_per_launch": asm_bytes,
+                              "peak_note": f"{pk['src']} copy bandwidth"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_arm(wl, 3, 1)
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
