@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "kdir.cuh"
 #include "misc.cuh"
+#include "trmm_tc.cuh"
 
 using namespace dsvgp;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -64,6 +65,13 @@ int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const floa
 int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, double* C2, int64_t ldc2, const double* D2, int64_t ldd2, dsvgp_stream_t s) {
   return gemm<double>(ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd, C2, ldc2, D2, ldd2);
 }
+
+int dsvgp_gemm_tc_supported_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N) { return gemm_tc_supported(A, lda, B, ldb, b_kmajor, N); }
+int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo, int nsplit, float* split_ws, dsvgp_stream_t s) {
+  return gemm_tc(Ah, Al, lda, Bh, Bl, ldb, b_kmajor, M, N, K, (float)alpha, (float)beta, C, ldc, D, ldd, C2, ldc2, D2, ldd2, a_tri, c_lower, chunk, Clo, C2lo, nsplit, split_ws, ST(s));
+}
+int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s) { return split_lo(x, ldx, lo, ldl, rows, cols, ST(s)); }
+int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s) { return transpose_f32(src, lds, dst, ldd, rows, cols, ST(s)); }
 
 int dsvgp_cast_f64_f32(const double* a, int64_t lda, float* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<double, float>(a, lda, b, ldb, r, c, tril, ST(s)); }
 int dsvgp_cast_f32_f64(const float* a, int64_t lda, double* b, int64_t ldb, int r, int c, int tril, dsvgp_stream_t s) { return cast2d<float, double>(a, lda, b, ldb, r, c, tril, ST(s)); }

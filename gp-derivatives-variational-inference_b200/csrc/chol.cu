@@ -28,63 +28,140 @@ void chol_plan(int Mq, int* Mp, int* nb0, int* nlev) {
   *nlev = k;
 }
 
-// factorise the nb x nb block at A (lower part read), write L block (upper zeroed) and its inverse W block
+// Factorise the nb x nb block at A (lower part read) and invert the factor, both inside one CTA in shared memory,
+// blocked by 8 columns so that almost all work is rank-8 updates (8 FMAs per shared-memory element touched) and only
+// 2 block barriers per 8 columns are on the critical path:
+//   factor : (A) one warp factors the 8x8 diagonal block in registers (pivots and multipliers move by shuffles),
+//            (B) one thread per row solves the 8-column panel, (C) all threads apply the rank-8 trailing update.
+//   inverse: block row I:  T = L[I,0:I] * W[0:I,0:I],  D = inv(L[I,I]) (one warp),  W[I,0:I] = -D * T,  W[I,I] = D.
+// The block is padded to a multiple of 8 with the identity.  Writes L (upper part zeroed) and W = L^-1.
 __global__ void __launch_bounds__(POTRF_THREADS)
 potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl,
                 double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int ld = nb + 1;
-  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nb][ld]
-  double* Ws = Ls + nb * ld;                          // [nb][ld]
-  double* dg = Ws + nb * ld;                          // [nb]
-  const int tid = threadIdx.x;
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int i = e / nb, c = e % nb;
-    Ls[i * ld + c] = (c <= i) ? A[(int64_t)i * lda + c] : 0.0;
-    Ws[i * ld + c] = 0.0;
-  }
-  for (int j = 0; j < nb; ++j) {
+  const int nbp = (nb + 7) & ~7, ld = nbp + 1;
+  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
+  double* Ws = Ls + nbp * ld;                         // [nbp][ld]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 31, ty = tid >> 5;             // 32 x 16 mapping of the trailing update
+  for (int i = ty; i < nbp; i += 16)
+    for (int c = tx; c < nbp; c += 32) {
+      Ls[i * ld + c] = (c <= i) ? ((i < nb) ? A[(int64_t)i * lda + c] : (i == c ? 1.0 : 0.0)) : 0.0;
+      Ws[i * ld + c] = 0.0;
+    }
+  // ------------------------------------------------------------------------------------------------ factor
+  for (int k0 = 0; k0 < nbp; k0 += 8) {
     __syncthreads();
-    const double djj = Ls[j * ld + j];
-    double ljj;
-    if (!(djj > 0.0)) {          // also catches NaN
-      if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
-      ljj = nan("");
-    } else {
-      ljj = sqrt(djj);
+    if (warp == 0) {                                   // (A) lanes r = lane & 7 hold row r of the diagonal block
+      const int r = lane & 7;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = Ls[(k0 + r) * ld + k0 + c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double d = __shfl_sync(0xffffffffu, a[k], k);
+        double ljj;
+        if (!(d > 0.0)) {                              // also catches NaN
+          if (lane == 0) atomicCAS(info, 0, row_offset + k0 + k + 1);
+          ljj = nan("");
+        } else {
+          ljj = sqrt(d);
+        }
+        if (r == k) a[k] = ljj;
+        else if (r > k) a[k] = a[k] / ljj;
+#pragma unroll
+        for (int c = k + 1; c < 8; ++c) {
+          const double lck = __shfl_sync(0xffffffffu, a[k], c);
+          if (r >= c) a[c] -= a[k] * lck;
+        }
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c <= r) Ls[(k0 + r) * ld + k0 + c] = a[c];
+      }
     }
-    if (tid == 0) dg[j] = ljj;
-    const double inv = 1.0 / ljj;
-    for (int i = j + 1 + tid; i < nb; i += POTRF_THREADS) Ls[i * ld + j] *= inv;
     __syncthreads();
-    const int m = nb - j - 1;
-    for (int e = tid; e < m * m; e += POTRF_THREADS) {
-      const int i = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= i) Ls[i * ld + c] -= Ls[i * ld + j] * Ls[c * ld + j];
+    for (int i = k0 + 8 + tid; i < nbp; i += POTRF_THREADS) {      // (B) panel: x L11^T = a
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[c] = Ls[i * ld + k0 + c];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double sacc = x[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) sacc -= x[q] * Ls[(k0 + c) * ld + k0 + q];
+        x[c] = sacc / Ls[(k0 + c) * ld + k0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Ls[i * ld + k0 + c] = x[c];
+    }
+    __syncthreads();
+    const int t0 = k0 + 8;                                         // (C) rank-8 trailing update
+    for (int i = t0 + ty; i < nbp; i += 16) {
+      double li[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) li[q] = Ls[i * ld + k0 + q];
+      for (int c = t0 + tx; c <= i; c += 32) {
+        double sacc = Ls[i * ld + c];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc -= li[q] * Ls[c * ld + k0 + q];
+        Ls[i * ld + c] = sacc;
+      }
+    }
+  }
+  // ----------------------------------------------------------------------------------------------- inverse
+  for (int I0 = 0; I0 < nbp; I0 += 8) {
+    __syncthreads();
+    {                                                  // T[r][c] -> Ws[I0+r][c], c < I0
+      const int r = tid & 7;
+      for (int c = tid >> 3; c < I0; c += POTRF_THREADS / 8) {
+        double sacc = 0.0;
+        for (int k = c & ~7; k < I0; ++k) sacc += Ls[(I0 + r) * ld + k] * Ws[k * ld + c];
+        Ws[(I0 + r) * ld + c] = sacc;
+      }
+    }
+    if (warp == 0 && lane < 8) {                       // D = inv(L[I,I]): lane j solves column j
+      const int j = lane;
+      double x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k)
+          if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
+        x[i] = (i >= j) ? sacc / Ls[(I0 + i) * ld + I0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
+    }
+    __syncthreads();
+    {                                                  // W[I0+r][c] = -sum_{q<=r} D[r][q] T[q][c]  (in place, per 8-lane group)
+      const int r = tid & 7;
+      for (int c0 = 0; c0 < I0; c0 += POTRF_THREADS / 8) {
+        const int c = c0 + (tid >> 3);
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = (c < I0) ? Ws[(I0 + q) * ld + c] : 0.0;
+        __syncwarp();
+        if (c < I0) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q <= r) sacc -= Ws[(I0 + r) * ld + I0 + q] * t[q];
+          Ws[(I0 + r) * ld + c] = sacc;
+        }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
-  for (int j = tid; j < nb; j += POTRF_THREADS) Ls[j * ld + j] = dg[j];
-  __syncthreads();
-  // inverse by forward substitution, 4 threads per column (k-sum split 4 ways, combined by shuffles)
-  {
-    const int col = tid >> 2, part = tid & 3;
-    for (int i = 0; i < nb; ++i) {
-      double s = 0.0;
-      if (col < nb && col <= i)
-        for (int k = col + part; k < i; k += 4) s += Ls[i * ld + k] * Ws[k * ld + col];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && col < nb && col <= i) Ws[i * ld + col] = ((i == col ? 1.0 : 0.0) - s) / Ls[i * ld + i];
-      __syncwarp();
+  for (int i = ty; i < nb; i += 16)
+    for (int c = tx; c < nb; c += 32) {
+      L[(int64_t)i * ldl + c] = Ls[i * ld + c];
+      W[(int64_t)i * ldw + c] = Ws[i * ld + c];
     }
-  }
-  __syncthreads();
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int i = e / nb, c = e % nb;
-    L[(int64_t)i * ldl + c] = Ls[i * ld + c];
-    W[(int64_t)i * ldw + c] = Ws[i * ld + c];
-  }
 }
 
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
@@ -92,7 +169,8 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   if (Mp <= 0) return DSVGP_OK;
   if (!Awork || !L || !W || !info || nb0 <= 0 || nb0 > 128 || (nb0 << nlev) != Mp) return DSVGP_ERR_ARG;
   const int nblk = 1 << nlev;
-  const size_t smem = sizeof(double) * (size_t)(2 * nb0 * (nb0 + 1) + nb0);
+  const int nbp = (nb0 + 7) & ~7;
+  const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 1));
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(potrf_inv_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(info, 0, sizeof(int), st);

@@ -1,0 +1,25 @@
+// tcgen05 / TMA 3xTF32 GEMM (definitions in trmm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dsvgp {
+
+// 1 if the operands satisfy the TMA constraints (16-byte aligned bases, leading dims % 4 == 0, for a K x N
+// row-major B the last 32-column block inside the row) and the driver exposes cuTensorMapEncodeTiled.
+int gemm_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N);
+
+// C = alpha * A * B + beta * D (+ C2 = C + D2).  A: M x K row-major (zeros outside its triangle).  B: K x N row-major
+// (b_kmajor = 0) or N x K row-major (b_kmajor = 1).  *_lo = x - trunc_tf32(x) (split_lo).  a_tri: 1 lower / 2 upper
+// k-range trimming; c_lower: skip tiles above the diagonal; chunk: k-blocks (of 32) per tensor-core accumulation chain.
+int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor,
+            int M, int N, int K, float alpha, float beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2,
+            int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo,
+            int nsplit, float* split_ws, cudaStream_t st);
+// Clo / C2lo (optional): lo parts of C / C2 written by the same epilogue (operands of a following product).
+// nsplit > 1: split-K over gridDim.z; raw partial sums go to split_ws (nsplit * M * round_up(N,4) floats) and are
+// summed in fp64 by a second kernel (needs C2 == Clo == null).
+
+int split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, cudaStream_t st);
+int transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, cudaStream_t st);
+
+}  // namespace dsvgp

@@ -27,6 +27,8 @@ from .ops import F32, F64, TRI_LOWER, TRI_UPPER
 KZZ_JITTER = 1e-3          # add_jitter() default            DGVS.py:144
 PRED_JITTER = 1e-4         # data_data_covar.add_jitter(1e-4) DGVS.py:198,203
 CHOL_RETRY = (1e-6, 1e-5, 1e-4)   # psd_safe_cholesky(jitter=1e-6): 1e-6 * 10**i, i < 3   DGVS.py:74
+USE_TC = True      # fp32 model: run the big whitening products on tcgen05 (set False to force the mma.sync kernels)
+TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 
 
 class NanError(RuntimeError):
@@ -55,7 +57,13 @@ class Factor:
         self.hyp = e(8)
         self.info = torch.zeros(1, dtype=torch.int32, device=device)
         self.Kzz, self.L, self.W = e(self.Mp, self.Mp), e(self.Mp, self.Mp), e(self.Mp, self.Mp)
-        self.Wt = e(self.Mq, self.Mq, dt=dtype) if dtype == F32 else self.W      # W in the model dtype
+        self.ldm = _round_up(self.Mq, 8)
+        self.Wt = e(self.Mq, self.ldm, dt=dtype)[:, : self.Mq] if dtype == F32 else self.W   # W in the model dtype
+        # operands of the tcgen05 products (fp32 model): explicit transposes and "lo" parts (x - trunc_tf32(x))
+        self.tc = dtype == F32 and USE_TC
+        if self.tc:
+            mk = lambda: e(self.Mq, self.ldm, dt=dtype)[:, : self.Mq]
+            self.Wt_lo, self.WtT, self.WtT_lo = mk(), mk(), mk()
         self.uzT = self.invzT = self.uz64 = self.invz64 = None
         self.valid = False
 
@@ -68,25 +76,39 @@ class Workspace:
         self.n, self.d, self.M, self.p, self.p2 = n, d, M, p, p2
         self.Mq, self.nq = M * (p + 1), n * (p2 + 1)
         Mq, nq = self.Mq, self.nq
-        self.ldn = _round_up(max(nq, 1), 8)
+        self.ldn = _round_up(max(nq, 1), 32)       # whole 32-column TMA blocks inside every row
+        self.ldm = _round_up(Mq, 8)
+        self.ldg = _round_up(Mq, 32)
         e = lambda *s, dt=T: torch.empty(*s, dtype=dt, device=device)
         self.Kzx, self.A, self.B, self.Bp, self.C = (e(Mq, self.ldn) for _ in range(5))
-        self.E, self.Hp = e(Mq, Mq), e(Mq, Mq)
+        sq = lambda: e(Mq, self.ldm)[:, :Mq]
+        self.E, self.Hp = sq(), sq()
+        self.tc = T == F32 and USE_TC and Mq >= 128 and nq >= 256
+        if self.tc:
+            self.lo1, self.lo2 = e(Mq, self.ldn), e(Mq, self.ldn)        # "lo" parts of the current big operands
+            self.E_lo, self.ET, self.ET_lo = sq(), sq(), sq()
+            sg = lambda: e(Mq, self.ldg)[:, :Mq]
+            self.G_lo, self.H_lo = sg(), sg()
+            # split-K of the Gram product: its lower 128x256 tiles alone (156 at M' = 3072) leave the second wave of a
+            # 148-SM part nearly empty; 8 k-slices give 8.4 waves and an fp64 sum over the slices
+            self.syrk_split = max(1, min(8, self.nq // 4096))
+            self.split_ws = e(self.syrk_split * Mq * _round_up(Mq, 4)) if self.syrk_split > 1 else None
         self.nslab = max(1, ops.reduce_slabs(Mq, nq))
         self.pm, self.pv = e(self.nslab, nq), e(self.nslab, nq)
         self.mu, self.var, self.gmu, self.gvar = e(nq), e(nq), e(nq), e(nq)
         self.tp = e(max(1, min(64, nq // 2048)), Mq)
         # [G | t] (model dtype) and [scalars(8) | gZ | gVz] (double) are the two buffers summed over ranks.
         # scalars: 0 data term, 1 explicit dELBO/dnoise, 4 d ell, 5 d outputscale, 6 d noise via variance, 7 d c
-        self.big = e(Mq * Mq + Mq)
-        self.G, self.t = self.big[: Mq * Mq].view(Mq, Mq), self.big[Mq * Mq:]
+        self.big = torch.zeros(Mq * self.ldg + Mq, dtype=T, device=device)
+        self.G, self.t = self.big[: Mq * self.ldg].view(Mq, self.ldg)[:, :Mq], self.big[Mq * self.ldg:]
         self.small = torch.zeros(8 + M * d + M * p * d, dtype=F64, device=device)
         self.sc = self.small[:8]
         self.gZ = self.small[8: 8 + M * d].view(M, d)
         self.gVz = self.small[8 + M * d:].view(M * p, d) if p else None
         self.kl = torch.zeros(1, dtype=F64, device=device)
         self.scratch = e(8192, dt=F64)
-        self.H, self.X = e(Mq, Mq), e(Mq, Mq)
+        self.H = e(Mq, self.ldg)[:, :Mq] if T == F32 else sq()
+        self.X = sq()
         self.Xd = e(Mq, Mq, dt=F64) if T == F32 else self.X
         self.dL, self.Y, self.Psi, self.S = (e(Mq, Mq, dt=F64) for _ in range(4))
         self.gm, self.gLs = e(Mq), e(Mq, Mq)
@@ -131,6 +153,10 @@ class Engine:
         ops.cholesky_inverse(f.Kzz, f.L, f.W, f.nb0, f.nlev, f.info)
         if T == F32:
             ops.cast2d(f.W, f.Wt, f.Mq, f.Mq, tril=True)
+            if f.tc:
+                ops.split_lo(f.Wt, f.Wt_lo)
+                ops.transpose(f.Wt, f.WtT)
+                ops.split_lo(f.WtT, f.WtT_lo)
 
     @staticmethod
     def _check(f, P):
@@ -149,9 +175,26 @@ class Engine:
         Mq, nq = ws.Mq, ws.nq
         Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
         ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx)
-        ops.gemm(f.Wt, Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)                        # A = L^-1 K_zx
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
         ops.tril_minus_eye(P.Ls_raw, ws.E)
+        if ws.tc and f.tc:
+            # tcgen05 path: every operand as (raw, lo); A operands are explicit (transposed) triangular matrices
+            ops.split_lo(ws.E, ws.E_lo)
+            ops.transpose(ws.E, ws.ET)
+            ops.split_lo(ws.ET, ws.ET_lo)
+            ops.split_lo(Kzx, ws.lo1, Mq, nq)
+            ops.gemm_tc(f.Wt, f.Wt_lo, Kzx, ws.lo1, A, Mq, nq, Mq, a_tri=TRI_LOWER, chunk=TC_CHUNK,
+                        C_lo=ws.lo2)                                                     # A = L^-1 K_zx  (+ A_lo)
+            ops.gemm_tc(ws.ET, ws.ET_lo, A, ws.lo2, ws.Bp, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK,
+                        C2=B if need_C else None, D2=A if need_C else None, C2_lo=ws.lo1 if need_C else None)
+            if need_C:
+                ops.gemm_tc(ws.E, ws.E_lo, B, ws.lo1, C, Mq, nq, Mq, a_tri=TRI_LOWER, beta=1.0, D=ws.Bp, chunk=TC_CHUNK)
+                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C)
+            else:
+                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, Bp=ws.Bp)
+            ops.predict_finish(ws.pm, ws.pv, nq, ws.p2, f.hyp, ws.mu, ws.var, add_noise, PRED_JITTER)
+            return
+        ops.gemm(f.Wt, Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)                        # A = L^-1 K_zx
         ops.gemm(ws.E, A, ws.Bp, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq, C2=B if need_C else None,
                  D2=A if need_C else None)
         if need_C:
@@ -169,16 +212,33 @@ class Engine:
         A, Ag, C, dKzx = ws.A, ws.B, ws.C, ws.Kzx
         ops.pred_bwd_scalars(gmu, gvar, ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)
         ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t)                      # C <- dA ; Ag ; t = A gmu
-        ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)              # dK_zx = L^-T dA
+        tc = ws.tc and f.tc
+        if tc:
+            ops.split_lo(C, ws.lo1, Mq, nq)
+            ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
+        else:
+            ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
         ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
-        ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)                        # G = A diag(gvar) A^T
+        if tc:                                                                           # G = A diag(gvar) A^T
+            ops.split_lo(Ag, ws.lo1, Mq, nq)                                             # (A_lo is still in ws.lo2)
+            ops.gemm_tc(Ag, ws.lo1, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
+                        nsplit=ws.syrk_split, split_ws=ws.split_ws)
+        else:
+            ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)
         ops.mirror_lower(ws.G, Mq)
         if self.reduce_hook is not None:
             self.reduce_hook(ws.big, ws.small)
         # ---- replicated tail: O(M'^3), identical on every rank
         W, L = f.W, f.L
-        ops.gemm(ws.E, ws.G, ws.Hp, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq, C2=ws.H, D2=ws.G)   # H = L_s^T G
-        ops.gemm(ws.E, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=2.0, D=ws.Hp, M=Mq, N=Mq, K=Mq)  # 2 (S - I) G
+        if tc:
+            ops.split_lo(ws.G, ws.G_lo)
+            ops.gemm_tc(ws.ET, ws.ET_lo, ws.G, ws.G_lo, ws.Hp, Mq, Mq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK, C2=ws.H,
+                        D2=ws.G, C2_lo=ws.H_lo)                                          # H = L_s^T G = G + E^T G
+            ops.gemm_tc(ws.E, ws.E_lo, ws.H, ws.H_lo, ws.X, Mq, Mq, Mq, a_tri=TRI_LOWER, alpha=2.0, beta=2.0, D=ws.Hp,
+                        chunk=TC_CHUNK)                                                  # 2 (S - I) G
+        else:
+            ops.gemm(ws.E, ws.G, ws.Hp, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq, C2=ws.H, D2=ws.G)
+            ops.gemm(ws.E, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=2.0, D=ws.Hp, M=Mq, N=Mq, K=Mq)
         ops.add_outer(ws.X, P.m, ws.t, 1.0)                                              # X = dA A^T
         if T == F32:
             ops.cast2d(ws.X, ws.Xd)

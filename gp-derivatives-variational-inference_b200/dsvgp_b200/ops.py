@@ -98,6 +98,33 @@ def gemm(A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, a_tri=TRI_NONE, b_tri
     return C
 
 
+def split_lo(x, lo=None, rows=None, cols=None):
+    """lo = x - trunc_tf32(x) (the part of x the TF32 tensor core does not see)."""
+    lo = torch.empty_like(x) if lo is None else lo
+    call("dsvgp_split_lo_f32", x, _ld(x), lo, _ld(lo), x.shape[0] if rows is None else rows,
+         x.shape[1] if cols is None else cols)
+    return lo
+
+
+def transpose(src, dst, rows=None, cols=None):
+    call("dsvgp_transpose_f32", src, _ld(src), dst, _ld(dst), src.shape[0] if rows is None else rows,
+         src.shape[1] if cols is None else cols)
+    return dst
+
+
+def gemm_tc_supported(A, B, b_kmajor, N):
+    return bool(call_raw("dsvgp_gemm_tc_supported_f32", A, _ld(A), B, _ld(B), int(b_kmajor), int(N)))
+
+
+def gemm_tc(A, A_lo, B, B_lo, C, M, N, K, b_kmajor=False, alpha=1.0, beta=0.0, D=None, C2=None, D2=None, a_tri=TRI_NONE,
+            c_lower=False, chunk=2, C_lo=None, C2_lo=None, nsplit=1, split_ws=None):
+    """tcgen05 3xTF32 product C[:M,:N] = alpha * A[:M,:K] @ (B[:K,:N] or B[:N,:K]^T) + beta*D (+ C2 = C + D2)."""
+    call("dsvgp_gemm_tc_f32", A, A_lo, _ld(A), B, B_lo, _ld(B), int(b_kmajor), M, N, K, float(alpha), float(beta), C, _ld(C),
+         D, _ld(D) if D is not None else 0, C2, _ld(C2) if C2 is not None else 0, D2, _ld(D2) if D2 is not None else 0,
+         a_tri, int(c_lower), chunk, C_lo, C2_lo, int(nsplit), split_ws)
+    return C
+
+
 def chol_plan(Mq):
     return _lib.chol_plan(Mq)
 

@@ -97,6 +97,21 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s);
 int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, double* C2, int64_t ldc2, const double* D2, int64_t ldd2, dsvgp_stream_t s);
 
+/* The same product on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA-fed, accumulators in tensor memory)
+ * for the fp32 model's big whitening products -- TriangularLazyTensor.inv_matmul and the L_s products of
+ * DirectionalGradVariationalStrategy.py:181-205 and their backward.  A: M x K row-major with explicit zeros outside
+ * its triangle; B: K x N row-major (b_kmajor = 0) or N x K row-major (b_kmajor = 1, Gram matrices).  Every operand is
+ * given as the raw fp32 array plus lo = x - trunc_tf32(x) (dsvgp_split_lo_f32); 3 MMAs per k-step give fp32-grade
+ * products, `chunk` (k-blocks of 32) bounds the length of the tensor-core accumulation chain.  a_tri trims the k-range
+ * (1 lower, 2 upper), c_lower skips tiles above the diagonal.  Clo / C2lo (optional) receive the lo parts of C / C2 from
+ * the same epilogue.  nsplit > 1: split-K over gridDim.z with an fp64 reduction of the partial sums held in split_ws
+ * (nsplit * M * round_up(N,4) floats; requires C2 == Clo == NULL).  dsvgp_gemm_tc_supported_f32 tells whether the operands
+ * meet the TMA constraints (otherwise use dsvgp_gemm_f32). */
+int dsvgp_gemm_tc_supported_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N);
+int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo, int nsplit, float* split_ws, dsvgp_stream_t s);
+int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s);
+int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s);
+
 /* helpers on M' x M' matrices of the replicated tail */
 int dsvgp_cast_f64_f32(const double* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
 int dsvgp_cast_f32_f64(const float* src, int64_t lds, double* dst, int64_t ldd, int rows, int cols, int tril, dsvgp_stream_t s);
