@@ -298,7 +298,19 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / k
-    ms_gemm = timed_local(lambda: ops.gemm(fac.Wt, ws.Kzx, ws.A, a_tri=ops.TRI_LOWER, M=Mq, N=nq, K=Mq), reps)
+    from dsvgp_b200 import engine as _eng
+    use_tc = bool(getattr(ws, "tc", False) and getattr(fac, "tc", False))
+    if use_tc:
+        ops.split_lo(ws.Kzx, ws.lo1, Mq, nq)
+        whiten = lambda: ops.gemm_tc(fac.Wt, fac.Wt_lo, ws.Kzx, ws.lo1, ws.A, Mq, nq, Mq, a_tri=ops.TRI_LOWER,
+                                     chunk=_eng.TC_CHUNK, C_lo=ws.lo2)
+        kname = ("gemm_tc_kernel (A = L^-1 K_zx: tcgen05.mma kind::tf32 x3 (3xTF32), TMA-fed, TMEM accumulators restarted every "
+                 f"{_eng.TC_CHUNK} k-blocks, fp32 master sums)")
+    else:
+        whiten = lambda: ops.gemm(fac.Wt, ws.Kzx, ws.A, a_tri=ops.TRI_LOWER, M=Mq, N=nq, K=Mq)
+        kname = ("gemm_kernel (A = L^-1 K_zx, fp64 DMMA mma.sync)" if dtype == torch.float64
+                 else "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)")
+    ms_gemm = timed_local(whiten, reps)
     ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
     s = 8 if dtype == torch.float64 else 4
     gemm_flops = float(Mq) * Mq * nq
@@ -316,8 +328,7 @@ def main():
                 "d2h_bytes_per_step": 4 + (8 if dtype == torch.float64 else 4)},
         "gpu_launches": launches, "launches_per_step": launches / args.steps,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)" if dtype != torch.float64
-                     else "gemm_kernel (A = L^-1 K_zx, fp64 DMMA)", "bound": "tensor",
+        "roofline": {"kernel": kname, "bound": "tensor",
                      "achieved": gemm_flops / (ms_gemm * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": gemm_flops / (ms_gemm * 1e-3) / 1e12 / tensor_peak, "traffic": ncu_traffic("gemm_whiten"),
                      "ms": ms_gemm, "flops_per_launch": gemm_flops, "peak_note": peak_note},
