@@ -222,6 +222,28 @@ def test_cholesky_jitter_ladder_and_errors():
 
 
 @pytest.mark.parametrize("variant,n,d,M,p,dtype", [
+    ("dsvgp", 500, 3, 512, 1, F64),         # C2 bunny-shaped: full M, the reference's minibatch (bunny.sub:22), fp64
+    ("dsvgp", 512, 10, 1024, 2, F32),       # C3 synthetic1-shaped: full M, the reference's minibatch, tcgen05 path
+    ("dsvgp", 1024, 10, 1024, 2, F32),
+    ("dsvgp", 512, 60, 800, 3, F32),        # C4 rover-shaped, full M
+    ("dfree", 512, 18, 1024, 2, F32),       # C5 uci_dfree-shaped, full M
+])
+def test_full_size_matches_oracle(variant, n, d, M, p, dtype):
+    """BASELINE.json's full inducing sizes at the reference's own minibatch sizes against the fp64 CPU oracle
+    (1-2 s of oracle time each on the GPU box's host cores)."""
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed=1, variant=variant, N=100 * n)
+    up = lambda t: None if t is None else t.double()
+    P64 = P.clone(F64)
+    ref_val, ref_grads = O.elbo_and_grads(P64, up(x), up(Vx), up(y), num_data, variant)
+    model, lik, val, grads, out = run_step(variant, P, x, Vx, y, num_data, d, dtype)
+    f64 = dtype == F64
+    check_against(val, grads, ref_val, ref_grads, 1e-10 if f64 else 1e-4, 1e-10 if f64 else 1e-4)
+    mean, var = O.predict(P64, up(x), up(Vx), variant)
+    assert rel(out.mean, mean) < (1e-10 if f64 else 1e-4)
+    assert rel(out.variance, var) < (1e-10 if f64 else 1e-4)
+
+
+@pytest.mark.parametrize("variant,n,d,M,p,dtype", [
     ("dsvgp", 2048, 3, 512, 1, F64),        # C2 bunny-shaped, full M
     ("dsvgp", 2048, 10, 1024, 2, F32),      # C3 synthetic1-shaped, full M
     ("dsvgp", 1024, 60, 800, 3, F32),       # C4 rover-shaped, full M
