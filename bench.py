@@ -311,7 +311,8 @@ def main():
         kname = ("gemm_kernel (A = L^-1 K_zx, fp64 DMMA mma.sync)" if dtype == torch.float64
                  else "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)")
     ms_gemm = timed_local(whiten, reps)
-    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
+    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon), reps)
+    ms_asm_general = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
     s = 8 if dtype == torch.float64 else 4
     gemm_flops = float(Mq) * Mq * nq
     if dtype == torch.float64:
@@ -332,9 +333,12 @@ def main():
                      "achieved": gemm_flops / (ms_gemm * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": gemm_flops / (ms_gemm * 1e-3) / 1e12 / tensor_peak, "traffic": ncu_traffic("gemm_whiten"),
                      "ms": ms_gemm, "flops_per_launch": gemm_flops, "peak_note": peak_note},
-        "roofline_assembly": {"kernel": "kdir_fwd_blocked (K_zx)", "bound": "hbm", "achieved": asm_bytes / (ms_asm * 1e-3) / 1e9,
+        "roofline_assembly": {"kernel": "kdir_fwd_v4 / kdir_fwd_blocked (K_zx)", "bound": "hbm", "achieved": asm_bytes / (ms_asm * 1e-3) / 1e9,
                               "peak": pk["hbm"], "unit": "GB/s", "frac": asm_bytes / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
                               "traffic": ncu_traffic("kdir_fwd"), "ms": ms_asm, "bytes_per_launch": asm_bytes,
+                              "path": "canonical data-side directions (detected on device)" if ws.canon is not None else "general directions",
+                              "general_directions_ms": ms_asm_general,
+                              "general_directions_frac": asm_bytes / (ms_asm_general * 1e-3) / 1e9 / pk["hbm"],
                               "peak_note": f"{pk['src']} copy bandwidth"},
     }
     if world == 1 and not args.no_cpu_baseline:

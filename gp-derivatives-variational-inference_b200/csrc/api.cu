@@ -25,6 +25,15 @@ int dsvgp_normalize_dirs_f32(const float* v, int rows, int d, float* vh, float* 
 int dsvgp_normalize_dirs_f64(const double* v, int rows, int d, double* vh, double* inv, dsvgp_stream_t s) { return normalize_dirs<double, double>(v, rows, d, vh, inv, ST(s)); }
 int dsvgp_normalize_dirs_f32f64(const float* v, int rows, int d, double* vh, double* inv, dsvgp_stream_t s) { return normalize_dirs<float, double>(v, rows, d, vh, inv, ST(s)); }
 
+int dsvgp_normalize_dirs_canon_f32(const float* v, int rows, int d, float* vh, float* inv, int* cidx, int* canon_flag, dsvgp_stream_t s) {
+  if (!cidx || !canon_flag) return DSVGP_ERR_ARG;
+  return normalize_dirs<float, float>(v, rows, d, vh, inv, ST(s), cidx, canon_flag);
+}
+int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, dsvgp_stream_t s) {
+  if (!x1 || !x2 || !hyp || !K || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;
+  return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag);
+}
+
 #define KFWD(NAME, T, TK)                                                                                          \
   int NAME(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,            \
            const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, dsvgp_stream_t s) {                 \

@@ -20,18 +20,34 @@ namespace dsvgp {
 
 // ------------------------------------------------------------------------------------------------ prep
 // One warp per direction row: vhat = v / |v|, inv_norm = 1/|v|   (RBFKernelDirectionalGrad.py:57-58)
+// cidx (optional): per row, the coordinate of its single non-zero entry with the sign in bit 31, and *canon_flag is
+// cleared if any row is not one-hot (the flag must be set to 1 by the caller beforehand).
 template <typename T, typename TK>
 __global__ void normalize_dirs_kernel(const T* __restrict__ v, int rows, int d, TK* __restrict__ vhat,
-                                      TK* __restrict__ inv_norm) {
+                                      TK* __restrict__ inv_norm, int* __restrict__ cidx, int* __restrict__ canon_flag) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   TK s = 0;
+  int nnz = 0, pos = 0, neg = 0;
   for (int c = lane; c < d; c += 32) {
     TK a = (TK)v[(int64_t)row * d + c];
     s += a * a;
+    if (a != TK(0)) {
+      ++nnz;
+      pos = c;
+      neg = a < TK(0);
+    }
   }
   s = warp_sum(s);
+  if (cidx) {
+    const int tot = warp_sum(nnz);
+    const int code = warp_sum(nnz ? (pos | (neg ? (int)0x80000000 : 0)) : 0);    // exact when tot == 1
+    if (lane == 0) {
+      cidx[row] = (tot == 1) ? code : 0;
+      if (tot != 1 && canon_flag) *canon_flag = 0;
+    }
+  }
   const TK inv = TK(1) / dsqrt<TK>(s);
   for (int c = lane; c < d; c += 32) vhat[(int64_t)row * d + c] = (TK)v[(int64_t)row * d + c] * inv;
   if (lane == 0 && inv_norm) inv_norm[row] = inv;
@@ -158,6 +174,209 @@ kdir_fwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, co
   for (int e = tid; e < rows * (TJ * Q2); e += 256) {
     const int rr = e / (TJ * Q2), cc = e % (TJ * Q2);
     if (cc < cols) Kt[(int64_t)rr * ldk + cc] = Ks[rr * LDS + cc];
+  }
+}
+
+// ---------------------------------------------------------------------------------- forward (fp32, vectorised)
+// The hot assembly (K_zx of an fp32 model).  A lane owns 4 CONSECUTIVE column points, a warp 128 of them, so
+//   * column-side operands are read from shared memory as one LDS.128 per (c, plane) [layout (plane, c, j), j contiguous],
+//     row-side operands as broadcast LDS.128 over 4 c's [layout (row, plane, c), c contiguous];
+//   * each output row segment of a warp (128 points x (P2+1) floats, contiguous in memory) is transposed through a
+//     per-warp shared-memory strip so that every global store instruction writes 512 contiguous bytes.
+// One CTA keeps ONE 128-point column tile (all d coordinates) resident and sweeps V4_TIB = 64 row points over it, one
+// row point per warp per pass, so the tile load is amortised over 8192 point pairs and the sweep has no block barriers.
+// Canonical column-side directions (every row of v2 one-hot: what train_gp / eval_gp pass, directional_vi.py:87-88,
+// :292-293) are detected on the device by normalize_dirs (no host sync): then D.w and u.w are lookups, not dot
+// products, and the per-pair work drops from (1+p1)(1+p2) to (1+p1) FMAs per coordinate.
+constexpr int V4_TJ = 128, V4_TIB = 64;
+
+template <int P1, int P2>
+size_t fwd_v4_smem_bytes(int dpad) {
+  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * dpad + (P2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (P2 + 1));
+}
+
+template <int P1, int P2>
+__global__ void __launch_bounds__(256, 2)
+kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
+            const float* __restrict__ w2, const int* __restrict__ cidx2, const int* __restrict__ canon_flag, int n2, int d,
+            const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk) {
+  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ, TIB = V4_TIB;
+  const int dpad = (d + 3) & ~3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* rs = reinterpret_cast<float*>(smem_raw);          // [TIB][Q1][dpad]   row point i: x1_i then u_i1..u_iP1
+  float* cs = rs + TIB * Q1 * dpad;                        // [Q2][dpad][TJ]    plane 0: x2, plane 1+b: w_b
+  float* strip = cs + Q2 * dpad * TJ;                      // [8 warps][TJ*Q2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * TIB, j0 = blockIdx.x * TJ;
+  const bool canon = (P2 > 0) && cidx2 != nullptr && canon_flag != nullptr && (*canon_flag != 0);
+
+  for (int e = tid; e < TIB * Q1 * dpad; e += 256) {       // row side: consecutive threads -> consecutive c
+    const int cc = e % dpad, ia = e / dpad, i = ia / Q1, a = ia % Q1;
+    float v = 0.f;
+    if (i0 + i < n1 && cc < d)
+      v = (a == 0) ? x1[(int64_t)(i0 + i) * d + cc] : u1[(int64_t)((i0 + i) * P1 + a - 1) * d + cc];
+    rs[e] = v;
+  }
+  {                                                        // column side: consecutive threads -> consecutive j
+    const int j = tid & 127, planes = canon ? 1 : Q2;
+    for (int row = tid >> 7; row < planes * dpad; row += 2) {
+      const int b = row / dpad, cc = row % dpad;
+      float v = 0.f;
+      if (j0 + j < n2 && cc < d)
+        v = (b == 0) ? x2[(int64_t)(j0 + j) * d + cc] : w2[(int64_t)((j0 + j) * P2 + b - 1) * d + cc];
+      cs[row * TJ + j] = v;
+    }
+  }
+  __syncthreads();
+
+  // canonical column directions: coordinate index / sign of this lane's 4 points, and x2 at that coordinate
+  int cix[P2 > 0 ? P2 : 1][4];
+  float csg[P2 > 0 ? P2 : 1][4], xjc[P2 > 0 ? P2 : 1][4];
+  if (canon) {
+#pragma unroll
+    for (int b = 0; b < P2; ++b)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + 4 * lane + q;
+        const int code = (j < n2) ? cidx2[(int64_t)j * P2 + b] : 0;
+        cix[b][q] = code & 0x7fffffff;
+        csg[b][q] = (code < 0) ? -1.f : 1.f;
+        xjc[b][q] = cs[cix[b][q] * TJ + 4 * lane + q];
+      }
+  }
+
+  const float ell = (float)hyp[0], os = use_os ? (float)hyp[1] : 1.f;
+  const float il2 = 1.f / (ell * ell);
+  float* mystrip = strip + warp * (TJ * Q2);
+  const bool vec_ok = ((ldk & 3) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+  const int cols = min(TJ * Q2, (n2 - j0) * Q2);
+
+  for (int it = 0; it < TIB / 8; ++it) {
+    const int il = it * 8 + warp, gi = i0 + il;
+    if (gi >= n1) break;                                   // warp-uniform
+    const float* rbase = rs + (il * Q1) * dpad;
+    float r2[4], al[P1 > 0 ? P1 : 1][4], be[P2 > 0 ? P2 : 1][4], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r2[q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < P1; ++a) al[a][q] = 0.f;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) be[b][q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P2; ++b) ga[a][b][q] = 0.f;
+    }
+    if (!canon) {
+      for (int c4 = 0; c4 < dpad; c4 += 4) {
+        const float4 xr = *reinterpret_cast<const float4*>(rbase + c4);
+        float4 ur[P1 > 0 ? P1 : 1];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) ur[a] = *reinterpret_cast<const float4*>(rbase + (1 + a) * dpad + c4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 xj4 = *reinterpret_cast<const float4*>(cs + (c4 + k) * TJ + 4 * lane);
+          const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
+          float wj[P2 > 0 ? P2 : 1][4];
+#pragma unroll
+          for (int b = 0; b < P2; ++b) {
+            const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * dpad + c4 + k) * TJ + 4 * lane);
+            wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
+          }
+          const float xi = k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w;
+          float ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+          for (int a = 0; a < P1; ++a) ui[a] = k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float dl = xi - xj[q];
+            r2[q] = fmaf(dl, dl, r2[q]);
+#pragma unroll
+            for (int b = 0; b < P2; ++b) be[b][q] = fmaf(dl, wj[b][q], be[b][q]);
+#pragma unroll
+            for (int a = 0; a < P1; ++a) {
+              al[a][q] = fmaf(dl, ui[a], al[a][q]);
+#pragma unroll
+              for (int b = 0; b < P2; ++b) ga[a][b][q] = fmaf(ui[a], wj[b][q], ga[a][b][q]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int c4 = 0; c4 < dpad; c4 += 4) {
+        const float4 xr = *reinterpret_cast<const float4*>(rbase + c4);
+        float4 ur[P1 > 0 ? P1 : 1];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) ur[a] = *reinterpret_cast<const float4*>(rbase + (1 + a) * dpad + c4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 xj4 = *reinterpret_cast<const float4*>(cs + (c4 + k) * TJ + 4 * lane);
+          const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
+          const float xi = k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w;
+          float ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+          for (int a = 0; a < P1; ++a) ui[a] = k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float dl = xi - xj[q];
+            r2[q] = fmaf(dl, dl, r2[q]);
+#pragma unroll
+            for (int a = 0; a < P1; ++a) al[a][q] = fmaf(dl, ui[a], al[a][q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < P2; ++b)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          be[b][q] = csg[b][q] * (rbase[cix[b][q]] - xjc[b][q]);                   // D . w  with w = +-e_idx
+#pragma unroll
+          for (int a = 0; a < P1; ++a) ga[a][b][q] = csg[b][q] * rbase[(1 + a) * dpad + cix[b][q]];   // u . w
+        }
+    }
+
+    float kk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) kk[q] = os * expf(-0.5f * r2[q] * il2);
+#pragma unroll
+    for (int a = 0; a < Q1; ++a) {
+      float o[4 * Q2];                                     // this lane's 4*Q2 consecutive floats of output row (gi, a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool dg = (diag_add != 0.f) && (gi == j0 + 4 * lane + q);
+        if (a == 0) {
+          o[q * Q2] = kk[q] + (dg ? diag_add : 0.f);
+#pragma unroll
+          for (int b = 0; b < P2; ++b) o[q * Q2 + 1 + b] = kk[q] * be[b][q] * il2;
+        } else {
+          const float aa = al[a > 0 ? a - 1 : 0][q] * il2;
+          o[q * Q2] = -kk[q] * aa;
+#pragma unroll
+          for (int b = 0; b < P2; ++b)
+            o[q * Q2 + 1 + b] = kk[q] * (ga[a > 0 ? a - 1 : 0][b][q] * il2 - aa * be[b][q] * il2) +
+                                ((dg && a - 1 == b) ? diag_add : 0.f);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < Q2; ++v)
+        *reinterpret_cast<float4*>(mystrip + lane * 4 * Q2 + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      __syncwarp();
+      float* grow = K + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2;
+#pragma unroll
+      for (int v = 0; v < Q2; ++v) {
+        const int col = v * 128 + 4 * lane;
+        const float4 t = *reinterpret_cast<const float4*>(mystrip + col);
+        if (vec_ok && col + 3 < cols) {
+          *reinterpret_cast<float4*>(grow + col) = t;
+        } else {
+          const float tv[4] = {t.x, t.y, t.z, t.w};
+          for (int z = 0; z < 4; ++z)
+            if (col + z < cols) grow[col + z] = tv[z];
+        }
+      }
+    }
   }
 }
 
@@ -579,9 +798,9 @@ __global__ void kdir_bwd_reduce_scalars(const double* __restrict__ part_sc, int 
 
 // ================================================================================================ host side
 template <typename T, typename TK>
-int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st) {
+int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st, int* cidx, int* canon_flag) {
   if (rows <= 0) return DSVGP_OK;
-  normalize_dirs_kernel<T, TK><<<ceil_div(rows, 8), 256, 0, st>>>(v, rows, d, vhat, inv_norm);
+  normalize_dirs_kernel<T, TK><<<ceil_div(rows, 8), 256, 0, st>>>(v, rows, d, vhat, inv_norm, cidx, canon_flag);
   CHECK_LAUNCH();
   return DSVGP_OK;
 }
@@ -598,11 +817,37 @@ static int launch_fwd_blocked(const T* x1, const TK* u1, int n1, const T* x2, co
   return DSVGP_OK;
 }
 
+template <int P1, int P2>
+static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* x2, const float* w2, const int* cidx2,
+                         const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
+                         int64_t ldk, cudaStream_t st) {
+  const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3);
+  auto kern = kdir_fwd_v4<P1, P2>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, V4_TIB));
+  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
 template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
-             const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st) {
+             const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st, const int* cidx2,
+             const int* canon_flag) {
   if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
   if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
+  if constexpr (sizeof(T) == 4 && sizeof(TK) == 4) {
+    // wide enough for 128-point column tiles, and the resident tiles fit in shared memory
+    const int dpad = (d + 3) & ~3;
+    const size_t need = sizeof(float) * (size_t)(V4_TIB * (p1 + 1) * dpad + (p2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (p2 + 1));
+    if (n2 >= 512 && need <= 200 * 1024) {
+#define V4_CASE(A, B)                                                                                          \
+  if (p1 == A && p2 == B)                                                                                      \
+    return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, st);
+      V4_CASE(1, 1) V4_CASE(2, 2) V4_CASE(1, 0) V4_CASE(2, 0) V4_CASE(3, 0)
+#undef V4_CASE
+    }
+  }
 #define FWD_CASE(A, B)                                                                                         \
   if (p1 == A && p2 == B)                                                                                      \
     return launch_fwd_blocked<T, TK, A, B>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, diag_add, K, ldk, st);
@@ -703,9 +948,9 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
 
 // explicit instantiations: (T, TK) in {(f32,f32), (f64,f64), (f32,f64)}
 #define INST(T, TK)                                                                                             \
-  template int normalize_dirs<T, TK>(const T*, int, int, TK*, TK*, cudaStream_t);                               \
+  template int normalize_dirs<T, TK>(const T*, int, int, TK*, TK*, cudaStream_t, int*, int*);                               \
   template int kdir_fwd<T, TK>(const T*, const TK*, int, int, const T*, const TK*, int, int, int, const double*, \
-                               int, double, TK*, int64_t, cudaStream_t);                                        \
+                               int, double, TK*, int64_t, cudaStream_t, const int*, const int*);                                        \
   template int kdir_bwd<T, TK>(const T*, const TK*, const TK*, int, int, const T*, const TK*, int, int, int,    \
                                const double*, int, const TK*, int64_t, int, double, double*, double*, double*,  \
                                void*, size_t, cudaStream_t);

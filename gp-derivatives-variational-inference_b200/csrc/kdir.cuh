@@ -7,12 +7,14 @@ namespace dsvgp {
 int bwd_num_chunks(int n1, int n2);
 
 template <typename T, typename TK>
-int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st);
+int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st, int* cidx = nullptr,
+                   int* canon_flag = nullptr);   // cidx/canon_flag: one-hot (canonical) row detection, see kdir.cu
 
 // hyp: device double[8] = {ell, outputscale, noise, constant, sigmoid(raw_ell), sigmoid(raw_os), sigmoid(raw_noise), -}
 template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
-             const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st);
+             const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st,
+             const int* cidx2 = nullptr, const int* canon_flag = nullptr);   // canonical column-side fast path (fp32)
 
 template <typename TK>
 int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t st);

@@ -113,6 +113,7 @@ class Workspace:
         self.dL, self.Y, self.Psi, self.S = (e(Mq, Mq, dt=F64) for _ in range(4))
         self.gm, self.gLs = e(Mq), e(Mq, Mq)
         self.wx = None
+        self.canon = None          # (cidx, flag) of the data-side directions when detected canonical on device
 
 
 class Engine:
@@ -169,12 +170,25 @@ class Engine:
                 raise NanError(f"NaN/inf in `{name}` reached the Cholesky factorisation of K_zz")
         return False
 
+    @staticmethod
+    def _data_dirs(ws, Vx, T):
+        """normalised data-side directions (+ on-device detection of canonical rows for the fp32 fast path)"""
+        if not ws.p2:
+            ws.canon = None
+            return None
+        if T == F32:
+            wx, _, cidx, flag = ops.normalize_dirs_canon(Vx)
+            ws.canon = (cidx, flag)
+            return wx
+        ws.canon = None
+        return ops.normalize_dirs(Vx, T)[0]
+
     # ------------------------------------------------------------------------------------------------ forward
     @staticmethod
     def _forward(ws, f, P, x, wx, add_noise, need_C):
         Mq, nq = ws.Mq, ws.nq
         Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
-        ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx)
+        ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx, canon=ws.canon)
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
         ops.tril_minus_eye(P.Ls_raw, ws.E)
         if ws.tc and f.tc:
@@ -278,7 +292,7 @@ class Engine:
         f = self.factor(dev, T, d, M, p)
         f.valid = False
         nq_global = (n_global if n_global is not None else n) * (p2 + 1)
-        wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        wx = self._data_dirs(ws, Vx, T)
         for extra in (0.0,) + CHOL_RETRY:
             self._factorise(f, P, T, extra)
             self._forward(ws, f, P, x, wx, through_likelihood, need_C=True)
@@ -306,7 +320,7 @@ class Engine:
         ws = self.workspace(x.device, T, n, d, P.Z.shape[0], p, p2)
         f = self.factor(x.device, T, d, P.Z.shape[0], p)
         f.valid = False
-        ws.wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        ws.wx = self._data_dirs(ws, Vx, T)
         for extra in (0.0,) + CHOL_RETRY:
             self._factorise(f, P, T, extra)
             self._forward(ws, f, P, x, ws.wx, add_noise, need_C=True)
@@ -340,7 +354,7 @@ class Engine:
             else:
                 raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4")
             f.valid = reuse_factor
-        wx = ops.normalize_dirs(Vx, T)[0] if p2 else None
+        wx = self._data_dirs(ws, Vx, T)
         self._forward(ws, f, P, x, wx, add_noise, need_C=False)
         return ws.mu.clone(), ws.var.clone()
 

@@ -43,11 +43,27 @@ def normalize_dirs(v, k_dtype=None):
     return vhat, inv
 
 
-def kdir_fwd(x1, u1, p1, x2, w2, p2, hyp, out, use_os=True, diag_add=0.0):
-    """out[:n1(p1+1), :n2(p2+1)] = [os*] K(x1, x2; u1, w2) (+ diag_add on the diagonal)."""
+def normalize_dirs_canon(v):
+    """fp32 normalize_dirs that also detects one-hot (canonical) rows on the device: returns
+    (vhat, inv_norm, cidx int32[rows], flag int32[1]); flag stays 1 iff every row is one-hot."""
+    v = v.contiguous()
+    vhat, inv = torch.empty_like(v), torch.empty(v.shape[0], dtype=v.dtype, device=v.device)
+    cidx = torch.empty(v.shape[0], dtype=torch.int32, device=v.device)
+    flag = torch.ones(1, dtype=torch.int32, device=v.device)
+    call("dsvgp_normalize_dirs_canon_f32", v, v.shape[0], v.shape[1], vhat, inv, cidx, flag)
+    return vhat, inv, cidx, flag
+
+
+def kdir_fwd(x1, u1, p1, x2, w2, p2, hyp, out, use_os=True, diag_add=0.0, canon=None):
+    """out[:n1(p1+1), :n2(p2+1)] = [os*] K(x1, x2; u1, w2) (+ diag_add on the diagonal).
+    canon = (cidx, flag) from normalize_dirs_canon(v2) enables the canonical-direction fast path (fp32)."""
     n1, d = x1.shape
     n2 = x2.shape[0]
     assert out.shape[0] >= n1 * (p1 + 1) and out.shape[1] >= n2 * (p2 + 1)
+    if canon is not None and p2 and x1.dtype == F32 and out.dtype == F32:
+        call("dsvgp_kdir_fwd_canon_f32", x1, u1 if p1 else None, n1, p1, x2, w2, canon[0], canon[1], n2, p2, d, hyp,
+             int(use_os), float(diag_add), out, _ld(out))
+        return out
     call("dsvgp_kdir_fwd_" + _pair_suffix(x1.dtype, out.dtype), x1, u1 if p1 else None, n1, p1, x2,
          w2 if p2 else None, n2, p2, d, hyp, int(use_os), float(diag_add), out, _ld(out))
     return out

@@ -65,6 +65,14 @@ int dsvgp_kdir_fwd_f32(const float* x1, const float* u1, int n1, int p1, const f
 int dsvgp_kdir_fwd_f64(const double* x1, const double* u1, int n1, int p1, const double* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, double* K, int64_t ldk, dsvgp_stream_t s);
 int dsvgp_kdir_fwd_f32f64(const float* x1, const double* u1, int n1, int p1, const float* x2, const double* w2, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, double* K, int64_t ldk, dsvgp_stream_t s);
 
+/* Canonical-direction fast path of the fp32 assembly.  dsvgp_normalize_dirs_canon_f32 additionally writes, per
+ * direction row, the coordinate of its single non-zero entry (sign in bit 31) and clears *canon_flag (device int, set
+ * to 1 by the caller) if any row is not one-hot.  dsvgp_kdir_fwd_canon_f32 takes those for the SECOND argument's
+ * directions: when the flag is still set -- eye(d) rows, which is what train_gp / eval_gp pass (directional_vi.py:87-88,
+ * :292-293) -- D.w and u.w become lookups.  Decided on the device, no host synchronisation; results are identical. */
+int dsvgp_normalize_dirs_canon_f32(const float* v, int rows, int d, float* vhat, float* inv_norm, int* cidx, int* canon_flag, dsvgp_stream_t s);
+int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, dsvgp_stream_t s);
+
 /* diag=True branch -- RBFKernelDirectionalGrad.py:110-119 */
 int dsvgp_kdir_diag_f32(int n, int p, const double* hyp, int use_os, float* out, dsvgp_stream_t s);
 int dsvgp_kdir_diag_f64(int n, int p, const double* hyp, int use_os, double* out, dsvgp_stream_t s);

@@ -56,7 +56,8 @@ def _gpu_kernel(ops, x1, x2, v1, v2, raw_ell, raw_os, k_dtype, diag_add=0.0, use
 @pytest.mark.parametrize("n1,n2,d,p1,p2", [
     (7, 9, 2, 2, 2), (60, 200, 2, 2, 2), (33, 65, 3, 1, 1), (50, 70, 10, 2, 2), (40, 45, 60, 3, 3),
     (37, 129, 18, 2, 0), (20, 31, 4, 1, 0), (19, 23, 5, 3, 0), (16, 16, 7, 0, 0),
-    (9, 11, 3, 4, 4), (6, 8, 5, 5, 5), (5, 7, 4, 2, 1), (1, 1, 1, 1, 1)])
+    (9, 11, 3, 4, 4), (6, 8, 5, 5, 5), (5, 7, 4, 2, 1), (1, 1, 1, 1, 1),
+    (40, 600, 10, 2, 2), (17, 1000, 3, 1, 1), (33, 515, 18, 2, 0), (9, 777, 5, 3, 0), (20, 640, 4, 1, 0), (8, 512, 60, 2, 2)])
 def test_kdir_forward_matches_oracle(ops, dtype, k_dtype, n1, n2, d, p1, p2):
     x1, x2, v1, v2, raw_ell, raw_os = _kernel_inputs(n1, n2, d, p1, p2, dtype, 100 + n1 + d)
     K = _gpu_kernel(ops, x1, x2, v1, v2, raw_ell, raw_os, k_dtype)
@@ -77,6 +78,32 @@ def test_kdir_forward_matches_reference_golden(ops):
             hyp = ops.hyp_from_raw(c["raw_ell"].reshape(-1).cuda())
             n, p = c["x1"].shape[0], c["v1"].shape[0] // c["x1"].shape[0]
             assert rel(ops.kdir_diag(n, p, hyp, dt, use_os=False), c["Kdiag"]) < 1e-12
+
+
+@pytest.mark.parametrize("n1,n2,d,p1,p2", [(40, 600, 10, 2, 2), (17, 1000, 3, 1, 1), (70, 515, 18, 3, 3), (8, 640, 60, 2, 2)])
+def test_kdir_forward_canonical_fast_path(ops, n1, n2, d, p1, p2):
+    """One-hot data-side directions (any sign / scale), detected on the device, must give the same matrix as the
+    general path; a single non-canonical row must switch the whole call back to the general path."""
+    x1, x2, v1, _, raw_ell, raw_os = _kernel_inputs(n1, n2, d, p1, p2, F32, 300 + n1)
+    g = torch.Generator().manual_seed(n2)
+    idx = torch.randint(0, d, (n2 * p2,), generator=g)
+    scale = torch.randn(n2 * p2, generator=g)
+    scale[scale.abs() < 0.1] = 0.7
+    v2 = torch.zeros(n2 * p2, d)
+    v2[torch.arange(n2 * p2), idx] = scale
+    for make_general in (False, True):
+        if make_general:
+            v2[5, (idx[5] + 1) % d] = 0.3
+        hyp = ops.hyp_from_raw(raw_ell.reshape(-1).cuda(), raw_os.cuda())
+        u1 = ops.normalize_dirs(v1.cuda())[0]
+        w2, _, cidx, flag = ops.normalize_dirs_canon(v2.cuda())
+        assert int(flag.item()) == (0 if make_general else 1)
+        K = torch.full((n1 * (p1 + 1), (n2 * (p2 + 1) + 31) // 32 * 32), -7.0, device="cuda")
+        ops.kdir_fwd(x1.cuda(), u1, p1, x2.cuda(), w2, p2, hyp, K, canon=(cidx, flag))
+        ell, osc = torch.nn.functional.softplus(raw_ell.double()).reshape(()), torch.nn.functional.softplus(raw_os.double())
+        Kref = osc * O.kernel_closed_form(x1.double(), x2.double(), v1.double(), v2.double(), ell)
+        assert rel(K[:, : n2 * (p2 + 1)], Kref) < 2e-6
+        assert float(K[:, n2 * (p2 + 1):].max()) == -7.0 if K.shape[1] > n2 * (p2 + 1) else True
 
 
 def test_kdir_jitter_and_symmetry(ops):
