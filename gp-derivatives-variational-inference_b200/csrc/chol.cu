@@ -42,6 +42,7 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
   const int nbp = (nb + 7) & ~7, ld = nbp + 1;
   double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
   double* Ws = Ls + nbp * ld;                         // [nbp][ld]
+  double* rdg = Ws + nbp * ld;                        // [nbp] reciprocals of the diagonal of L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 31, ty = tid >> 5;             // 32 x 16 mapping of the trailing update
   for (int i = ty; i < nbp; i += 16)
@@ -67,8 +68,13 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
         } else {
           ljj = sqrt(d);
         }
-        if (r == k) a[k] = ljj;
-        else if (r > k) a[k] = a[k] / ljj;
+        const double rinv = 1.0 / ljj;
+        if (r == k) {
+          a[k] = ljj;
+          if (lane < 8) rdg[k0 + k] = rinv;
+        } else if (r > k) {
+          a[k] = a[k] * rinv;
+        }
 #pragma unroll
         for (int c = k + 1; c < 8; ++c) {
           const double lck = __shfl_sync(0xffffffffu, a[k], c);
@@ -91,7 +97,7 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
         double sacc = x[c];
 #pragma unroll
         for (int q = 0; q < c; ++q) sacc -= x[q] * Ls[(k0 + c) * ld + k0 + q];
-        x[c] = sacc / Ls[(k0 + c) * ld + k0 + c];
+        x[c] = sacc * rdg[k0 + c];
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) Ls[i * ld + k0 + c] = x[c];
@@ -111,6 +117,22 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
     }
   }
   // ----------------------------------------------------------------------------------------------- inverse
+  __syncthreads();
+  if (tid < nbp) {                                     // D = inv(L[I,I]) for every 8x8 diagonal block: thread = column
+    const int I0 = tid & ~7, j = tid & 7;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k)
+        if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
+      x[i] = (i >= j) ? sacc * rdg[I0 + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
+  }
   for (int I0 = 0; I0 < nbp; I0 += 8) {
     __syncthreads();
     {                                                  // T[r][c] -> Ws[I0+r][c], c < I0
@@ -120,21 +142,6 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
         for (int k = c & ~7; k < I0; ++k) sacc += Ls[(I0 + r) * ld + k] * Ws[k * ld + c];
         Ws[(I0 + r) * ld + c] = sacc;
       }
-    }
-    if (warp == 0 && lane < 8) {                       // D = inv(L[I,I]): lane j solves column j
-      const int j = lane;
-      double x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        double sacc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k)
-          if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
-        x[i] = (i >= j) ? sacc / Ls[(I0 + i) * ld + I0 + i] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
     }
     __syncthreads();
     {                                                  // W[I0+r][c] = -sum_{q<=r} D[r][q] T[q][c]  (in place, per 8-lane group)
@@ -170,10 +177,27 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   if (!Awork || !L || !W || !info || nb0 <= 0 || nb0 > 128 || (nb0 << nlev) != Mp) return DSVGP_ERR_ARG;
   const int nblk = 1 << nlev;
   const int nbp = (nb0 + 7) & ~7;
-  const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 1));
+  const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 1) + nbp);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(potrf_inv_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(info, 0, sizeof(int), st);
+  // Look-ahead: after the panel of step k, the main stream updates only block column k+1 (all the next diagonal
+  // block and panel need) and goes straight to the next diagonal block; the rest of the trailing update runs on a side
+  // stream.  Events order (a) side(k) after panel(k), (b) the column update of step k+1 after side(k) (both write block
+  // column k+2).  Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_main[64], ev_side[64];
+  static bool ev_ready = false;
+  if (!ev_ready) {
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    for (int i = 0; i < 64; ++i) {
+      cudaEventCreateWithFlags(&ev_main[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_side[i], cudaEventDisableTiming);
+    }
+    ev_ready = true;
+  }
+  const bool lookahead = nblk >= 4 && nblk <= 64;
+  int last_side = -1;
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
     potrf_inv_block<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o,
@@ -186,12 +210,31 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
       int rc = gemm1<double>(false, true, m, nb0, nb0, 1.0, Awork + (o + nb0) * lda + o, lda, W + o * ldw + o, ldw, 0.0,
                              L21, ldl, TRI_NONE, TRI_UPPER, 0, st);
       if (rc) return rc;
-      // trailing update  A22 -= L21 * L21^T  (lower tiles only)
-      rc = gemm1<double>(false, true, m, m, nb0, -1.0, L21, ldl, L21, ldl, 1.0,
-                         Awork + (o + nb0) * lda + (o + nb0), lda, TRI_NONE, TRI_NONE, 1, st);
-      if (rc) return rc;
+      double* A22 = Awork + (o + nb0) * lda + (o + nb0);
+      if (!lookahead) {
+        // trailing update  A22 -= L21 * L21^T  (lower tiles only)
+        rc = gemm1<double>(false, true, m, m, nb0, -1.0, L21, ldl, L21, ldl, 1.0, A22, lda, TRI_NONE, TRI_NONE, 1, st);
+        if (rc) return rc;
+      } else {
+        if (last_side >= 0) cudaStreamWaitEvent(st, ev_side[last_side], 0);
+        // block column k+1:  A22[:, 0:nb0] -= L21 * L21[0:nb0, :]^T
+        rc = gemm1<double>(false, true, m, nb0, nb0, -1.0, L21, ldl, L21, ldl, 1.0, A22, lda, TRI_NONE, TRI_NONE, 0, st);
+        if (rc) return rc;
+        const int m2 = m - nb0;
+        if (m2 > 0) {
+          cudaEventRecord(ev_main[k], st);
+          cudaStreamWaitEvent(side, ev_main[k], 0);
+          const double* L21b = L21 + (int64_t)nb0 * ldl;
+          rc = gemm1<double>(false, true, m2, m2, nb0, -1.0, L21b, ldl, L21b, ldl, 1.0, A22 + (int64_t)nb0 * lda + nb0, lda,
+                             TRI_NONE, TRI_NONE, 1, side);
+          if (rc) return rc;
+          cudaEventRecord(ev_side[k], side);
+          last_side = k;
+        }
+      }
     }
   }
+  if (lookahead && last_side >= 0) cudaStreamWaitEvent(st, ev_side[last_side], 0);
   // recursive inverse; Awork (no longer needed) is the scratch for T = L21 * W11
   for (int lev = 0; lev < nlev; ++lev) {
     const int b = nb0 << lev, npairs = nblk >> (lev + 1);
