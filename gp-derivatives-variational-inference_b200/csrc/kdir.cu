@@ -636,6 +636,245 @@ kdir_bwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, co
   }
 }
 
+// ---------------------------------------------------------------------------------- backward (fp32, vectorised)
+// Same thread mapping as kdir_fwd_v4 (a lane owns 4 consecutive column points, a CTA keeps one 128-point column tile
+// resident and sweeps 64 row points over it, one per warp per pass).  Per row point the lane recomputes its 4 kernel
+// blocks, reads the matching 4*(P2+1)-float segments of the upstream rows straight from global memory (contiguous per
+// warp), forms the coefficients of d/dx1_i and d/du_ia and accumulates them over the coordinates; a transposing
+// butterfly (31 shuffles per 32 values) sums the 32 lanes, and the warp writes ONE partial row per (column tile, row
+// point).  kdir_bwd_reduce_rows sums the partials over column tiles (deterministic) and applies the normalisation chain.
+template <int NV>
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[NV], int lane) {
+  // NV = 32: on return lane l holds sum over lanes of v[l] in v[0]
+  static_assert(NV == 32, "butterfly works on 32 values");
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+}
+
+template <int P1, int P2, int DP>
+size_t bwd_v4_smem_bytes() {
+  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * DP + (P2 + 1) * DP * V4_TJ) + 64 * sizeof(double);
+}
+
+template <int P1, int P2, int DP>
+__global__ void __launch_bounds__(256, 1)
+kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
+            const float* __restrict__ w2, int n2, int d, const double* __restrict__ hyp, int use_os,
+            const float* __restrict__ dK, int64_t lddk, float* __restrict__ part, double* __restrict__ part_sc) {
+  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ, TIB = V4_TIB, NV = Q1 * DP, NG = (NV + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);       // [64]
+  float* rs = reinterpret_cast<float*>(red + 64);          // [TIB][Q1][DP]
+  float* cs = rs + TIB * Q1 * DP;                          // [Q2][DP][TJ]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * TIB, j0 = blockIdx.x * TJ;
+
+  for (int e = tid; e < TIB * Q1 * DP; e += 256) {
+    const int cc = e % DP, ia = e / DP, i = ia / Q1, a = ia % Q1;
+    float v = 0.f;
+    if (i0 + i < n1 && cc < d)
+      v = (a == 0) ? x1[(int64_t)(i0 + i) * d + cc] : u1[(int64_t)((i0 + i) * P1 + a - 1) * d + cc];
+    rs[e] = v;
+  }
+  {
+    const int j = tid & 127;
+    for (int row = tid >> 7; row < Q2 * DP; row += 2) {
+      const int b = row / DP, cc = row % DP;
+      float v = 0.f;
+      if (j0 + j < n2 && cc < d)
+        v = (b == 0) ? x2[(int64_t)(j0 + j) * d + cc] : w2[(int64_t)((j0 + j) * P2 + b - 1) * d + cc];
+      cs[row * TJ + j] = v;
+    }
+  }
+  __syncthreads();
+
+  const float ell = (float)hyp[0], os = use_os ? (float)hyp[1] : 1.f;
+  const float il2 = 1.f / (ell * ell), iell = 1.f / ell;
+  const bool vec_ok = ((lddk & 3) == 0) && ((reinterpret_cast<uintptr_t>(dK) & 15) == 0);
+  const int cols = min(TJ * Q2, (n2 - j0) * Q2);
+  double s_ell = 0.0, s_os = 0.0;
+
+  for (int it = 0; it < TIB / 8; ++it) {
+    const int il = it * 8 + warp, gi = i0 + il;
+    if (gi >= n1) break;                                   // warp-uniform
+    const float* rbase = rs + (il * Q1) * DP;
+    // ---- recompute the 4 kernel blocks of this lane
+    float r2[4], al[P1 > 0 ? P1 : 1][4], be[P2 > 0 ? P2 : 1][4], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r2[q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < P1; ++a) al[a][q] = 0.f;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) be[b][q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P2; ++b) ga[a][b][q] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < DP; ++c) {
+      const float4 xj4 = *reinterpret_cast<const float4*>(cs + c * TJ + 4 * lane);
+      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
+      float wj[P2 > 0 ? P2 : 1][4];
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * DP + c) * TJ + 4 * lane);
+        wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
+      }
+      const float xi = rbase[c];
+      float ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+      for (int a = 0; a < P1; ++a) ui[a] = rbase[(1 + a) * DP + c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dl = xi - xj[q];
+        r2[q] = fmaf(dl, dl, r2[q]);
+#pragma unroll
+        for (int b = 0; b < P2; ++b) be[b][q] = fmaf(dl, wj[b][q], be[b][q]);
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+          al[a][q] = fmaf(dl, ui[a], al[a][q]);
+#pragma unroll
+          for (int b = 0; b < P2; ++b) ga[a][b][q] = fmaf(ui[a], wj[b][q], ga[a][b][q]);
+        }
+      }
+    }
+    // ---- upstream blocks: row (gi, a) holds this lane's 4*Q2 consecutive floats
+    float g[Q1][4 * Q2];
+#pragma unroll
+    for (int a = 0; a < Q1; ++a) {
+      const float* grow = dK + (int64_t)(gi * Q1 + a) * lddk + (int64_t)j0 * Q2 + lane * 4 * Q2;
+#pragma unroll
+      for (int v = 0; v < Q2; ++v) {
+        const int col = lane * 4 * Q2 + 4 * v;
+        if (vec_ok && col + 3 < cols) {
+          const float4 t = *reinterpret_cast<const float4*>(grow + 4 * v);
+          g[a][4 * v] = t.x; g[a][4 * v + 1] = t.y; g[a][4 * v + 2] = t.z; g[a][4 * v + 3] = t.w;
+        } else {
+#pragma unroll
+          for (int z = 0; z < 4; ++z) g[a][4 * v + z] = (col + z < cols) ? grow[4 * v + z] : 0.f;
+        }
+      }
+    }
+    // ---- coefficients per pair
+    float e0[4], ea[P1 > 0 ? P1 : 1][4], eb[P2 > 0 ? P2 : 1][4], hab[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float k = os * expf(-0.5f * r2[q] * il2);
+      float as[P1 > 0 ? P1 : 1], bs[P2 > 0 ? P2 : 1];
+#pragma unroll
+      for (int a = 0; a < P1; ++a) as[a] = al[a][q] * il2;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) bs[b] = be[b][q] * il2;
+      float qk = g[0][q * Q2], sdd = 0.f;
+      float dbs[P2 > 0 ? P2 : 1], das[P1 > 0 ? P1 : 1];
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        dbs[b] = g[0][q * Q2 + 1 + b];
+        qk += dbs[b] * bs[b];
+      }
+#pragma unroll
+      for (int a = 0; a < P1; ++a) {
+        const float ga0 = g[1 + (a < P1 ? a : 0)][q * Q2];
+        das[a] = -ga0;
+        qk -= ga0 * as[a];
+#pragma unroll
+        for (int b = 0; b < P2; ++b) {
+          const float gab = g[1 + (a < P1 ? a : 0)][q * Q2 + 1 + b];
+          const float gam = ga[a][b][q] * il2;
+          qk += gab * (gam - as[a] * bs[b]);
+          das[a] -= gab * bs[b];
+          dbs[b] -= gab * as[a];
+          sdd += k * gab * gam;
+          hab[a][b][q] = k * gab * il2;
+        }
+      }
+      e0[q] = -qk * k * il2;
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        sdd += k * dbs[b] * bs[b];
+        eb[b][q] = k * dbs[b] * il2;
+      }
+#pragma unroll
+      for (int a = 0; a < P1; ++a) {
+        sdd += k * das[a] * as[a];
+        ea[a][q] = k * das[a] * il2;
+      }
+      s_ell += (double)(qk * k * r2[q] * il2 * iell - 2.f * sdd * iell);
+      s_os += (double)(qk * k / os);
+    }
+    // ---- accumulate d/dx1_i and d/du_ia over this lane's 4 pairs
+    float acc[NG * 32];
+#pragma unroll
+    for (int f = 0; f < NG * 32; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int c = 0; c < DP; ++c) {
+      const float4 xj4 = *reinterpret_cast<const float4*>(cs + c * TJ + 4 * lane);
+      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
+      float wj[P2 > 0 ? P2 : 1][4];
+#pragma unroll
+      for (int b = 0; b < P2; ++b) {
+        const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * DP + c) * TJ + 4 * lane);
+        wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
+      }
+      const float xi = rbase[c];
+      float ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+      for (int a = 0; a < P1; ++a) ui[a] = rbase[(1 + a) * DP + c];
+      float gx = 0.f, gu[P1 > 0 ? P1 : 1];
+#pragma unroll
+      for (int a = 0; a < P1; ++a) gu[a] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dl = xi - xj[q];
+        gx = fmaf(e0[q], dl, gx);
+#pragma unroll
+        for (int b = 0; b < P2; ++b) gx = fmaf(eb[b][q], wj[b][q], gx);
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+          gx = fmaf(ea[a][q], ui[a], gx);
+          gu[a] = fmaf(ea[a][q], dl, gu[a]);
+#pragma unroll
+          for (int b = 0; b < P2; ++b) gu[a] = fmaf(hab[a][b][q], wj[b][q], gu[a]);
+        }
+      }
+      acc[c] = gx;
+#pragma unroll
+      for (int a = 0; a < P1; ++a) acc[(1 + a) * DP + c] = gu[a];
+    }
+    // ---- sum over the 32 lanes, one partial row per (column tile, row point)
+    float* prow = part + ((int64_t)blockIdx.x * n1 * Q1 + (int64_t)gi * Q1) * d;
+#pragma unroll
+    for (int grp = 0; grp < NG; ++grp) {
+      float v[32];
+#pragma unroll
+      for (int f = 0; f < 32; ++f) v[f] = acc[grp * 32 + f];
+      warp_transpose_sum<32>(v, lane);
+      const int f = grp * 32 + lane;                        // flattened (a', c) with pitch DP
+      if (f < NV) {
+        const int a = f / DP, c = f % DP;
+        if (c < d) prow[a * d + c] = v[0];
+      }
+    }
+  }
+  const double t_ell = block_sum<double, 256>(s_ell, red);
+  const double t_os = block_sum<double, 256>(s_os, red + 32);
+  if (tid == 0) {
+    const int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    part_sc[2 * b] = t_ell;
+    part_sc[2 * b + 1] = t_os;
+  }
+}
+
 // ------------------------------------------------------------------------------------ backward (runtime p)
 // One thread per point pair, atomics into double accumulators.  Any p <= DSVGP_MAXP; not tuned.
 template <typename T, typename TK>
@@ -869,8 +1108,19 @@ int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t
 }
 
 // workspace (bytes) the backward needs for an (n1,p1) x (n2,p2) call
+bool bwd_v4_ok(int n1, int p1, int n2, int p2, int d) {
+  return d <= 16 && n2 >= 512 && ((p1 == 1 && p2 == 1) || (p1 == 2 && p2 == 2) || (p1 == 1 && p2 == 0) || (p1 == 2 && p2 == 0));
+}
+
 template <typename TK>
 size_t kdir_bwd_workspace(int n1, int p1, int n2, int p2, int d) {
+  if (sizeof(TK) == 4 && bwd_v4_ok(n1, p1, n2, p2, d)) {
+    const size_t nt = ceil_div(n2, 128), nrc = ceil_div(n1, 64);
+    const size_t v4 = sizeof(float) * nt * n1 * (p1 + 1) * d + sizeof(double) * 2 * nt * nrc + 512;
+    const int rt0 = ceil_div(n1, BWD_TI), nch0 = bwd_num_chunks(n1, n2);
+    const size_t old = sizeof(float) * (size_t)nch0 * n1 * (p1 + 1) * d + sizeof(double) * 2 * (size_t)rt0 * nch0 + 256;
+    return v4 > old ? v4 : old;
+  }
   const bool fast = (p1 <= DSVGP_MAXP_FAST && (p2 == p1 || p2 == 0) && BWD_TI * (p1 + 1) * d <= 256 * BWD_MAXACC);
   if (!fast) return sizeof(double) * ((size_t)n1 * d + (size_t)n1 * p1 * d) + 256;
   const int rt = ceil_div(n1, BWD_TI);
@@ -924,6 +1174,39 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
   if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
   if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
   if (ws_bytes < kdir_bwd_workspace<TK>(n1, p1, n2, p2, d)) return DSVGP_ERR_WORKSPACE;
+  if constexpr (sizeof(T) == 4 && sizeof(TK) == 4) {
+    if (bwd_v4_ok(n1, p1, n2, p2, d) && !dk_trans) {
+      const int nt = ceil_div(n2, V4_TJ), nrc = ceil_div(n1, V4_TIB);
+      float* part = reinterpret_cast<float*>(ws);
+      const size_t part_bytes = round_up64(sizeof(float) * (size_t)nt * n1 * (p1 + 1) * d, 16);
+      double* part_sc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + part_bytes);
+      const int DPr = (d + 3) & ~3;
+      dim3 grid(nt, nrc);
+      int launched = 0;
+#define BV4(A, B, DPV)                                                                                         \
+  if (!launched && p1 == A && p2 == B && DPr == DPV) {                                                         \
+    const size_t smem = bwd_v4_smem_bytes<A, B, DPV>();                                                        \
+    auto kern = kdir_bwd_v4<A, B, DPV>;                                                                        \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, dK, lddk, part, part_sc);            \
+    launched = 1;                                                                                              \
+  }
+#define BV4_ALL(A, B) BV4(A, B, 4) BV4(A, B, 8) BV4(A, B, 12) BV4(A, B, 16)
+      BV4_ALL(1, 1) BV4_ALL(2, 2) BV4_ALL(1, 0) BV4_ALL(2, 0)
+#undef BV4_ALL
+#undef BV4
+      if (launched) {
+        CHECK_LAUNCH();
+        kdir_bwd_reduce_rows<float><<<ceil_div(n1 * (p1 + 1), 8), 256, 0, st>>>(part, nt, n1, p1, d, u1, inv1, scale, gx, gv);
+        CHECK_LAUNCH();
+        if (gsc) {
+          kdir_bwd_reduce_scalars<<<1, 256, 0, st>>>(part_sc, nt * nrc, gsc);
+          CHECK_LAUNCH();
+        }
+        return DSVGP_OK;
+      }
+    }
+  }
   const bool fast = (p1 <= DSVGP_MAXP_FAST && (p2 == p1 || p2 == 0) && BWD_TI * (p1 + 1) * d <= 256 * BWD_MAXACC);
   if (fast) {
 #define BWD_CASE(A, B)                                                                                         \

@@ -5,6 +5,7 @@
 namespace dsvgp {
 
 int bwd_num_chunks(int n1, int n2);
+bool bwd_v4_ok(int n1, int p1, int n2, int p2, int d);
 
 template <typename T, typename TK>
 int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStream_t st, int* cidx = nullptr,

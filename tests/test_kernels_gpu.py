@@ -118,7 +118,8 @@ def test_kdir_jitter_and_symmetry(ops):
 @pytest.mark.parametrize("dtype,k_dtype", [(F64, F64), (F32, F32), (F32, F64)])
 @pytest.mark.parametrize("n1,n2,d,p1,p2", [
     (20, 50, 2, 2, 2), (33, 200, 3, 1, 1), (50, 300, 10, 2, 2), (17, 40, 60, 3, 3), (37, 129, 18, 2, 0),
-    (19, 23, 5, 3, 0), (16, 16, 7, 0, 0), (9, 11, 3, 4, 4), (5, 7, 4, 2, 1), (70, 2100, 4, 2, 2)])
+    (19, 23, 5, 3, 0), (16, 16, 7, 0, 0), (9, 11, 3, 4, 4), (5, 7, 4, 2, 1), (70, 2100, 4, 2, 2),
+    (100, 700, 10, 2, 2), (65, 513, 3, 1, 1), (33, 1111, 16, 2, 0), (9, 640, 7, 1, 0), (130, 900, 13, 2, 2)])
 def test_kdir_backward_matches_oracle_autograd(ops, dtype, k_dtype, n1, n2, d, p1, p2):
     x1, x2, v1, v2, raw_ell, raw_os = _kernel_inputs(n1, n2, d, p1, p2, dtype, 200 + n1 + d)
     g = torch.Generator().manual_seed(7)
