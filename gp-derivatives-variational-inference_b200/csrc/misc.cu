@@ -86,6 +86,34 @@ __global__ void sym_phi_kernel(const double* __restrict__ Y, int64_t ldy, double
   P[(int64_t)i * ldp + j] = 0.5 * Y[(int64_t)a * ldy + b];
 }
 
+// Phi = tril(Y) with halved diagonal (Cholesky-backward middle factor, Murray 2016)
+__global__ void phi_lower_kernel(const double* __restrict__ Y, int64_t ldy, double* __restrict__ P, int64_t ldp, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n || i >= n) return;
+  P[(int64_t)i * ldp + j] = (j < i) ? Y[(int64_t)i * ldy + j] : (j == i ? 0.5 * Y[(int64_t)i * ldy + j] : 0.0);
+}
+
+// A <- (A + A^T) / 2 in place
+__global__ void symmetrize_kernel(double* A, int64_t ld, int n) {
+  __shared__ double ta[32][33], tb[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    ta[r][tx] = (i < n && j < n) ? A[(int64_t)i * ld + j] : 0.0;
+    const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+    tb[r][tx] = (i2 < n && j2 < n) ? A[(int64_t)i2 * ld + j2] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < n && j < n) A[(int64_t)i * ld + j] = 0.5 * (ta[r][tx] + tb[tx][r]);
+    const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+    if (bi != bj && i2 < n && j2 < n) A[(int64_t)i2 * ld + j2] = 0.5 * (tb[r][tx] + ta[tx][r]);
+  }
+}
+
 // --------------------------------------------------------------------------------- predictive mean / variance
 // partial column sums over a slab of rows:  pm[s][j] = sum_i A_ij m_i ,  pv[s][j] = sum_i A_ij C_ij
 template <typename T>
@@ -380,6 +408,22 @@ int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStr
   if (n <= 0) return DSVGP_OK;
   dim3 grid(ceil_div(n, 256), n);
   sym_phi_kernel<<<grid, 256, 0, st>>>(Y, ldy, P, ldp, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int phi_lower(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 256), n);
+  phi_lower_kernel<<<grid, 256, 0, st>>>(Y, ldy, P, ldp, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int symmetrize(double* A, int64_t ld, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(n, 32), ceil_div(n, 32)), block(32, 8);
+  symmetrize_kernel<<<grid, block, 0, st>>>(A, ld, n);
   CHECK_LAUNCH();
   return DSVGP_OK;
 }

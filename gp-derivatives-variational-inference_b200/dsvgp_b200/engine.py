@@ -258,10 +258,11 @@ class Engine:
             ops.cast2d(ws.X, ws.Xd)
         ops.gemm(W, ws.Xd, ws.dL, ta=True, a_tri=TRI_UPPER, alpha=-1.0, c_tri=1, M=Mq, N=Mq, K=Mq)     # -tril(W^T X)
         ops.gemm(L, ws.dL, ws.Y, ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, c_tri=1, M=Mq, N=Mq, K=Mq)  # L^T dL
-        ops.sym_phi(ws.Y, ws.Psi, Mq)                                                    # Psi = sym(Phi(Y))
-        ops.gemm(W, ws.Psi, ws.Y, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq)            # Y <- W^T Psi
-        ops.gemm(ws.Y, W, ws.S, b_tri=TRI_LOWER, c_tri=1, M=Mq, N=Mq, K=Mq)              # dK_zz = W^T Psi W
-        ops.mirror_lower(ws.S, Mq)
+        # dK_zz = sym(W^T Phi W), Phi = tril(Y) with halved diagonal: Phi W is lower x lower (M'^3/3 flops)
+        ops.phi_lower(ws.Y, ws.Psi, Mq)
+        ops.gemm(ws.Psi, W, ws.Y, a_tri=TRI_LOWER, b_tri=TRI_LOWER, c_tri=1, M=Mq, N=Mq, K=Mq)        # Y <- Phi W (lower)
+        ops.gemm(W, ws.Y, ws.S, ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, M=Mq, N=Mq, K=Mq)          # W^T (Phi W)
+        ops.symmetrize(ws.S, Mq)
         ops.kdir_bwd(P.Z, f.uz64, f.invz64, ws.p, P.Z, f.uz64, ws.p, f.hyp, ws.S, ws.gZ, ws.gVz, ws.sc[4:6],
                      scale=2.0)
         ops.var_grads(ws.H, P.Ls_raw, ws.t, P.m, inv_num_data, ws.gm, ws.gLs)

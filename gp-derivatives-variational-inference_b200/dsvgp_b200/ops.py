@@ -182,6 +182,16 @@ def sym_phi(Y, P, n):
     return P
 
 
+def phi_lower(Y, P, n):
+    call("dsvgp_phi_lower_f64", Y, _ld(Y), P, _ld(P), n)
+    return P
+
+
+def symmetrize(A, n):
+    call("dsvgp_symmetrize_f64", A, _ld(A), n)
+    return A
+
+
 def reduce_slabs(rows, cols):
     return call_raw("dsvgp_reduce_slabs", rows, cols)
 

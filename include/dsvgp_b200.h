@@ -134,6 +134,9 @@ int dsvgp_add_outer_f64(double* A, int64_t ld, int n, const double* u, const dou
 int dsvgp_tril_minus_eye_f32(const float* Ls, int64_t ldl, float* E, int64_t lde, int n, dsvgp_stream_t s);
 int dsvgp_tril_minus_eye_f64(const double* Ls, int64_t ldl, double* E, int64_t lde, int n, dsvgp_stream_t s);
 int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s);
+/* Cholesky backward dK = sym(L^-T Phi(L^T dL) L^-1): Phi = tril with halved diagonal; A <- (A + A^T)/2 in place */
+int dsvgp_phi_lower_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s);
+int dsvgp_symmetrize_f64(double* A, int64_t ld, int n, dsvgp_stream_t s);
 
 /* predictive mean / diagonal variance (DirectionalGradVariationalStrategy.py:188,:192-205):
  *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or, with B' = B - A given in
