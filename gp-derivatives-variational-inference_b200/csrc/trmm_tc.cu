@@ -34,12 +34,18 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 32;               // BK fp32 = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 4;                     // 16 KB
-constexpr int B_BYTES = BN * BK * 4;                     // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
-constexpr int STAGES = 2;
 constexpr int THREADS = 320;
 constexpr int EPI_WARPS = 8;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's CTA 0
+// CG = 1: one CTA per 128x256 tile.  CG = 2: a CTA PAIR (tcgen05 cta_group::2) per 256x256 tile -- each CTA stages its
+// own 128 rows of A and its own 128 columns of B, so the operand bytes per SM drop by a third and one more stage fits.
+template <int CG> struct Geo {
+  static constexpr int BN_LOCAL = BN / CG;
+  static constexpr int B_BYTES = BN_LOCAL * BK * 4;                  // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // hi + lo of both operands: 96 KB / 64 KB
+  static constexpr int STAGES = CG == 1 ? 2 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,6 +68,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {          // arrive on the pair leader's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-SM TMA loads: executed by both CTAs of a pair into their own shared memory; the bytes are counted on CTA 0's barrier
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {           // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -129,9 +169,11 @@ struct Params {
   int a_tri, c_lower, b_kmajor, chunk;     // chunk: k-blocks per tensor-core accumulation chain
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+template <int CG>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUtensorMap& mapAl, const CUtensorMap& mapBh,
+                                             const CUtensorMap& mapBl, const Params& p) {
+  constexpr int STAGES = Geo<CG>::STAGES, STAGE_BYTES = Geo<CG>::STAGE_BYTES, B_BYTES = Geo<CG>::B_BYTES;
+  constexpr int BNL = Geo<CG>::BN_LOCAL;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -142,14 +184,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;        // position in the CTA pair; rank 0 issues the MMAs
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  if (p.c_lower && n0 >= m0 + BM) return;                        // tile strictly above the diagonal
+  const int m0p = CG == 2 ? (m0 - (int)rank * BM) : m0;          // first row of the pair's 256-row tile
+  if (p.c_lower && n0 >= m0p + BM * CG) return;                  // tile strictly above the diagonal (pair-uniform)
 
-  // k-block range that can be non-zero for this row tile
+  // k-block range that can be non-zero for this (pair of) row tile(s)
   const int nkb = (p.K + BK - 1) / BK;
   int kb0 = 0, kb1 = nkb;
-  if (p.a_tri == 1) kb1 = min(nkb, (m0 + BM + BK - 1) / BK);     // lower: k <= row
-  if (p.a_tri == 2) kb0 = m0 / BK;                               // upper: k >= row
+  if (p.a_tri == 1) kb1 = min(nkb, (m0p + BM * CG + BK - 1) / BK);   // lower: k <= row
+  if (p.a_tri == 2) kb0 = m0p / BK;                                  // upper: k >= row
   if (gridDim.z > 1) {                                           // split-K: this CTA takes an even share of the range
     const int tot = max(kb1 - kb0, 0), per = (tot + gridDim.z - 1) / gridDim.z;
     kb0 = kb0 + blockIdx.z * per;
@@ -165,16 +209,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], EPI_WARPS);
+      mbar_init(&tempty[b], EPI_WARPS * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();                         // the peer's barriers must exist before anyone signals them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -185,24 +235,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int s = i % STAGES, kb = kb0 + i;
         if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
         unsigned char* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_2d(st, &mapAh, &full[s], kb * BK, m0);
-        tma_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BK, m0);
-        if (p.b_kmajor) {
-          tma_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BK, n0);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BK, n0);
+        const int nb = n0 + (int)rank * BNL;                    // this CTA's share of the B columns
+        if constexpr (CG == 1) {
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(st, &mapAh, &full[s], kb * BK, m0);
+          tma_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BK, m0);
+          if (p.b_kmajor) {
+            tma_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BK, nb);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BK, nb);
+          } else {
+            tma_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BK, nb / 32);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BK, nb / 32);
+          }
         } else {
-          tma_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BK, n0 / 32);
-          tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BK, n0 / 32);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
+          tma2_load_2d(st, &mapAh, &full[s], kb * BK, m0);
+          tma2_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BK, m0);
+          if (p.b_kmajor) {
+            tma2_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BK, nb);
+            tma2_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BK, nb);
+          } else {
+            tma2_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BK, nb / 32);
+            tma2_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BK, nb / 32);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, A K-major, B per flag, N=256, M=128
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, A K-major, B per flag, N=256, M=128 (256 for a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)((BM * CG) >> 4) << 24);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES, c = i / p.chunk, buf = c & 1;
         const bool chunk_start = (i % p.chunk) == 0;
@@ -229,12 +293,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             bh = umma_desc(st + 2 * A_BYTES + ks * 1024, BK * 128, 512, 1);
             bl = umma_desc(st + 2 * A_BYTES + B_BYTES + ks * 1024, BK * 128, 512, 1);
           }
-          umma_tf32(d_tmem, al, bh, idesc, (chunk_start && ks == 0) ? 0u : 1u);   // small terms first
-          umma_tf32(d_tmem, ah, bl, idesc, 1u);
-          umma_tf32(d_tmem, ah, bh, idesc, 1u);
+          if constexpr (CG == 1) {
+            umma_tf32(d_tmem, al, bh, idesc, (chunk_start && ks == 0) ? 0u : 1u);   // small terms first
+            umma_tf32(d_tmem, ah, bl, idesc, 1u);
+            umma_tf32(d_tmem, ah, bh, idesc, 1u);
+          } else {
+            umma2_tf32(d_tmem, al, bh, idesc, (chunk_start && ks == 0) ? 0u : 1u);
+            umma2_tf32(d_tmem, ah, bl, idesc, 1u);
+            umma2_tf32(d_tmem, ah, bh, idesc, 1u);
+          }
         }
-        umma_commit(&empty[s]);                                     // smem stage free once these MMAs retire
-        if ((i % p.chunk) == p.chunk - 1 || i == nk - 1) umma_commit(&tfull[buf]);   // chunk finished
+        const bool chunk_end = (i % p.chunk) == p.chunk - 1 || i == nk - 1;
+        if constexpr (CG == 1) {
+          umma_commit(&empty[s]);                                   // smem stage free once these MMAs retire
+          if (chunk_end) umma_commit(&tfull[buf]);                  // chunk finished
+        } else {
+          umma2_commit_both(&empty[s]);                             // ... in both CTAs of the pair
+          if (chunk_end) umma2_commit_both(&tfull[buf]);
+        }
       }
     }
   } else {
@@ -260,7 +336,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tempty[buf]);
+        else mbar_arrive_cta0(&tempty[buf]);
+      }
     }
     // Stage this warp's 32 x 128 block through shared memory (the operand ring is idle: the last chunk is complete, so
     // every TMA load has landed and every MMA has retired) so that global traffic is row-contiguous: one warp
@@ -329,11 +408,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();                         // the peer may still be reading operands / TMEM
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  gemm_tc_body<1>(mapAh, mapAl, mapBh, mapBl, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  gemm_tc_body<2>(mapAh, mapAl, mapBh, mapBl, p);
 }
 
 __global__ void split_lo_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ lo, int64_t ldl, int rows, int cols) {
@@ -409,10 +502,10 @@ static bool map_kmajor(CUtensorMap* m, const float* base, int64_t ld, int rows, 
 }
 
 // row-major [K][N] fp32 (N contiguous) viewed as [N/32][K][32]: box = 32 x BK x BN/32 lands as BN/32 column blocks
-static bool map_mnmajor(CUtensorMap* m, const float* base, int64_t ld, int K, int N) {
+static bool map_mnmajor(CUtensorMap* m, const float* base, int64_t ld, int K, int N, int box_cols) {
   cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)((N + 31) / 32)};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
-  cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)(BN / 32)};
+  cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)(box_cols / 32)};
   cuuint32_t es[3] = {1, 1, 1};
   return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -420,6 +513,10 @@ static bool map_mnmajor(CUtensorMap* m, const float* base, int64_t ld, int K, in
 }
 
 }  // namespace tc
+
+static int g_tc_cta_group = 2;   // CTA pairs by default: +9% over single-CTA tiles on the C3 whitening product
+void set_tc_cta_group(int cg) { g_tc_cta_group = (cg == 2) ? 2 : 1; }
+int get_tc_cta_group() { return g_tc_cta_group; }
 
 int gemm_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N) {
   if (!tc::encode_fn()) return 0;
@@ -438,23 +535,31 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
   if (nsplit > 1 && (!split_ws || C2 || Clo)) return DSVGP_ERR_ARG;
   if (!gemm_tc_supported(Ah, lda, Bh, ldb, b_kmajor, N) || !gemm_tc_supported(Al, lda, Bl, ldb, b_kmajor, N))
     return DSVGP_ERR_ARG;
+  const int cg = g_tc_cta_group;
+  const int bnl = tc::BN / cg;                       // B columns staged per CTA
   CUtensorMap mAh, mAl, mBh, mBl;
   bool ok = tc::map_kmajor(&mAh, Ah, lda, M, K, tc::BM) && tc::map_kmajor(&mAl, Al, lda, M, K, tc::BM);
-  if (b_kmajor) ok = ok && tc::map_kmajor(&mBh, Bh, ldb, N, K, tc::BN) && tc::map_kmajor(&mBl, Bl, ldb, N, K, tc::BN);
-  else ok = ok && tc::map_mnmajor(&mBh, Bh, ldb, K, N) && tc::map_mnmajor(&mBl, Bl, ldb, K, N);
+  if (b_kmajor) ok = ok && tc::map_kmajor(&mBh, Bh, ldb, N, K, bnl) && tc::map_kmajor(&mBl, Bl, ldb, N, K, bnl);
+  else ok = ok && tc::map_mnmajor(&mBh, Bh, ldb, K, N, bnl) && tc::map_mnmajor(&mBl, Bl, ldb, K, N, bnl);
   if (!ok) return DSVGP_ERR_ARG;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<1>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess)
       return DSVGP_ERR_LAUNCH;
     attr_set = true;
   }
+  const int mtiles = cg == 2 ? ((ceil_div(M, tc::BM) + 1) & ~1) : ceil_div(M, tc::BM);   // whole CTA pairs
+  auto launch = [&](const tc::Params& pp, int nz) {
+    dim3 grid(mtiles, ceil_div(N, tc::BN), nz);
+    if (cg == 2) tc::gemm_tc2_kernel<<<grid, tc::THREADS, tc::Geo<2>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+    else tc::gemm_tc_kernel<<<grid, tc::THREADS, tc::Geo<1>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+  };
   if (nsplit > 1) {
     const int64_t ldp = round_up64(N, 4), stride = (int64_t)M * ldp;
     tc::Params p{split_ws, nullptr, nullptr, nullptr, nullptr, nullptr, ldp, 0, 0, 0, stride, M, N, K, 1.f, 0.f,
                  a_tri, c_lower, b_kmajor, chunk};
-    dim3 grid(ceil_div(M, tc::BM), ceil_div(N, tc::BN), nsplit);
-    tc::gemm_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+    launch(p, nsplit);
     CHECK_LAUNCH();
     dim3 rgrid(ceil_div(N, 256), M);
     tc::splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(split_ws, nsplit, stride, ldp, M, N, alpha, beta, D, ldd, C, ldc, c_lower);
@@ -462,8 +567,7 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
     return DSVGP_OK;
   }
   tc::Params p{C, D, C2, D2, Clo, C2lo, ldc, ldd, ldc2, ldd2, 0, M, N, K, alpha, beta, a_tri, c_lower, b_kmajor, chunk};
-  dim3 grid(ceil_div(M, tc::BM), ceil_div(N, tc::BN), 1);
-  tc::gemm_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  launch(p, 1);
   CHECK_LAUNCH();
   return DSVGP_OK;
 }

@@ -19,6 +19,10 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
 // nsplit > 1: split-K over gridDim.z; raw partial sums go to split_ws (nsplit * M * round_up(N,4) floats) and are
 // summed in fp64 by a second kernel (needs C2 == Clo == null).
 
+// 1: one CTA per 128x256 tile (tcgen05 cta_group::1); 2: CTA pairs on 256x256 tiles (cta_group::2, 2-SM TMA, multicast commit)
+void set_tc_cta_group(int cg);
+int get_tc_cta_group();
+
 int split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, cudaStream_t st);
 int transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, cudaStream_t st);
 

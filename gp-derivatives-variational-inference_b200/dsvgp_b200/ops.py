@@ -128,6 +128,11 @@ def transpose(src, dst, rows=None, cols=None):
     return dst
 
 
+def set_tc_cta_group(cg):
+    """1: one CTA per 128x256 tile; 2: CTA pairs (tcgen05 cta_group::2) on 256x256 tiles."""
+    return call_raw("dsvgp_set_tc_cta_group", int(cg))
+
+
 def gemm_tc_supported(A, B, b_kmajor, N):
     return bool(call_raw("dsvgp_gemm_tc_supported_f32", A, _ld(A), B, _ld(B), int(b_kmajor), int(N)))
 

@@ -117,6 +117,9 @@ int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const doub
  * meet the TMA constraints (otherwise use dsvgp_gemm_f32). */
 int dsvgp_gemm_tc_supported_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N);
 int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo, int nsplit, float* split_ws, dsvgp_stream_t s);
+/* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles
+ * (cta_group::2: each CTA stages half of the operands, 2-SM TMA loads, multicast commits).  Returns the value in force. */
+int dsvgp_set_tc_cta_group(int cg);
 int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s);
 int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s);
 

@@ -7,6 +7,8 @@ from dsvgp_b200 import ops
 F32, F64 = torch.float32, torch.float64
 def rel(a, b): return float((a.double() - b.double()).abs().max() / b.double().abs().max())
 torch.manual_seed(0)
+CG = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+print('cta_group', ops.set_tc_cta_group(CG))
 def run(M, N, K, b_kmajor=False, a_tri=0, c_lower=False, chunk=2, alpha=1.0, beta=0.0, dual=False, ldpad=0):
     A = torch.randn(M, K, device="cuda", dtype=F64)
     if a_tri == 1: A = A.tril()
