@@ -29,9 +29,9 @@ int dsvgp_normalize_dirs_canon_f32(const float* v, int rows, int d, float* vh, f
   if (!cidx || !canon_flag) return DSVGP_ERR_ARG;
   return normalize_dirs<float, float>(v, rows, d, vh, inv, ST(s), cidx, canon_flag);
 }
-int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, dsvgp_stream_t s) {
+int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, float* Klo, dsvgp_stream_t s) {
   if (!x1 || !x2 || !hyp || !K || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;
-  return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag);
+  return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag, Klo);
 }
 
 #define KFWD(NAME, T, TK)                                                                                          \
@@ -123,9 +123,9 @@ int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
     return pred_bwd_scalars<T>(gmu, gvar, nq, p2, hyp, add_noise, gsc, ws, ST(s));                                 \
   }                                                                                                                \
   int dsvgp_dA_##SUF(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu,              \
-                     const T* gvar, T* tp, int nslab, T* t, dsvgp_stream_t s) {                                    \
+                     const T* gvar, T* tp, int nslab, T* t, T* Clo, T* Aglo, dsvgp_stream_t s) {                   \
     if (!A || !C || !m || !gmu || !gvar || !tp || !t || nslab < 1) return DSVGP_ERR_ARG;                           \
-    return dA_apply<T>(A, C, Ag, ld, rows, nq, m, gmu, gvar, tp, nslab, t, ST(s));                                 \
+    return dA_apply<T>(A, C, Ag, ld, rows, nq, m, gmu, gvar, tp, nslab, t, Clo, Aglo, ST(s));                      \
   }                                                                                                                \
   int dsvgp_kl_##SUF(const T* m, const T* Ls, int64_t ld, int Mq, double* out, double* ws, dsvgp_stream_t s) {     \
     if (!m || !Ls || !out || !ws) return DSVGP_ERR_ARG;                                                            \

@@ -177,6 +177,14 @@ kdir_fwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, co
   }
 }
 
+// lo = rn_tf32(x - trunc_tf32(x)): the part of x a TF32 tensor core does not see (see trmm_tc.cu)
+__device__ __forceinline__ float tf32_lo_part(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  return __uint_as_float(t);
+}
+
 // ---------------------------------------------------------------------------------- forward (fp32, vectorised)
 // The hot assembly (K_zx of an fp32 model).  A lane owns 4 CONSECUTIVE column points, a warp 128 of them, so
 //   * column-side operands are read from shared memory as one LDS.128 per (c, plane) [layout (plane, c, j), j contiguous],
@@ -199,7 +207,8 @@ template <int P1, int P2>
 __global__ void __launch_bounds__(256, 2)
 kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
             const float* __restrict__ w2, const int* __restrict__ cidx2, const int* __restrict__ canon_flag, int n2, int d,
-            const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk) {
+            const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk,
+            float* __restrict__ Klo) {
   constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ, TIB = V4_TIB;
   const int dpad = (d + 3) & ~3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -364,16 +373,23 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
         *reinterpret_cast<float4*>(mystrip + lane * 4 * Q2 + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
       __syncwarp();
       float* grow = K + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2;
+      float* lrow = Klo ? Klo + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2 : nullptr;   // same leading dimension
 #pragma unroll
       for (int v = 0; v < Q2; ++v) {
         const int col = v * 128 + 4 * lane;
         const float4 t = *reinterpret_cast<const float4*>(mystrip + col);
-        if (vec_ok && col + 3 < cols) {
+        if (vec_ok && col + 3 < cols && (!lrow || (reinterpret_cast<uintptr_t>(Klo) & 15) == 0)) {
           *reinterpret_cast<float4*>(grow + col) = t;
+          if (lrow)
+            *reinterpret_cast<float4*>(lrow + col) =
+                make_float4(tf32_lo_part(t.x), tf32_lo_part(t.y), tf32_lo_part(t.z), tf32_lo_part(t.w));
         } else {
           const float tv[4] = {t.x, t.y, t.z, t.w};
           for (int z = 0; z < 4; ++z)
-            if (col + z < cols) grow[col + z] = tv[z];
+            if (col + z < cols) {
+              grow[col + z] = tv[z];
+              if (lrow) lrow[col + z] = tf32_lo_part(tv[z]);
+            }
         }
       }
     }
@@ -1059,20 +1075,20 @@ static int launch_fwd_blocked(const T* x1, const TK* u1, int n1, const T* x2, co
 template <int P1, int P2>
 static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* x2, const float* w2, const int* cidx2,
                          const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
-                         int64_t ldk, cudaStream_t st) {
+                         int64_t ldk, float* Klo, cudaStream_t st) {
   const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3);
   auto kern = kdir_fwd_v4<P1, P2>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, V4_TIB));
-  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk);
+  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
   CHECK_LAUNCH();
-  return DSVGP_OK;
+  return Klo ? 1 : DSVGP_OK;       // 1: the lo companion was written too
 }
 
 template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
              const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st, const int* cidx2,
-             const int* canon_flag) {
+             const int* canon_flag, TK* Klo) {
   if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
   if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
   if constexpr (sizeof(T) == 4 && sizeof(TK) == 4) {
@@ -1082,7 +1098,7 @@ int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w
     if (n2 >= 512 && need <= 200 * 1024) {
 #define V4_CASE(A, B)                                                                                          \
   if (p1 == A && p2 == B)                                                                                      \
-    return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, st);
+    return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, Klo, st);
       V4_CASE(1, 1) V4_CASE(2, 2) V4_CASE(1, 0) V4_CASE(2, 0) V4_CASE(3, 0)
 #undef V4_CASE
     }
@@ -1233,7 +1249,7 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
 #define INST(T, TK)                                                                                             \
   template int normalize_dirs<T, TK>(const T*, int, int, TK*, TK*, cudaStream_t, int*, int*);                               \
   template int kdir_fwd<T, TK>(const T*, const TK*, int, int, const T*, const TK*, int, int, int, const double*, \
-                               int, double, TK*, int64_t, cudaStream_t, const int*, const int*);                                        \
+                               int, double, TK*, int64_t, cudaStream_t, const int*, const int*, TK*);                                        \
   template int kdir_bwd<T, TK>(const T*, const TK*, const TK*, int, int, const T*, const TK*, int, int, int,    \
                                const double*, int, const TK*, int64_t, int, double, double*, double*, double*,  \
                                void*, size_t, cudaStream_t);

@@ -15,7 +15,8 @@ int normalize_dirs(const T* v, int rows, int d, TK* vhat, TK* inv_norm, cudaStre
 template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
              const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st,
-             const int* cidx2 = nullptr, const int* canon_flag = nullptr);   // canonical column-side fast path (fp32)
+             const int* cidx2 = nullptr, const int* canon_flag = nullptr,   // canonical column-side fast path (fp32)
+             TK* Klo = nullptr);   // fp32 only: also write the TF32 'lo' companion of K; returns 1 if it was written
 
 template <typename TK>
 int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t st);

@@ -268,11 +268,18 @@ pred_bwd_scalars_kernel(const T* __restrict__ gmu, const T* __restrict__ gvar, i
 // ------------------------------------------------------------------------------ backward through mean / variance
 // In place  C_ij <- m_i*gmu_j + 2*gvar_j*C_ij  (= dELBO/dA),  Ag_ij <- A_ij*gvar_j  (left factor of the weighted
 // SYRK G = A diag(gvar) A^T),  tp[s][i] = sum_{j in slab s} A_ij*gmu_j  (= dELBO/dm and the rank-one part of dL).
+__device__ __forceinline__ float tf32_lo(float x) {     // rn_tf32(x - trunc_tf32(x)), see trmm_tc.cu
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  return __uint_as_float(t);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 dA_kernel(const T* __restrict__ A, T* __restrict__ C, T* __restrict__ Ag, int64_t ld, int rows, int nq,
           const T* __restrict__ m, const T* __restrict__ gmu, const T* __restrict__ gvar, int cols_per_slab,
-          T* __restrict__ tp) {
+          T* __restrict__ tp, T* __restrict__ Clo, T* __restrict__ Aglo) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 8 + warp;
   if (i >= rows) return;
@@ -283,8 +290,13 @@ dA_kernel(const T* __restrict__ A, T* __restrict__ C, T* __restrict__ Ag, int64_
     const int64_t o = (int64_t)i * ld + j;
     const T a = A[o], gm = gmu[j], gv = gvar[j];
     t += a * gm;
-    C[o] = mi * gm + T(2) * gv * C[o];
+    const T dA = mi * gm + T(2) * gv * C[o];
+    C[o] = dA;
     if (Ag) Ag[o] = a * gv;
+    if constexpr (sizeof(T) == 4) {
+      if (Clo) Clo[o] = tf32_lo(dA);
+      if (Aglo) Aglo[o] = tf32_lo(a * gv);
+    }
   }
   t = warp_sum(t);
   if (lane == 0) tp[(int64_t)blockIdx.y * rows + i] = t;
@@ -490,12 +502,12 @@ int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* 
 
 template <typename T>
 int dA_apply(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu, const T* gvar, T* tp,
-             int nslab, T* t, cudaStream_t st) {
+             int nslab, T* t, T* Clo, T* Aglo, cudaStream_t st) {
   if (rows <= 0 || nq <= 0) return DSVGP_OK;
   const int cps = ceil_div(ceil_div(nq, nslab), 32) * 32;
   const int ns = ceil_div(nq, cps);
   dim3 grid(ceil_div(rows, 8), ns);
-  dA_kernel<T><<<grid, 256, 0, st>>>(A, C, Ag, ld, rows, nq, m, gmu, gvar, cps, tp);
+  dA_kernel<T><<<grid, 256, 0, st>>>(A, C, Ag, ld, rows, nq, m, gmu, gvar, cps, tp, Clo, Aglo);
   CHECK_LAUNCH();
   sum_parts_kernel<T><<<ceil_div(rows, 256), 256, 0, st>>>(tp, ns, rows, t);
   CHECK_LAUNCH();
@@ -537,7 +549,7 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
                              double*, cudaStream_t);                                                               \
   template int pred_bwd_scalars<T>(const T*, const T*, int, int, const double*, int, double*, double*,             \
                                    cudaStream_t);                                                                  \
-  template int dA_apply<T>(const T*, T*, T*, int64_t, int, int, const T*, const T*, const T*, T*, int, T*,         \
+  template int dA_apply<T>(const T*, T*, T*, int64_t, int, int, const T*, const T*, const T*, T*, int, T*, T*, T*, \
                            cudaStream_t);                                                                          \
   template int kl_divergence<T>(const T*, const T*, int64_t, int, double*, double*, cudaStream_t);                 \
   template int var_grads<T>(const T*, int64_t, const T*, int64_t, const T*, const T*, int, double, T*, T*,         \

@@ -30,7 +30,7 @@ int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* 
                      double* ws, cudaStream_t st);
 template <typename T>
 int dA_apply(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, const T* gmu, const T* gvar, T* tp,
-             int nslab, T* t, cudaStream_t st);
+             int nslab, T* t, T* Clo, T* Aglo, cudaStream_t st);
 template <typename T>
 int kl_divergence(const T* m, const T* Ls, int64_t ld, int Mq, double* out, double* ws, cudaStream_t st);
 template <typename T>

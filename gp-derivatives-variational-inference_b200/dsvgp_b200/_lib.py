@@ -73,10 +73,12 @@ def stream():
 
 
 def call(name, *args):
-    """Call an int-returning entry point on torch's current stream; raise on a non-zero status."""
+    """Call an int-returning entry point on torch's current stream; raise on a negative status.
+    Returns the (non-negative) status: a few entry points use 1 to report an optional extra output."""
     rc = getattr(_lib, name)(*[_arg(a) for a in args], stream())
-    if rc != 0:
+    if rc < 0:
         raise DsvgpError(f"{name} failed: {ERRORS.get(rc, rc)}")
+    return rc
 
 
 def call_raw(name, *args):

@@ -85,7 +85,7 @@ class Workspace:
         self.E, self.Hp = sq(), sq()
         self.tc = T == F32 and USE_TC and Mq >= 128 and nq >= 256
         if self.tc:
-            self.lo1, self.lo2 = e(Mq, self.ldn), e(Mq, self.ldn)        # "lo" parts of the current big operands
+            self.lo1, self.lo2, self.lo3 = (e(Mq, self.ldn) for _ in range(3))   # "lo" parts of the current big operands
             self.E_lo, self.ET, self.ET_lo = sq(), sq(), sq()
             sg = lambda: e(Mq, self.ldg)[:, :Mq]
             self.G_lo, self.H_lo = sg(), sg()
@@ -188,15 +188,17 @@ class Engine:
     def _forward(ws, f, P, x, wx, add_noise, need_C):
         Mq, nq = ws.Mq, ws.nq
         Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
-        ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx, canon=ws.canon)
+        tc = ws.tc and f.tc
+        have_lo = ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx, canon=ws.canon, out_lo=ws.lo1 if tc else None)
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
         ops.tril_minus_eye(P.Ls_raw, ws.E)
-        if ws.tc and f.tc:
+        if tc:
             # tcgen05 path: every operand as (raw, lo); A operands are explicit (transposed) triangular matrices
             ops.split_lo(ws.E, ws.E_lo)
             ops.transpose(ws.E, ws.ET)
             ops.split_lo(ws.ET, ws.ET_lo)
-            ops.split_lo(Kzx, ws.lo1, Mq, nq)
+            if not have_lo:
+                ops.split_lo(Kzx, ws.lo1, Mq, nq)
             ops.gemm_tc(f.Wt, f.Wt_lo, Kzx, ws.lo1, A, Mq, nq, Mq, a_tri=TRI_LOWER, chunk=TC_CHUNK,
                         C_lo=ws.lo2)                                                     # A = L^-1 K_zx  (+ A_lo)
             ops.gemm_tc(ws.ET, ws.ET_lo, A, ws.lo2, ws.Bp, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK,
@@ -225,17 +227,17 @@ class Engine:
         T, Mq, nq = x.dtype, ws.Mq, ws.nq
         A, Ag, C, dKzx = ws.A, ws.B, ws.C, ws.Kzx
         ops.pred_bwd_scalars(gmu, gvar, ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)
-        ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t)                      # C <- dA ; Ag ; t = A gmu
         tc = ws.tc and f.tc
+        ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t,                      # C <- dA ; Ag ; t = A gmu
+                     C_lo=ws.lo1 if tc else None, Ag_lo=ws.lo3 if tc else None)          # (+ their lo parts)
         if tc:
-            ops.split_lo(C, ws.lo1, Mq, nq)
             ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
         else:
             ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
         ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
         if tc:                                                                           # G = A diag(gvar) A^T
-            ops.split_lo(Ag, ws.lo1, Mq, nq)                                             # (A_lo is still in ws.lo2)
-            ops.gemm_tc(Ag, ws.lo1, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
+            # (A_lo is still in ws.lo2 from the forward pass)
+            ops.gemm_tc(Ag, ws.lo3, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
                         nsplit=ws.syrk_split, split_ws=ws.split_ws)
         else:
             ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)

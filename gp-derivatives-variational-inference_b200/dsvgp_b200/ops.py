@@ -54,19 +54,22 @@ def normalize_dirs_canon(v):
     return vhat, inv, cidx, flag
 
 
-def kdir_fwd(x1, u1, p1, x2, w2, p2, hyp, out, use_os=True, diag_add=0.0, canon=None):
+def kdir_fwd(x1, u1, p1, x2, w2, p2, hyp, out, use_os=True, diag_add=0.0, canon=None, out_lo=None):
     """out[:n1(p1+1), :n2(p2+1)] = [os*] K(x1, x2; u1, w2) (+ diag_add on the diagonal).
-    canon = (cidx, flag) from normalize_dirs_canon(v2) enables the canonical-direction fast path (fp32)."""
+    canon = (cidx, flag) from normalize_dirs_canon(v2) enables the canonical-direction fast path (fp32).
+    out_lo (fp32, same leading dimension): TF32 'lo' companion; the return value says whether it was written."""
     n1, d = x1.shape
     n2 = x2.shape[0]
     assert out.shape[0] >= n1 * (p1 + 1) and out.shape[1] >= n2 * (p2 + 1)
-    if canon is not None and p2 and x1.dtype == F32 and out.dtype == F32:
-        call("dsvgp_kdir_fwd_canon_f32", x1, u1 if p1 else None, n1, p1, x2, w2, canon[0], canon[1], n2, p2, d, hyp,
-             int(use_os), float(diag_add), out, _ld(out))
-        return out
+    if x1.dtype == F32 and out.dtype == F32 and (canon is not None or out_lo is not None):
+        assert out_lo is None or _ld(out_lo) == _ld(out)
+        cidx, flag = canon if (canon is not None and p2) else (None, None)
+        rc = call("dsvgp_kdir_fwd_canon_f32", x1, u1 if p1 else None, n1, p1, x2, w2 if p2 else None, cidx, flag, n2, p2, d,
+                  hyp, int(use_os), float(diag_add), out, _ld(out), out_lo)
+        return rc == 1
     call("dsvgp_kdir_fwd_" + _pair_suffix(x1.dtype, out.dtype), x1, u1 if p1 else None, n1, p1, x2,
          w2 if p2 else None, n2, p2, d, hyp, int(use_os), float(diag_add), out, _ld(out))
-    return out
+    return False
 
 
 def kdir_diag(n, p, hyp, dtype, use_os=True):
@@ -223,8 +226,8 @@ def pred_bwd_scalars(gmu, gvar, p2, hyp, add_noise, gsc, ws):
     call("dsvgp_pred_bwd_scalars_" + suffix(gmu.dtype), gmu, gvar, gmu.numel(), p2, hyp, int(add_noise), gsc, ws)
 
 
-def dA_apply(A, C, Ag, rows, nq, m, gmu, gvar, tp, t):
-    call("dsvgp_dA_" + suffix(A.dtype), A, C, Ag, _ld(A), rows, nq, m, gmu, gvar, tp, tp.shape[0], t)
+def dA_apply(A, C, Ag, rows, nq, m, gmu, gvar, tp, t, C_lo=None, Ag_lo=None):
+    call("dsvgp_dA_" + suffix(A.dtype), A, C, Ag, _ld(A), rows, nq, m, gmu, gvar, tp, tp.shape[0], t, C_lo, Ag_lo)
 
 
 def kl_divergence(m, Ls_raw, out, ws):

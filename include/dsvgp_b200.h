@@ -69,9 +69,11 @@ int dsvgp_kdir_fwd_f32f64(const float* x1, const double* u1, int n1, int p1, con
  * direction row, the coordinate of its single non-zero entry (sign in bit 31) and clears *canon_flag (device int, set
  * to 1 by the caller) if any row is not one-hot.  dsvgp_kdir_fwd_canon_f32 takes those for the SECOND argument's
  * directions: when the flag is still set -- eye(d) rows, which is what train_gp / eval_gp pass (directional_vi.py:87-88,
- * :292-293) -- D.w and u.w become lookups.  Decided on the device, no host synchronisation; results are identical. */
+ * :292-293) -- D.w and u.w become lookups.  Decided on the device, no host synchronisation; results are identical.
+ * Klo (optional, same leading dimension as K): TF32 'lo' companion of K for dsvgp_gemm_tc_f32; the call returns 1
+ * instead of 0 when it was written (the vectorised kernel took the shape), otherwise use dsvgp_split_lo_f32. */
 int dsvgp_normalize_dirs_canon_f32(const float* v, int rows, int d, float* vhat, float* inv_norm, int* cidx, int* canon_flag, dsvgp_stream_t s);
-int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, dsvgp_stream_t s);
+int dsvgp_kdir_fwd_canon_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, float* Klo, dsvgp_stream_t s);
 
 /* diag=True branch -- RBFKernelDirectionalGrad.py:110-119 */
 int dsvgp_kdir_diag_f32(int n, int p, const double* hyp, int use_os, float* out, dsvgp_stream_t s);
@@ -163,9 +165,9 @@ int dsvgp_pred_bwd_scalars_f32(const float* gmu, const float* gvar, int nq, int 
 int dsvgp_pred_bwd_scalars_f64(const double* gmu, const double* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc, double* ws, dsvgp_stream_t s);
 
 /* In place C <- m gmu^T + 2 C diag(gvar) (= dL/dA); Ag <- A diag(gvar) (NULL to skip); t = A gmu.
- * tp: nslab*rows scratch. */
-int dsvgp_dA_f32(const float* A, float* C, float* Ag, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, dsvgp_stream_t s);
-int dsvgp_dA_f64(const double* A, double* C, double* Ag, int64_t ld, int rows, int nq, const double* m, const double* gmu, const double* gvar, double* tp, int nslab, double* t, dsvgp_stream_t s);
+ * tp: nslab*rows scratch.  Clo / Aglo (optional, fp32 only): TF32 'lo' companions of the new C and of Ag. */
+int dsvgp_dA_f32(const float* A, float* C, float* Ag, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, float* Clo, float* Aglo, dsvgp_stream_t s);
+int dsvgp_dA_f64(const double* A, double* C, double* Ag, int64_t ld, int rows, int nq, const double* m, const double* gmu, const double* gvar, double* tp, int nslab, double* t, double* Clo, double* Aglo, dsvgp_stream_t s);
 
 /* KL(N(m, Ls Ls^T) || N(0, I)) with Ls = tril(raw) (_VariationalStrategy.kl_divergence, gpytorch);
  * out[0] += KL.  ws: 296 doubles. */
