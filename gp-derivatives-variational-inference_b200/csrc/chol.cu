@@ -185,17 +185,22 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // block and panel need) and goes straight to the next diagonal block; the rest of the trailing update runs on a side
   // stream.  Events order (a) side(k) after panel(k), (b) the column update of step k+1 after side(k) (both write block
   // column k+2).  Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_main[64], ev_side[64];
-  static bool ev_ready = false;
-  if (!ev_ready) {
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+  struct SideCtx { cudaStream_t side = nullptr; cudaEvent_t ev_main[64], ev_side[64]; bool ready = false; };
+  static SideCtx ctxs[16];                              // one side stream + event pool per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideCtx& sc = ctxs[dev & 15];
+  if (!sc.ready) {
+    if (cudaStreamCreateWithFlags(&sc.side, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     for (int i = 0; i < 64; ++i) {
-      cudaEventCreateWithFlags(&ev_main[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_side[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&sc.ev_main[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&sc.ev_side[i], cudaEventDisableTiming);
     }
-    ev_ready = true;
+    sc.ready = true;
   }
+  cudaStream_t side = sc.side;
+  cudaEvent_t* ev_main = sc.ev_main;
+  cudaEvent_t* ev_side = sc.ev_side;
   const bool lookahead = nblk >= 4 && nblk <= 64;
   int last_side = -1;
   for (int k = 0; k < nblk; ++k) {

@@ -66,6 +66,7 @@ class Factor:
             self.Wt_lo, self.WtT, self.WtT_lo = mk(), mk(), mk()
         self.uzT = self.invzT = self.uz64 = self.invz64 = None
         self.valid = False
+        self.owner = None          # (strategy id, parameter versions) the memoised factor belongs to
 
 
 class Workspace:
@@ -340,6 +341,11 @@ class Engine:
         return self._collect(ws, f, P, x.dtype, ws.sc[6])
 
     # ------------------------------------------------------------------------------------------ public: eval
+    @staticmethod
+    def _owner_token(P):
+        """identity + in-place version of every parameter the factor depends on"""
+        return tuple((t.data_ptr(), t._version) for t in (P.Z, P.Vz, P.raw_ell, P.raw_os, P.c) if t is not None)
+
     def predict(self, P, x, Vx, p, p2, add_noise, reuse_factor=False):
         """eval_gp's per-batch prediction (directional_vi.py:296-298).  reuse_factor: eval-mode memoisation of
         the Cholesky factor (DGVS.py:72) -- K_zz is factorised once and reused until the strategy invalidates it."""
@@ -348,7 +354,8 @@ class Engine:
         M = P.Z.shape[0]
         ws = self.workspace(x.device, T, n, d, M, p, p2)
         f = self.factor(x.device, T, d, M, p)
-        if not (reuse_factor and f.valid):
+        token = self._owner_token(P)
+        if not (reuse_factor and f.valid and f.owner == token):
             f.valid = False
             for extra in (0.0,) + CHOL_RETRY:
                 self._factorise(f, P, T, extra)
@@ -357,6 +364,7 @@ class Engine:
             else:
                 raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4")
             f.valid = reuse_factor
+            f.owner = token
         wx = self._data_dirs(ws, Vx, T)
         self._forward(ws, f, P, x, wx, add_noise, need_C=False)
         return ws.mu.clone(), ws.var.clone()

@@ -203,6 +203,27 @@ def test_training_reduces_loss_and_checkpoint_roundtrip(tmp_path):
     assert rel(means2, means) < 1e-5 and rel(variances2, variances) < 1e-5
 
 
+def test_eval_factor_cache_is_per_model_and_follows_parameters():
+    """Eval-mode memoisation of the Cholesky factor (DGVS.py:72) must not leak between two models of the same shape,
+    and must be dropped when parameters change in place or train() is called."""
+    P1, x, Vx, y, nd = O.make_problem(40, 3, 12, 2, F64, 21)
+    P2, _, _, _, _ = O.make_problem(40, 3, 12, 2, F64, 22)
+    m1, l1 = build("dsvgp", P1, 3, F64)
+    m2, l2 = build("dsvgp", P2, 3, F64)
+    for m, l in ((m1, l1), (m2, l2)):
+        m.eval(), l.eval()
+    with torch.no_grad():
+        a1 = l1(m1(x.cuda(), derivative_directions=Vx)).mean
+        a2 = l2(m2(x.cuda(), derivative_directions=Vx)).mean
+        b1 = l1(m1(x.cuda(), derivative_directions=Vx)).mean
+    assert rel(a1, O.predict(P1, x, Vx)[0]) < 1e-10 and rel(a2, O.predict(P2, x, Vx)[0]) < 1e-10 and rel(b1, a1) < 1e-14
+    with torch.no_grad():
+        m1.variational_strategy.inducing_points.add_(0.01)
+        P1.Z = P1.Z + 0.01
+        c1 = l1(m1(x.cuda(), derivative_directions=Vx)).mean
+    assert rel(c1, O.predict(P1, x, Vx)[0]) < 1e-10
+
+
 def test_cholesky_jitter_ladder_and_errors():
     """psd_safe_cholesky semantics: duplicate inducing points + tiny outputscale still factorise thanks to the 1e-3
     jitter; NaN parameters raise NanError; an indefinite matrix raises NotPSDError."""
