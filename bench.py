@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
         return self
@@ -311,7 +311,10 @@ def main():
         kname = ("gemm_kernel (A = L^-1 K_zx, fp64 DMMA mma.sync)" if dtype == torch.float64
                  else "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)")
     ms_gemm = timed_local(whiten, reps)
-    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon), reps)
+    # kernel assembly as the step runs it (K_zx plus, on the tcgen05 path, its TF32 "lo" companion) and K only
+    asm_lo = ws.lo1 if use_tc else None
+    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon, out_lo=asm_lo), reps)
+    ms_asm_k = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon), reps)
     ms_asm_general = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
     s = 8 if dtype == torch.float64 else 4
     gemm_flops = float(Mq) * Mq * nq
@@ -333,12 +336,18 @@ def main():
                      "achieved": gemm_flops / (ms_gemm * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": gemm_flops / (ms_gemm * 1e-3) / 1e12 / tensor_peak, "traffic": ncu_traffic("gemm_whiten"),
                      "ms": ms_gemm, "flops_per_launch": gemm_flops, "peak_note": peak_note},
-        "roofline_assembly": {"kernel": "kdir_fwd_v4 / kdir_fwd_blocked (K_zx)", "bound": "hbm", "achieved": asm_bytes / (ms_asm * 1e-3) / 1e9,
-                              "peak": pk["hbm"], "unit": "GB/s", "frac": asm_bytes / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
-                              "traffic": ncu_traffic("kdir_fwd"), "ms": ms_asm, "bytes_per_launch": asm_bytes,
+        "roofline_assembly": {"kernel": "kdir_fwd_v4 / kdir_fwd_blocked (K_zx), K only -- what RBFKernelDirectionalGrad.forward returns",
+                              "bound": "hbm", "achieved": asm_bytes / (ms_asm_k * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                              "frac": asm_bytes / (ms_asm_k * 1e-3) / 1e9 / pk["hbm"], "traffic": ncu_traffic("kdir_fwd_k_only"),
+                              "ms": ms_asm_k, "bytes_per_launch": asm_bytes,
                               "path": "canonical data-side directions (detected on device)" if ws.canon is not None else "general directions",
                               "general_directions_ms": ms_asm_general,
                               "general_directions_frac": asm_bytes / (ms_asm_general * 1e-3) / 1e9 / pk["hbm"],
+                              "in_step": {"note": "inside the training step the same launch also writes the TF32 lo companion of K_zx "
+                                                  "(fused, replaces a separate split pass): twice the bytes",
+                                          "ms": ms_asm, "bytes_written": asm_bytes * (2 if use_tc else 1),
+                                          "hbm_frac": asm_bytes * (2 if use_tc else 1) / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
+                                          "traffic": ncu_traffic("kdir_fwd")},
                               "peak_note": f"{pk['src']} copy bandwidth"},
     }
     if world == 1 and not args.no_cpu_baseline:

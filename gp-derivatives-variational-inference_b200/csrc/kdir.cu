@@ -203,8 +203,11 @@ size_t fwd_v4_smem_bytes(int dpad) {
   return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * dpad + (P2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (P2 + 1));
 }
 
-template <int P1, int P2>
-__global__ void __launch_bounds__(256, 2)
+// MODE 0: general directions only (returns at once if the device flag says canonical); MODE 1: canonical only (returns
+// at once otherwise).  Both are launched back to back when a flag is supplied: the choice is made on the device without
+// a host synchronisation, and the canonical variant compiles to far fewer registers (3 CTAs per SM instead of 2).
+template <int P1, int P2, bool WITH_LO, int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 3 : 2)
 kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
             const float* __restrict__ w2, const int* __restrict__ cidx2, const int* __restrict__ canon_flag, int n2, int d,
             const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk,
@@ -217,7 +220,9 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
   float* strip = cs + Q2 * dpad * TJ;                      // [8 warps][TJ*Q2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = blockIdx.y * TIB, j0 = blockIdx.x * TJ;
-  const bool canon = (P2 > 0) && cidx2 != nullptr && canon_flag != nullptr && (*canon_flag != 0);
+  const bool flag_set = (P2 > 0) && cidx2 != nullptr && canon_flag != nullptr && (*canon_flag != 0);
+  if ((MODE == 1) != flag_set) return;                      // grid-uniform
+  constexpr bool canon = MODE == 1;
 
   for (int e = tid; e < TIB * Q1 * dpad; e += 256) {       // row side: consecutive threads -> consecutive c
     const int cc = e % dpad, ia = e / dpad, i = ia / Q1, a = ia % Q1;
@@ -241,7 +246,7 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
   // canonical column directions: coordinate index / sign of this lane's 4 points, and x2 at that coordinate
   int cix[P2 > 0 ? P2 : 1][4];
   float csg[P2 > 0 ? P2 : 1][4], xjc[P2 > 0 ? P2 : 1][4];
-  if (canon) {
+  if constexpr (canon) {
 #pragma unroll
     for (int b = 0; b < P2; ++b)
 #pragma unroll
@@ -277,7 +282,7 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
         for (int b = 0; b < P2; ++b) ga[a][b][q] = 0.f;
     }
-    if (!canon) {
+    if constexpr (!canon) {
       for (int c4 = 0; c4 < dpad; c4 += 4) {
         const float4 xr = *reinterpret_cast<const float4*>(rbase + c4);
         float4 ur[P1 > 0 ? P1 : 1];
@@ -373,14 +378,14 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
         *reinterpret_cast<float4*>(mystrip + lane * 4 * Q2 + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
       __syncwarp();
       float* grow = K + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2;
-      float* lrow = Klo ? Klo + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2 : nullptr;   // same leading dimension
+      float* lrow = WITH_LO ? Klo + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2 : nullptr;   // same leading dimension
 #pragma unroll
       for (int v = 0; v < Q2; ++v) {
         const int col = v * 128 + 4 * lane;
         const float4 t = *reinterpret_cast<const float4*>(mystrip + col);
-        if (vec_ok && col + 3 < cols && (!lrow || (reinterpret_cast<uintptr_t>(Klo) & 15) == 0)) {
+        if (vec_ok && col + 3 < cols && (!WITH_LO || (reinterpret_cast<uintptr_t>(Klo) & 15) == 0)) {
           *reinterpret_cast<float4*>(grow + col) = t;
-          if (lrow)
+          if constexpr (WITH_LO)
             *reinterpret_cast<float4*>(lrow + col) =
                 make_float4(tf32_lo_part(t.x), tf32_lo_part(t.y), tf32_lo_part(t.z), tf32_lo_part(t.w));
         } else {
@@ -388,7 +393,7 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
           for (int z = 0; z < 4; ++z)
             if (col + z < cols) {
               grow[col + z] = tv[z];
-              if (lrow) lrow[col + z] = tf32_lo_part(tv[z]);
+              if constexpr (WITH_LO) lrow[col + z] = tf32_lo_part(tv[z]);
             }
         }
       }
@@ -1077,11 +1082,17 @@ static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* 
                          const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
                          int64_t ldk, float* Klo, cudaStream_t st) {
   const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3);
-  auto kern = kdir_fwd_v4<P1, P2>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, V4_TIB));
-  kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
+  auto gen = Klo ? kdir_fwd_v4<P1, P2, true, 0> : kdir_fwd_v4<P1, P2, false, 0>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gen<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
   CHECK_LAUNCH();
+  if (P2 > 0 && cidx2 && canon_flag) {
+    auto can = Klo ? kdir_fwd_v4<P1, P2, true, 1> : kdir_fwd_v4<P1, P2, false, 1>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(can, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    can<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
+    CHECK_LAUNCH();
+  }
   return Klo ? 1 : DSVGP_OK;       // 1: the lo companion was written too
 }
 
