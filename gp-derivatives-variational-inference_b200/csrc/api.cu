@@ -2,20 +2,29 @@
 #include "../../include/dsvgp_b200.h"
 #include "chol.cuh"
 #include "common.cuh"
+#include "data.cuh"
 #include "gemm.cuh"
 #include "kdir.cuh"
 #include "misc.cuh"
+#include "optim.cuh"
 #include "trmm_tc.cuh"
 
 using namespace dsvgp;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 namespace dsvgp { unsigned long long g_launch_count = 0; }
+namespace dsvgp { extern int g_fwd_tib, g_fwd_stream_stores; }
 
 extern "C" {
 
 int dsvgp_version(void) { return 100; }
 int64_t dsvgp_launch_count(void) { return (int64_t)dsvgp::g_launch_count; }
+int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores) {
+  const int old = dsvgp::g_fwd_tib * 4 + dsvgp::g_fwd_stream_stores;
+  if (tib >= 8 && tib <= 64 && tib % 8 == 0) dsvgp::g_fwd_tib = tib;
+  if (stream_stores >= 0 && stream_stores <= 2) dsvgp::g_fwd_stream_stores = stream_stores;
+  return old;
+}
 int dsvgp_built_for_sm(void) { return 100; }
 
 int dsvgp_hyp_from_raw_f32(const float* a, const float* b, const float* c, const float* d, double* hyp, dsvgp_stream_t s) { return hyp_from_raw<float>(a, b, c, d, hyp, ST(s)); }
@@ -138,5 +147,11 @@ int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
   }
 PER_T(f32, float)
 PER_T(f64, double)
+
+int dsvgp_adam_step_f32(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s) { return adam_step<float>(ntensors, desc_host, ngroups, group_host, ST(s)); }
+int dsvgp_adam_step_f64(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s) { return adam_step<double>(ntensors, desc_host, ngroups, group_host, ST(s)); }
+
+int dsvgp_gather_batch_f32(const float* X, const float* Y, int64_t N, int d, int ycols, const int64_t* idx, int n, int p, const int* cols_host, float* xb, float* yb, float* V, dsvgp_stream_t s) { return gather_batch<float>(X, Y, N, d, ycols, idx, n, p, cols_host, xb, yb, V, ST(s)); }
+int dsvgp_gather_batch_f64(const double* X, const double* Y, int64_t N, int d, int ycols, const int64_t* idx, int n, int p, const int* cols_host, double* xb, double* yb, double* V, dsvgp_stream_t s) { return gather_batch<double>(X, Y, N, d, ycols, idx, n, p, cols_host, xb, yb, V, ST(s)); }
 
 }  // extern "C"

@@ -28,6 +28,20 @@ void chol_plan(int Mq, int* Mp, int* nb0, int* nlev) {
   *nlev = k;
 }
 
+// 1/sqrt(d) and sqrt(d) without the library sqrt + division (two long dependent sequences per pivot, 96 pivots on
+// the critical path of every diagonal block): fp32 rsqrt seed (relative error e ~ 2^-21), one third-order step
+// y <- y (1 + e/2 + 3e^2/8), e = 1 - d y^2 (error ~ e^3 = 2^-63), then l = d*y with one Newton correction.  Both
+// results are within 1 ulp.  Only used for d inside the fp32 normal range; the caller keeps sqrt()/division outside it.
+__device__ __forceinline__ void rsqrt_sqrt_f64(double d, double& rinv, double& root) {
+  double y = (double)rsqrtf((float)d);
+  const double e = fma(-d * y, y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  double l = d * y;
+  l = fma(fma(-l, l, d), 0.5 * y, l);
+  rinv = y;
+  root = l;
+}
+
 // Factorise the nb x nb block at A (lower part read) and invert the factor, both inside one CTA in shared memory,
 // blocked by 8 columns so that almost all work is rank-8 updates (8 FMAs per shared-memory element touched) and only
 // 2 block barriers per 8 columns are on the critical path:
@@ -61,14 +75,16 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double d = __shfl_sync(0xffffffffu, a[k], k);
-        double ljj;
+        double ljj, rinv;
         if (!(d > 0.0)) {                              // also catches NaN
           if (lane == 0) atomicCAS(info, 0, row_offset + k0 + k + 1);
-          ljj = nan("");
+          ljj = rinv = nan("");
+        } else if (d > 1e-30 && d < 1e30) {
+          rsqrt_sqrt_f64(d, rinv, ljj);
         } else {
           ljj = sqrt(d);
+          rinv = 1.0 / ljj;
         }
-        const double rinv = 1.0 / ljj;
         if (r == k) {
           a[k] = ljj;
           if (lane < 8) rdg[k0 + k] = rinv;

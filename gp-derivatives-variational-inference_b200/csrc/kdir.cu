@@ -198,9 +198,13 @@ __device__ __forceinline__ float tf32_lo_part(float x) {
 // products, and the per-pair work drops from (1+p1)(1+p2) to (1+p1) FMAs per coordinate.
 constexpr int V4_TJ = 128, V4_TIB = 64;
 
+int g_fwd_tib = V4_TIB;        // row points per CTA of kdir_fwd_v4 (benchmarking knob, multiple of 8, <= V4_TIB)
+int g_fwd_stream_stores = 2;   // 1: st.global.cs (evict-first) for the K / K_lo rows; 2 (default): when the output is
+                               // larger than half of the 126 MB L2 (measured on C3: K only 0.144 -> 0.136 ms, K + lo 0.209 -> 0.195 ms)
+
 template <int P1, int P2>
-size_t fwd_v4_smem_bytes(int dpad) {
-  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * dpad + (P2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (P2 + 1));
+size_t fwd_v4_smem_bytes(int dpad, int tib = V4_TIB) {
+  return sizeof(float) * (size_t)(tib * (P1 + 1) * dpad + (P2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (P2 + 1));
 }
 
 // MODE 0: general directions only (returns at once if the device flag says canonical); MODE 1: canonical only (returns
@@ -211,8 +215,8 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 3 : 2)
 kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
             const float* __restrict__ w2, const int* __restrict__ cidx2, const int* __restrict__ canon_flag, int n2, int d,
             const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk,
-            float* __restrict__ Klo) {
-  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ, TIB = V4_TIB;
+            float* __restrict__ Klo, int TIB, int stream_stores) {
+  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ;
   const int dpad = (d + 3) & ~3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* rs = reinterpret_cast<float*>(smem_raw);          // [TIB][Q1][dpad]   row point i: x1_i then u_i1..u_iP1
@@ -384,10 +388,13 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
         const int col = v * 128 + 4 * lane;
         const float4 t = *reinterpret_cast<const float4*>(mystrip + col);
         if (vec_ok && col + 3 < cols && (!WITH_LO || (reinterpret_cast<uintptr_t>(Klo) & 15) == 0)) {
-          *reinterpret_cast<float4*>(grow + col) = t;
-          if constexpr (WITH_LO)
-            *reinterpret_cast<float4*>(lrow + col) =
-                make_float4(tf32_lo_part(t.x), tf32_lo_part(t.y), tf32_lo_part(t.z), tf32_lo_part(t.w));
+          if (stream_stores) __stcs(reinterpret_cast<float4*>(grow + col), t);
+          else *reinterpret_cast<float4*>(grow + col) = t;
+          if constexpr (WITH_LO) {
+            const float4 tl = make_float4(tf32_lo_part(t.x), tf32_lo_part(t.y), tf32_lo_part(t.z), tf32_lo_part(t.w));
+            if (stream_stores) __stcs(reinterpret_cast<float4*>(lrow + col), tl);
+            else *reinterpret_cast<float4*>(lrow + col) = tl;
+          }
         } else {
           const float tv[4] = {t.x, t.y, t.z, t.w};
           for (int z = 0; z < 4; ++z)
@@ -1081,16 +1088,21 @@ template <int P1, int P2>
 static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* x2, const float* w2, const int* cidx2,
                          const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
                          int64_t ldk, float* Klo, cudaStream_t st) {
-  const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3);
-  dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, V4_TIB));
+  const int tib = g_fwd_tib;
+  const int64_t out_bytes = (int64_t)n1 * (P1 + 1) * n2 * (P2 + 1) * 4 * (Klo ? 2 : 1);
+  const int stream_stores = g_fwd_stream_stores == 2 ? (out_bytes > (int64_t)(64 << 20)) : g_fwd_stream_stores;
+  const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3, tib);
+  dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, tib));
   auto gen = Klo ? kdir_fwd_v4<P1, P2, true, 0> : kdir_fwd_v4<P1, P2, false, 0>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gen<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
+  gen<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo, tib,
+                               stream_stores);
   CHECK_LAUNCH();
   if (P2 > 0 && cidx2 && canon_flag) {
     auto can = Klo ? kdir_fwd_v4<P1, P2, true, 1> : kdir_fwd_v4<P1, P2, false, 1>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(can, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    can<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo);
+    can<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo, tib,
+                                 stream_stores);
     CHECK_LAUNCH();
   }
   return Klo ? 1 : DSVGP_OK;       // 1: the lo companion was written too

@@ -286,7 +286,35 @@ dA_kernel(const T* __restrict__ A, T* __restrict__ C, T* __restrict__ Ag, int64_
   const int c0 = blockIdx.y * cols_per_slab, c1 = min(nq, c0 + cols_per_slab);
   const T mi = m[i];
   T t = 0;
-  for (int j = c0 + lane; j < c1; j += 32) {
+  int jstart = c0;
+  if constexpr (sizeof(T) == 4) {
+    // 16-byte path: a lane owns 4 consecutive columns; every array is read / written once, the four outputs
+    // (2.4 GB at C3) with evict-first stores -- they are consumed once by the next GEMM and exceed L2 anyway
+    const bool al = ((ld & 3) == 0) && ((c0 & 3) == 0) &&
+                    (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(Ag) |
+                       reinterpret_cast<uintptr_t>(Clo) | reinterpret_cast<uintptr_t>(Aglo) |
+                       reinterpret_cast<uintptr_t>(gmu) | reinterpret_cast<uintptr_t>(gvar)) & 15) == 0);
+    if (al) {
+      const int cvec = c0 + ((c1 - c0) & ~3);
+      for (int j = c0 + 4 * lane; j < cvec; j += 128) {
+        const int64_t o = (int64_t)i * ld + j;
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(A + o));
+        const float4 c = __ldcs(reinterpret_cast<const float4*>(C + o));
+        const float4 gm = *reinterpret_cast<const float4*>(gmu + j);
+        const float4 gv = *reinterpret_cast<const float4*>(gvar + j);
+        t += a.x * gm.x + a.y * gm.y + a.z * gm.z + a.w * gm.w;
+        const float4 dA = make_float4(mi * gm.x + 2.f * gv.x * c.x, mi * gm.y + 2.f * gv.y * c.y,
+                                      mi * gm.z + 2.f * gv.z * c.z, mi * gm.w + 2.f * gv.w * c.w);
+        const float4 ag = make_float4(a.x * gv.x, a.y * gv.y, a.z * gv.z, a.w * gv.w);
+        __stcs(reinterpret_cast<float4*>(C + o), dA);
+        if (Ag) __stcs(reinterpret_cast<float4*>(Ag + o), ag);
+        if (Clo) __stcs(reinterpret_cast<float4*>(Clo + o), make_float4(tf32_lo(dA.x), tf32_lo(dA.y), tf32_lo(dA.z), tf32_lo(dA.w)));
+        if (Aglo) __stcs(reinterpret_cast<float4*>(Aglo + o), make_float4(tf32_lo(ag.x), tf32_lo(ag.y), tf32_lo(ag.z), tf32_lo(ag.w)));
+      }
+      jstart = cvec;
+    }
+  }
+  for (int j = jstart + lane; j < c1; j += 32) {
     const int64_t o = (int64_t)i * ld + j;
     const T a = A[o], gm = gmu[j], gv = gvar[j];
     t += a * gm;

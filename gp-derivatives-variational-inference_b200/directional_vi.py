@@ -15,6 +15,8 @@ import torch
 from torch.utils.data import DataLoader, TensorDataset
 
 from dsvgp_b200 import gp
+from dsvgp_b200.data import DeviceMinibatchSampler
+from dsvgp_b200.optim import FusedAdam
 
 from utils.count_params import count_params
 
@@ -71,6 +73,25 @@ def _batches(dataset, batch_size, shuffle, device):
             yield tuple(t.to(device) for t in batch)
 
 
+def _train_batches(dataset, batch_size, minibatch_dim, dim, device, dtype):
+    """Yield (x, interleaved y of the selected columns, per-point direction rows) for one epoch.  A TensorDataset
+    stays resident in HBM and every minibatch is one fused gather launch (dsvgp_b200/data.py); the column draw is
+    the reference's (`random.sample`, :75-77), so the same `random.seed` selects the same columns."""
+    if isinstance(dataset, TensorDataset) and len(dataset.tensors) == 2 and dataset.tensors[0].dtype == dataset.tensors[1].dtype:
+        sampler = getattr(dataset, "_dsvgp_sampler", None)
+        if sampler is None or sampler.batch_size != batch_size or sampler.x.device != device:
+            sampler = DeviceMinibatchSampler(dataset.tensors[0], dataset.tensors[1], batch_size, device)
+            dataset._dsvgp_sampler = sampler
+        for idx in sampler.epoch():
+            cols = DeviceMinibatchSampler.draw_columns(minibatch_dim, dim)
+            yield sampler.gather(idx, cols)
+        return
+    for x_batch, y_batch in _batches(dataset, batch_size, True, device):
+        y_batch, derivative_directions = select_cols_of_y(y_batch, minibatch_dim, dim)
+        yield (x_batch, y_batch.reshape(torch.numel(y_batch)),          # interleaved [f, d1..dp] per point
+               derivative_directions.to(dtype).repeat(y_batch.size(0), 1))
+
+
 def _initial_inducing(train_dataset, num_inducing, num_directions, dim, inducing_data_initialization):
     inducing_directions = torch.eye(dim)[:num_directions].repeat(num_inducing, 1)
     if inducing_data_initialization is True:
@@ -81,9 +102,12 @@ def _initial_inducing(train_dataset, num_inducing, num_directions, dim, inducing
 
 
 def _optimizers(model, likelihood, lr, lr_sched, n_samples, minibatch_size, num_epochs, gamma):
-    variational_optimizer = torch.optim.Adam([{"params": model.variational_parameters()}], lr=lr)
-    hyperparameter_optimizer = torch.optim.Adam([{"params": model.hyperparameters()},
-                                                 {"params": likelihood.parameters()}], lr=lr)
+    # same two optimisers and parameter groups as the reference (:192-199); each step() is one fused launch
+    vd = model.variational_strategy._variational_distribution
+    variational_optimizer = FusedAdam([{"params": model.variational_parameters()}], lr=lr,
+                                      lower_triangular=[vd.chol_variational_covar])
+    hyperparameter_optimizer = FusedAdam([{"params": model.hyperparameters()},
+                                          {"params": likelihood.parameters()}], lr=lr)
     if lr_sched == "step_lr":
         num_batches = int(np.ceil(n_samples / minibatch_size))
         milestones = [int(num_epochs * num_batches / 3), int(2 * num_epochs * num_batches / 3)]
@@ -133,10 +157,9 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
     total_step = 0
     loss = None
     for i in range(num_epochs):
-        for x_batch, y_batch in _batches(train_dataset, minibatch_size, True, device):
-            y_batch, derivative_directions = select_cols_of_y(y_batch, minibatch_dim, dim)
-            kwargs = {"derivative_directions": derivative_directions.to(dtype).repeat(y_batch.size(0), 1)}
-            y_batch = y_batch.reshape(torch.numel(y_batch))      # interleaved [f, d1..dp] per point
+        for x_batch, y_batch, derivative_directions in _train_batches(train_dataset, minibatch_size, minibatch_dim, dim,
+                                                                      device, dtype):
+            kwargs = {"derivative_directions": derivative_directions}
             variational_optimizer.zero_grad()
             hyperparameter_optimizer.zero_grad()
             output = likelihood(model(x_batch, **kwargs))

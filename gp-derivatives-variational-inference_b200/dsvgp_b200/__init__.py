@@ -6,13 +6,14 @@ at call time.
 """
 from . import _lib, ops  # noqa: F401  (fails loudly if the extension is missing)
 from .engine import ENGINE, NanError, NotPSDError
+from .optim import FusedAdam
 from .gp import (ApproximateGP, CholeskyVariationalDistribution, ConstantMean, DFreeDirectionalGradVariationalStrategy,
                  DirectionalGradVariationalStrategy, GaussianLikelihood, GradVariationalStrategy, MultivariateNormal,
                  PredictiveDistribution, PredictiveLogLikelihood, RBFKernelDirectionalGrad, RBFKernelGrad, ScaleKernel,
                  VariationalELBO)
 
 __all__ = ["ENGINE", "NanError", "NotPSDError", "ApproximateGP", "CholeskyVariationalDistribution", "ConstantMean",
-           "DFreeDirectionalGradVariationalStrategy", "DirectionalGradVariationalStrategy", "GaussianLikelihood",
+           "DFreeDirectionalGradVariationalStrategy", "DirectionalGradVariationalStrategy", "FusedAdam", "GaussianLikelihood",
            "GradVariationalStrategy", "MultivariateNormal", "PredictiveDistribution", "PredictiveLogLikelihood",
            "RBFKernelDirectionalGrad", "RBFKernelGrad", "ScaleKernel", "VariationalELBO"]
 __version__ = "0.1.0"

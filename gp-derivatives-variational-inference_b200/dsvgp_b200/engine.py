@@ -142,10 +142,14 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ factorisation
     @staticmethod
-    def _factorise(f, P, T, extra_jitter):
-        """hyper-parameter transforms, direction normalisation, K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+    def _hyp(f, P):
         ops.hyp_from_raw(P.raw_ell.reshape(-1), P.raw_os.reshape(-1),
                          None if P.raw_noise is None else P.raw_noise.reshape(-1), P.c.reshape(-1), out=f.hyp)
+
+    @staticmethod
+    def _factorise(f, P, T, extra_jitter):
+        """hyper-parameter transforms, direction normalisation, K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+        Engine._hyp(f, P)
         if f.p:
             f.uzT, f.invzT = ops.normalize_dirs(P.Vz, T)
             f.uz64, f.invz64 = (f.uzT, f.invzT) if T == F64 else ops.normalize_dirs(P.Vz, F64)
@@ -344,7 +348,7 @@ class Engine:
     @staticmethod
     def _owner_token(P):
         """identity + in-place version of every parameter the factor depends on"""
-        return tuple((t.data_ptr(), t._version) for t in (P.Z, P.Vz, P.raw_ell, P.raw_os, P.c) if t is not None)
+        return tuple((t.data_ptr(), t._version) for t in (P.Z, P.Vz, P.raw_ell, P.raw_os) if t is not None)
 
     def predict(self, P, x, Vx, p, p2, add_noise, reuse_factor=False):
         """eval_gp's per-batch prediction (directional_vi.py:296-298).  reuse_factor: eval-mode memoisation of
@@ -365,9 +369,68 @@ class Engine:
                 raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4")
             f.valid = reuse_factor
             f.owner = token
+        else:
+            self._hyp(f, P)        # the memoised factor does not depend on the noise / mean constant; hyp[2:4] do
         wx = self._data_dirs(ws, Vx, T)
         self._forward(ws, f, P, x, wx, add_noise, need_C=False)
         return ws.mu.clone(), ws.var.clone()
+
+    # ----------------------------------------------------------- public: full predictive covariance and samples
+    def predict_full(self, P, x, Vx, p, p2, add_noise, reuse_factor=False):
+        """mean (n') and the dense n' x n' covariance of q(f(X)) [+ noise]:
+        K_xx + 1e-4 I + A^T (S - I) A  (DGVS.py:192-205; SURVEY section 8f rank 4 -- what `preds.sample` of the BO
+        callers consumes, experiments/rover/test_turbo.py:119-150).  The training path never forms this matrix."""
+        T = x.dtype
+        n, d = x.shape
+        M = P.Z.shape[0]
+        ws = self.workspace(x.device, T, n, d, M, p, p2)
+        f = self.factor(x.device, T, d, M, p)
+        token = self._owner_token(P)
+        if not (reuse_factor and f.valid and f.owner == token):
+            f.valid = False
+            for extra in (0.0,) + CHOL_RETRY:
+                self._factorise(f, P, T, extra)
+                if self._check(f, P):
+                    break
+            else:
+                raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4")
+            f.valid = reuse_factor
+            f.owner = token
+        else:
+            self._hyp(f, P)
+        wx = self._data_dirs(ws, Vx, T)
+        self._forward(ws, f, P, x, wx, add_noise, need_C=True)
+        nq, Mq = ws.nq, ws.Mq
+        cov = torch.empty(nq, _round_up(nq, 4), dtype=T, device=x.device)[:, :nq]
+        ops.kdir_fwd(x, wx, p2, x, wx, p2, f.hyp, cov, diag_add=PRED_JITTER)
+        if add_noise:
+            cov.diagonal().add_(f.hyp[2].to(T))
+        ops.gemm(ws.A, ws.C, cov, ta=True, beta=1.0, M=nq, N=nq, K=Mq)            # += A^T (S - I) A
+        return ws.mu.clone(), cov
+
+    def sample_mvn(self, mean, cov, num_samples, generator=None):
+        """num_samples draws of N(mean, cov): fp64 Cholesky of cov on the library's own blocked factorisation (same
+        jitter ladder as psd_safe_cholesky), then mean + z L^T as one triangular product."""
+        nq = mean.shape[0]
+        dev = mean.device
+        Mp, nb0, nlev = ops.chol_plan(nq)
+        work, L, W = (torch.empty(Mp, Mp, dtype=F64, device=dev) for _ in range(3))
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        for extra in (0.0, 1e-8, 1e-6, 1e-5, 1e-4):
+            if Mp > nq:
+                ops.pad_identity(work, nq)
+            work[:nq, :nq] = cov
+            if extra:
+                work.diagonal()[:nq].add_(extra)
+            ops.cholesky_inverse(work, L, W, nb0, nlev, info)
+            if int(info.item()) == 0:
+                break
+        else:
+            raise NotPSDError("the predictive covariance is not positive definite after adding jitter up to 1e-4")
+        z = torch.randn(num_samples, nq, dtype=F64, device=dev, generator=generator)
+        out = torch.empty(num_samples, nq, dtype=F64, device=dev)
+        ops.gemm(z, L, out, tb=True, b_tri=TRI_UPPER, M=num_samples, N=nq, K=nq)      # z L^T
+        return (out + mean.to(F64)).to(mean.dtype)
 
     def invalidate(self):
         for f in self._fac.values():

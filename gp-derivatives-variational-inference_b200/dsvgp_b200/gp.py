@@ -336,11 +336,12 @@ class _Predictive(torch.autograd.Function):
 class PredictiveDistribution:
     """Lazy q(f(X)) returned by a variational strategy (stands in for gpytorch's MultivariateNormal with a lazy
     covariance).  Only what the reference's callers consume is offered: .mean / .loc, .variance, .stddev
-    (directional_vi.py:256-257, :297-298).  The full predictive covariance is SURVEY.md section 8f rank 4."""
+    (directional_vi.py:256-257, :297-298).  The full predictive covariance (.covariance_matrix) and .sample / .rsample are evaluated without autograd."""
 
     def __init__(self, strategy, x, Vx, likelihood=None):
         self._strategy, self._x, self._Vx, self._likelihood = strategy, x, Vx, likelihood
         self._cache = None
+        self._full = None
 
     def _with_likelihood(self, likelihood):
         return PredictiveDistribution(self._strategy, self._x, self._Vx, likelihood)
@@ -379,11 +380,35 @@ class PredictiveDistribution:
     def stddev(self):
         return self.variance.sqrt()
 
-    @property
-    def lazy_covariance_matrix(self):
-        raise NotImplementedError("only the predictive mean and diagonal variance are on the B200 hot path")
+    def _evaluate_full(self):
+        """(mean, dense covariance) -- evaluated without autograd (the BO callers sample under eval / no_grad)."""
+        if self._full is None:
+            st = self._strategy
+            P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, (t.detach() if t is not None else None for t in self._params()))))
+            with torch.no_grad():
+                self._full = ENGINE.predict_full(P, self._x, self._Vx, st._p(), st._p2(), self._likelihood is not None,
+                                                 reuse_factor=not st.training)
+        return self._full
 
-    covariance_matrix = lazy_covariance_matrix
+    @property
+    def covariance_matrix(self):
+        """Dense n' x n' predictive covariance K_xx + 1e-4 I + A^T (S - I) A (+ noise), DGVS.py:192-205."""
+        return self._evaluate_full()[1]
+
+    lazy_covariance_matrix = covariance_matrix
+
+    def rsample(self, sample_shape=torch.Size(), base_samples=None):
+        mean, cov = self._evaluate_full()
+        shape = torch.Size(sample_shape)
+        num = int(math.prod(shape)) if len(shape) else 1
+        out = ENGINE.sample_mvn(mean, cov, num)
+        return out.reshape(*shape, mean.shape[0])
+
+    def sample(self, sample_shape=torch.Size(), base_samples=None):
+        """preds.sample(torch.Size([n_samples])) -> (n_samples, n') as gpytorch's MultivariateNormal.sample
+        (experiments/rover/test_turbo.py:138)."""
+        with torch.no_grad():
+            return self.rsample(sample_shape)
 
 
 # ------------------------------------------------------------------------------------------------ objectives
@@ -445,6 +470,7 @@ class ApproximateGP(Module):
 def _ensure_updated_strategy_flag_set(module, state_dict, prefix, *args):
     """load_state_dict pre-hook of the reference strategies (DGVS.py:17-29): checkpoints from before the whitened
     parameterisation lack `updated_strategy`; they get False, which triggers the one-off re-whitening."""
+    module._flags_checked = False
     if prefix + "updated_strategy" not in state_dict:
         device = state_dict[list(state_dict.keys())[0]].device
         state_dict[prefix + "updated_strategy"] = torch.tensor(False, device=device)
@@ -470,6 +496,7 @@ class _DirectionalStrategyBase(Module):
         self.register_buffer("updated_strategy", torch.tensor(True))
         self._register_load_state_dict_pre_hook(_ensure_updated_strategy_flag_set, with_module=True)
         self._n_global = None          # set by distributed.shard(): global minibatch size of a sharded step
+        self._flags_checked = False    # host-side memo of the two flag buffers (reset by load_state_dict)
 
     # ---- shape helpers
     def _p(self):
@@ -536,11 +563,15 @@ class _DirectionalStrategyBase(Module):
     def __call__(self, x, prior=False, **kwargs):
         if prior:
             return self.model.forward(x, **kwargs)
-        if not self.updated_strategy.item():
-            self._rewhiten_legacy_parameters()
-        if not self.variational_params_initialized.item():
-            self._variational_distribution.initialize_from_prior()
-            self.variational_params_initialized.fill_(1)
+        if not self._flags_checked:
+            # the two flag buffers are read from the device ONCE (and again after load_state_dict), not on every
+            # call as in the reference (DGVS.py:211,:229): each .item() is a host synchronisation per minibatch
+            if not self.updated_strategy.item():
+                self._rewhiten_legacy_parameters()
+            if not self.variational_params_initialized.item():
+                self._variational_distribution.initialize_from_prior()
+                self.variational_params_initialized.fill_(1)
+            self._flags_checked = True
         vd = self._variational_distribution
         return self.forward(x, self.inducing_points, vd.variational_mean, None, **kwargs)
 

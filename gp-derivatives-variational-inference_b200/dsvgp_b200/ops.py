@@ -136,6 +136,11 @@ def set_tc_cta_group(cg):
     return call_raw("dsvgp_set_tc_cta_group", int(cg))
 
 
+def set_kdir_fwd_knobs(tib=-1, stream_stores=-1):
+    """benchmarking knobs of the fp32 assembly kernel (row points per CTA, evict-first stores)."""
+    return call_raw("dsvgp_set_kdir_fwd_knobs", int(tib), int(stream_stores))
+
+
 def gemm_tc_supported(A, B, b_kmajor, N):
     return bool(call_raw("dsvgp_gemm_tc_supported_f32", A, _ld(A), B, _ld(B), int(b_kmajor), int(N)))
 

@@ -45,6 +45,10 @@ int dsvgp_version(void);
 int dsvgp_built_for_sm(void);
 /* number of CUDA kernels this library has launched in this process (host-side counter) */
 int64_t dsvgp_launch_count(void);
+/* benchmarking knobs of the fp32 assembly kernel: row points per CTA (8..64, multiple of 8; default 64) and
+ * evict-first (st.global.cs) stores of the covariance rows (0 off, 1 on, 2 = when the output exceeds 64 MB, the
+ * default).  Negative = leave unchanged.  Returns tib*4 + stream_stores as set before the call. */
+int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores);
 
 /* Positive()/GreaterThan(1e-4) transforms of gpytorch that the reference reaches through
  * self.lengthscale (RBFKernelDirectionalGrad.py:67), ScaleKernel.outputscale (directional_vi.py:56) and
@@ -177,6 +181,28 @@ int dsvgp_kl_f64(const double* m, const double* Ls_raw, int64_t ld, int Mq, doub
 /* gm = t - m/num_data ; gLs = tril(2 H^T) - (tril(Ls) - diag(1/Ls_ii))/num_data  (H = Ls^T G) */
 int dsvgp_var_grads_f32(const float* H, int64_t ldh, const float* Ls_raw, int64_t ldl, const float* t, const float* m, int Mq, double inv_num_data, float* gm, float* gLs, int64_t ldg, dsvgp_stream_t s);
 int dsvgp_var_grads_f64(const double* H, int64_t ldh, const double* Ls_raw, int64_t ldl, const double* t, const double* m, int Mq, double inv_num_data, double* gm, double* gLs, int64_t ldg, dsvgp_stream_t s);
+
+/* ---- optimiser step ------------------------------------------------------------
+ * One launch of a fused multi-tensor Adam over every tensor of an optimiser: replaces torch.optim.Adam.step() of the
+ * reference's two optimisers (directional_vi.py:192-199, stepped at :251-254); arithmetic follows torch.optim.Adam
+ * (amsgrad=False, maximize=False) operation by operation in the parameter dtype.
+ *   desc_host  : HOST array, ntensors x 8 int64 = {param, grad, exp_avg, exp_avg_sq (device addresses), numel,
+ *                group index, tri_n, 0}; tri_n > 0 marks an n x n matrix whose strictly-upper gradient is
+ *                structurally zero (chol_variational_covar): only the lower triangle is visited.
+ *   group_host : HOST array, ngroups (<= 4) x 8 double = {lr, beta1, beta2, eps, weight_decay, step, 0, 0}; `step` is
+ *                the 1-based step count used for the bias corrections.
+ * Both host arrays are consumed before the call returns. */
+int dsvgp_adam_step_f32(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s);
+int dsvgp_adam_step_f64(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s);
+
+/* ---- input side ------------------------------------------------------------------
+ * Minibatch gather fused with select_cols_of_y (directional_vi.py:68-90, :229-241): for minibatch row i,
+ * xb[i,:] = X[idx[i],:], yb[i*(p+1)+a] = Y[idx[i], cols[a]] (interleaved), V[i*p+b,:] = e_{cols[1+b]-1}.
+ * X (N x d) and Y (N x ycols) are contiguous and resident on the device; idx = n int64 row indices on the device
+ * (NULL = rows 0..n-1); cols_host = p+1 column indices of Y on the HOST (cols[0] is the function-value column),
+ * consumed before the call returns; V may be NULL (no direction rows wanted, e.g. the derivative-free strategy). */
+int dsvgp_gather_batch_f32(const float* X, const float* Y, int64_t N, int d, int ycols, const int64_t* idx, int n, int p, const int* cols_host, float* xb, float* yb, float* V, dsvgp_stream_t s);
+int dsvgp_gather_batch_f64(const double* X, const double* Y, int64_t N, int d, int ycols, const int64_t* idx, int n, int p, const int* cols_host, double* xb, double* yb, double* V, dsvgp_stream_t s);
 
 #ifdef __cplusplus
 }

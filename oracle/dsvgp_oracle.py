@@ -264,6 +264,36 @@ def predictive(P, x, Vx, variant="dsvgp", structure="lean"):
     return mean, var
 
 
+def predictive_full(P, x, Vx, variant="dsvgp", add_noise=False):
+    """(mean, dense n' x n' covariance) of q(f(X)): K_xx + 1e-4 I + A^T (S - I) A, the matrix the strategy returns
+    as a lazy tensor (DGVS.py:192-208; DFree: value rows/columns only, :136) and that `preds.sample(...)` of the BO
+    callers factorises (experiments/rover/test_turbo.py:138).  add_noise: likelihood(dist) adds sigma^2 I."""
+    n, d = x.shape
+    M = P.Z.shape[0]
+    ell, osc = lengthscale(P), outputscale(P)
+    if variant == "grad":
+        Vz = canonical_directions(M, d, d, x.dtype)
+        Vx = canonical_directions(n, d, d, x.dtype)
+    else:
+        Vz = P.Vz
+    p = Vz.shape[0] // M
+    keep = slice(None, None, p + 1) if variant == "dfree" else slice(None)
+    Ls = chol_factor_of_q(P)
+    kern = kernel_reference_structure
+    Kzx = (osc * kern(P.Z, x, Vz, Vx, ell))[:, keep]
+    Kzz = osc * kern(P.Z, P.Z, Vz, Vz, ell)
+    Kxx = (osc * kern(x, x, Vx, Vx, ell))[keep, keep]
+    Kzz = Kzz + KZZ_JITTER * torch.eye(Kzz.shape[0], dtype=Kzz.dtype)
+    L = psd_safe_cholesky(Kzz.double())
+    A = torch.linalg.solve_triangular(L, Kzx.double(), upper=False).to(x.dtype)
+    mean = A.transpose(-1, -2) @ P.m + P.c.expand(A.shape[1])
+    mid_A = Ls @ (Ls.transpose(-1, -2) @ A) - A
+    cov = Kxx + PRED_JITTER * torch.eye(Kxx.shape[0], dtype=Kxx.dtype) + A.transpose(-1, -2) @ mid_A
+    if add_noise:
+        cov = cov + noise(P) * torch.eye(cov.shape[0], dtype=cov.dtype)
+    return mean, cov
+
+
 def clamp_variance(var):
     """MultivariateNormal.variance clamps at settings.min_variance (1e-6 fp32 / 1e-10 fp64), Q5."""
     return var.clamp_min(1e-10 if var.dtype == torch.float64 else 1e-6)

@@ -152,3 +152,17 @@ def test_cholesky_failure_ladder_and_nan():
     A[0, 0] = math.nan
     with pytest.raises(O.NanError):
         O.psd_safe_cholesky(A)
+
+
+@pytest.mark.parametrize("variant", ["dsvgp", "dfree", "grad"])
+def test_full_covariance_oracle_agrees_with_diagonal_path(variant):
+    """predictive_full (the matrix the strategy returns lazily, DGVS.py:192-208) has the lean path's variance on its
+    diagonal, is symmetric and positive definite."""
+    n, d, M, p = 23, 3, 11, (3 if variant == "grad" else 2)
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, torch.float64, seed=5, variant=variant)
+    mean, cov = O.predictive_full(P, x, Vx, variant, add_noise=True)
+    m2, v2 = O.predict(P, x, Vx, variant)
+    assert torch.allclose(mean, m2, rtol=1e-12, atol=1e-13)
+    assert torch.allclose(cov.diagonal(), v2, rtol=1e-11, atol=1e-13)
+    assert torch.allclose(cov, cov.T, rtol=1e-11, atol=1e-13)
+    assert float(torch.linalg.eigvalsh(0.5 * (cov + cov.T)).min()) > 0

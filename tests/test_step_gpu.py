@@ -314,3 +314,64 @@ def test_full_size_properties(variant, n, d, M, p, dtype):
         preds = lik(model(x.to(dtype).cuda(), **({} if variant == "grad" else {"derivative_directions": Vx.to(dtype)})))
     assert rel(preds.mean, out.mean) < (1e-12 if dtype == F64 else 1e-5)
     assert rel(preds.variance, out.variance) < (1e-11 if dtype == F64 else 1e-4)
+
+
+# -------------------------------------------------------- full predictive covariance + sampling (section 8f rank 4)
+@pytest.mark.parametrize("variant,n,d,M,p,dtype", [
+    ("dsvgp", 120, 3, 40, 1, F64), ("dsvgp", 150, 10, 64, 2, F32), ("dsvgp", 300, 10, 128, 2, F32),
+    ("dfree", 100, 6, 32, 2, F64), ("grad", 40, 3, 20, 3, F64), ("dsvgp", 96, 60, 50, 3, F32)])
+def test_full_predictive_covariance_matches_oracle(variant, n, d, M, p, dtype):
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed=7 + n, variant=variant, N=10 * n)
+    up = lambda t: None if t is None else t.double()
+    model, lik = build(variant, P, d, dtype)
+    model.eval(), lik.eval()
+    kw = {} if variant == "grad" else {"derivative_directions": Vx}
+    t = 1e-10 if dtype == F64 else 1e-4
+    with torch.no_grad():
+        for noisy in (False, True):
+            dist = model(x.cuda(), **kw)
+            dist = lik(dist) if noisy else dist
+            mean, cov = O.predictive_full(P.clone(F64), up(x), up(Vx), variant, add_noise=noisy)
+            assert rel(dist.mean, mean) < t
+            assert rel(dist.covariance_matrix, cov) < t
+            assert rel(dist.covariance_matrix.diagonal(), dist.variance) < 10 * t     # same thing two ways
+            assert dist.lazy_covariance_matrix.shape == (mean.numel(), mean.numel())
+
+
+def test_samples_follow_the_predictive_distribution():
+    """preds.sample(torch.Size([n_samples])) (experiments/rover/test_turbo.py:138): shape, and first two moments of
+    many draws against the oracle's mean / covariance (statistical tolerance)."""
+    variant, n, d, M, p, dtype = "dsvgp", 12, 4, 30, 2, F32
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed=3, variant=variant, N=10 * n)
+    model, lik = build(variant, P, d, dtype)
+    model.eval(), lik.eval()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        preds = lik(model(x.cuda(), derivative_directions=Vx))
+        s = preds.sample(torch.Size([200000]))
+        one = preds.sample()
+    assert s.shape == (200000, n * (p + 1)) and one.shape == (n * (p + 1),) and s.dtype == dtype
+    mean, cov = O.predictive_full(P.clone(F64), x.double(), Vx.double(), variant, add_noise=True)
+    sd = cov.diagonal().sqrt()
+    emp_mean = s.double().mean(0).cpu()
+    assert float(((emp_mean - mean) / sd).abs().max()) < 0.02            # 200k draws: standard error 0.0022 sd
+    emp_cov = torch.cov(s.double().T).cpu()
+    assert float(((emp_cov - cov) / (sd[:, None] * sd[None, :])).abs().max()) < 0.03
+    y_cand = s[:, ::p + 1].t()                                           # the caller's slicing (test_turbo.py:139)
+    assert y_cand.shape == (n, 200000)
+
+
+def test_memoised_factor_refreshes_noise_and_mean_constant():
+    """eval mode: model(x) and likelihood(model(x)) share the memoised Cholesky factor, but the noise (and the mean
+    constant) are read fresh on every call -- a stale hyp buffer once dropped the noise from the second call."""
+    variant, n, d, M, p, dtype = "dsvgp", 50, 3, 16, 1, F64
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed=11, variant=variant, N=10 * n)
+    model, lik = build(variant, P, d, dtype)
+    model.eval(), lik.eval()
+    with torch.no_grad():
+        latent = model(x.cuda(), derivative_directions=Vx)
+        v0, m0 = latent.variance.clone(), latent.mean.clone()
+        noisy = lik(model(x.cuda(), derivative_directions=Vx))
+        assert rel(noisy.variance - v0, O.noise(P).expand(v0.numel())) < 1e-9
+        model.mean_module.constant.add_(0.5)
+        assert rel(model(x.cuda(), derivative_directions=Vx).mean - m0, torch.full((m0.numel(),), 0.5, dtype=F64)) < 1e-9
