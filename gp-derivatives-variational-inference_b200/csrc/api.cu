@@ -126,6 +126,11 @@ int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
     if (!mu || !var || !y || !hyp || !gmu || !gvar || !sc || !ws) return DSVGP_ERR_ARG;                            \
     return elbo_terms<T>(mu, var, y, nq, hyp, w, min_var, gmu, gvar, sc, ws, ST(s));                               \
   }                                                                                                                \
+  int dsvgp_pll_terms_##SUF(const T* mu, const T* var, const T* y, int nq, double w, double min_var, T* gmu,       \
+                            T* gvar, double* sc, double* ws, dsvgp_stream_t s) {                                   \
+    if (!mu || !var || !y || !gmu || !gvar || !sc || !ws) return DSVGP_ERR_ARG;                                    \
+    return pll_terms<T>(mu, var, y, nq, w, min_var, gmu, gvar, sc, ws, ST(s));                                     \
+  }                                                                                                                \
   int dsvgp_pred_bwd_scalars_##SUF(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise,  \
                                    double* gsc, double* ws, dsvgp_stream_t s) {                                    \
     if (!gmu || !gvar || !hyp || !gsc || !ws) return DSVGP_ERR_ARG;                                                \

@@ -195,7 +195,7 @@ __global__ void predict_finish_kernel(const T* __restrict__ pm, const T* __restr
   }
   const double ell = hyp[0], os = hyp[1];
   const double kd = (j % (p2 + 1)) == 0 ? os : os / (ell * ell);
-  double v = kd + pred_jitter + sv + (add_noise ? hyp[2] : 0.0);
+  double v = kd + pred_jitter + sv + (double)add_noise * hyp[2];      // add_noise = how many times likelihood() was applied (Q3)
   if (v < min_var) v = min_var;
   mu[j] = (T)(sm + hyp[3]);
   var[j] = (T)v;
@@ -228,6 +228,29 @@ elbo_terms_kernel(const T* __restrict__ mu, const T* __restrict__ var, const T* 
   }
 }
 
+// PredictiveLogLikelihood data term (gpytorch.mlls.PredictiveLogLikelihood, mll_type="PLL", directional_vi.py:218-219):
+// log N(y_j; mu_j, v_j) with v the marginal variance (the caller has already added the noise as many times as
+// likelihood() was applied -- twice in the reference loop, Q3).  No explicit noise derivative: it flows through v.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pll_terms_kernel(const T* __restrict__ mu, const T* __restrict__ var, const T* __restrict__ y, int nq, double w,
+                 double min_var, T* __restrict__ gmu, T* __restrict__ gvar, double* __restrict__ sc_part) {
+  __shared__ double red[32];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  double term = 0;
+  if (j < nq) {
+    const double r = (double)y[j] - (double)mu[j], v = (double)var[j];
+    term = -0.5 * (r * r / v + log(v) + 1.8378770664093453) * w;
+    gmu[j] = (T)(w * r / v);
+    gvar[j] = (T)((v > min_var) ? -0.5 * w * (1.0 / v - r * r / (v * v)) : 0.0);
+  }
+  const double a = block_sum<double, 256>(term, red);
+  if (threadIdx.x == 0) {
+    sc_part[2 * blockIdx.x] = a;
+    sc_part[2 * blockIdx.x + 1] = 0.0;
+  }
+}
+
 // out[k] += sum_b part[b*stride + k], k < width   (one CTA)
 __global__ void sum_scalar_parts_kernel(const double* __restrict__ part, int nparts, int stride, int width,
                                         double* __restrict__ out) {
@@ -254,7 +277,7 @@ pred_bwd_scalars_kernel(const T* __restrict__ gmu, const T* __restrict__ gvar, i
     const bool val = (j % (p2 + 1)) == 0;
     d_os += gv * (val ? 1.0 : 1.0 / (ell * ell));
     d_ell += val ? 0.0 : gv * (-2.0 * os / (ell * ell * ell));
-    d_s2 += add_noise ? gv : 0.0;
+    d_s2 += (double)add_noise * gv;
     d_c += (double)gmu[j];
   }
   double v[4] = {d_ell, d_os, d_s2, d_c};
@@ -514,6 +537,18 @@ int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp,
   return DSVGP_OK;
 }
 
+template <typename T>
+int pll_terms(const T* mu, const T* var, const T* y, int nq, double w, double min_var, T* gmu, T* gvar, double* sc,
+              double* ws, cudaStream_t st) {
+  if (nq <= 0) return DSVGP_OK;
+  const int nb = ceil_div(nq, 256);
+  pll_terms_kernel<T><<<nb, 256, 0, st>>>(mu, var, y, nq, w, min_var, gmu, gvar, ws);
+  CHECK_LAUNCH();
+  sum_scalar_parts_kernel<<<1, 256, 0, st>>>(ws, nb, 2, 2, sc);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
 // gsc[0..3] += {d ell, d os, d sigma^2, d c} ; ws: 4*blocks doubles (blocks <= 296)
 template <typename T>
 int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc,
@@ -575,6 +610,8 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
                                  cudaStream_t);                                                                    \
   template int elbo_terms<T>(const T*, const T*, const T*, int, const double*, double, double, T*, T*, double*,    \
                              double*, cudaStream_t);                                                               \
+  template int pll_terms<T>(const T*, const T*, const T*, int, double, double, T*, T*, double*, double*,           \
+                            cudaStream_t);                                                                         \
   template int pred_bwd_scalars<T>(const T*, const T*, int, int, const double*, int, double*, double*,             \
                                    cudaStream_t);                                                                  \
   template int dA_apply<T>(const T*, T*, T*, int64_t, int, int, const T*, const T*, const T*, T*, int, T*, T*, T*, \

@@ -26,6 +26,9 @@ template <typename T>
 int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp, double w, double min_var, T* gmu,
                T* gvar, double* sc, double* ws, cudaStream_t st);
 template <typename T>
+int pll_terms(const T* mu, const T* var, const T* y, int nq, double w, double min_var, T* gmu, T* gvar, double* sc,
+              double* ws, cudaStream_t st);
+template <typename T>
 int pred_bwd_scalars(const T* gmu, const T* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc,
                      double* ws, cudaStream_t st);
 template <typename T>

@@ -119,8 +119,15 @@ class Workspace:
 
 class Engine:
     def __init__(self):
-        self._ws, self._fac = {}, {}
+        self._ws, self._fac, self._streams = {}, {}, {}
         self.reduce_hook = None     # callable(big_or_None, small) summing the buffers over ranks, or None
+
+    def _side_stream(self, device):
+        key = str(device)
+        st = self._streams.get(key)
+        if st is None:
+            st = self._streams[key] = torch.cuda.Stream(device=device)
+        return st
 
     def workspace(self, device, dtype, n, d, M, p, p2):
         key = (str(device), dtype, n, d, M, p, p2)
@@ -147,12 +154,18 @@ class Engine:
                          None if P.raw_noise is None else P.raw_noise.reshape(-1), P.c.reshape(-1), out=f.hyp)
 
     @staticmethod
-    def _factorise(f, P, T, extra_jitter):
-        """hyper-parameter transforms, direction normalisation, K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+    def _prep(f, P, T):
+        """hyper-parameter transforms and direction normalisation (everything K_zx and K_zz both need)"""
         Engine._hyp(f, P)
         if f.p:
             f.uzT, f.invzT = ops.normalize_dirs(P.Vz, T)
             f.uz64, f.invz64 = (f.uzT, f.invzT) if T == F64 else ops.normalize_dirs(P.Vz, F64)
+
+    @staticmethod
+    def _factorise(f, P, T, extra_jitter, prep=True):
+        """[hyper-parameter transforms, direction normalisation,] K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+        if prep:
+            Engine._prep(f, P, T)
         if f.Mp > f.Mq:
             ops.pad_identity(f.Kzz, f.Mq)
         ops.kdir_fwd(P.Z, f.uz64, f.p, P.Z, f.uz64, f.p, f.hyp, f.Kzz, diag_add=KZZ_JITTER + extra_jitter)
@@ -190,11 +203,12 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ forward
     @staticmethod
-    def _forward(ws, f, P, x, wx, add_noise, need_C):
+    def _assemble(ws, f, P, x, wx):
+        """Everything of the forward pass that does not need the Cholesky factor: K_zx (+ its TF32 lo part) and the
+        operands made from L_s.  elbo_step runs this on a side stream while K_zz is being factorised."""
         Mq, nq = ws.Mq, ws.nq
-        Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
         tc = ws.tc and f.tc
-        have_lo = ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, Kzx, canon=ws.canon, out_lo=ws.lo1 if tc else None)
+        have_lo = ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1 if tc else None)
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
         ops.tril_minus_eye(P.Ls_raw, ws.E)
         if tc:
@@ -203,7 +217,16 @@ class Engine:
             ops.transpose(ws.E, ws.ET)
             ops.split_lo(ws.ET, ws.ET_lo)
             if not have_lo:
-                ops.split_lo(Kzx, ws.lo1, Mq, nq)
+                ops.split_lo(ws.Kzx, ws.lo1, Mq, nq)
+
+    @staticmethod
+    def _forward(ws, f, P, x, wx, add_noise, need_C, assembled=False):
+        Mq, nq = ws.Mq, ws.nq
+        Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
+        tc = ws.tc and f.tc
+        if not assembled:
+            Engine._assemble(ws, f, P, x, wx)
+        if tc:
             ops.gemm_tc(f.Wt, f.Wt_lo, Kzx, ws.lo1, A, Mq, nq, Mq, a_tri=TRI_LOWER, chunk=TC_CHUNK,
                         C_lo=ws.lo2)                                                     # A = L^-1 K_zx  (+ A_lo)
             ops.gemm_tc(ws.ET, ws.ET_lo, A, ws.lo2, ws.Bp, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK,
@@ -288,11 +311,15 @@ class Engine:
         return g
 
     # ------------------------------------------------------------------------------------------ public: train
-    def elbo_step(self, P, x, Vx, y, num_data, p, p2, through_likelihood=True, n_global=None, want_grads=True):
-        """One fused forward(+backward) of VariationalELBO(likelihood, model, num_data)(likelihood(model(x)), y).
+    def elbo_step(self, P, x, Vx, y, num_data, p, p2, through_likelihood=True, n_global=None, want_grads=True,
+                  objective="elbo"):
+        """One fused forward(+backward) of VariationalELBO(likelihood, model, num_data)(likelihood(model(x)), y)
+        -- or, objective="pll", of PredictiveLogLikelihood (directional_vi.py:218-219).
 
-        Returns (elbo [0-dim float64 tensor], grads dict or None, mean, variance).  `variance` includes likelihood
-        noise iff through_likelihood (directional_vi.py:245 feeds likelihood(model(x)) to the ELBO, Q3)."""
+        Returns (objective value [0-dim float64 tensor], grads dict or None, mean, variance).  `through_likelihood`
+        is the number of times likelihood() has been applied to the distribution whose variance the data term sees
+        (bool or int): 1 for the ELBO on likelihood(model(x)) (directional_vi.py:245, Q3); for PLL the caller counts
+        log_marginal's own application too (2 in the reference loop).  `variance` includes that many noises."""
         T, dev = x.dtype, x.device
         n, d = x.shape
         M = P.Z.shape[0]
@@ -301,12 +328,24 @@ class Engine:
         f.valid = False
         nq_global = (n_global if n_global is not None else n) * (p2 + 1)
         wx = self._data_dirs(ws, Vx, T)
+        self._prep(f, P, T)
+        # K_zx assembly and the L_s operands do not depend on the factor: they run on a side stream underneath the
+        # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle)
+        cur, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._assemble(ws, f, P, x, wx)
         for extra in (0.0,) + CHOL_RETRY:
-            self._factorise(f, P, T, extra)
-            self._forward(ws, f, P, x, wx, through_likelihood, need_C=True)
+            self._factorise(f, P, T, extra, prep=False)
+            if extra == 0.0:
+                cur.wait_stream(side)
+            self._forward(ws, f, P, x, wx, through_likelihood, need_C=True, assembled=(extra == 0.0))
             ws.small.zero_()
             ws.kl.zero_()
-            ops.elbo_terms(ws.mu, ws.var, y, f.hyp, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
+            if objective == "pll":
+                ops.pll_terms(ws.mu, ws.var, y, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
+            else:
+                ops.elbo_terms(ws.mu, ws.var, y, f.hyp, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
             ops.kl_divergence(P.m, P.Ls_raw, ws.kl, ws.scratch)
             if want_grads:
                 self._backward(ws, f, P, x, wx, ws.gmu, ws.gvar, through_likelihood, 1.0 / num_data)
@@ -404,7 +443,7 @@ class Engine:
         cov = torch.empty(nq, _round_up(nq, 4), dtype=T, device=x.device)[:, :nq]
         ops.kdir_fwd(x, wx, p2, x, wx, p2, f.hyp, cov, diag_add=PRED_JITTER)
         if add_noise:
-            cov.diagonal().add_(f.hyp[2].to(T))
+            cov.diagonal().add_((f.hyp[2] * int(add_noise)).to(T))
         ops.gemm(ws.A, ws.C, cov, ta=True, beta=1.0, M=nq, N=nq, K=Mq)            # += A^T (S - I) A
         return ws.mu.clone(), cov
 

@@ -290,7 +290,8 @@ class _ElboStep(torch.autograd.Function):
         P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
         want = any(ctx.needs_input_grad[4:])      # (grad mode is off inside forward; this is the reliable signal)
         elbo, grads, mean, var = ENGINE.elbo_step(P, x, Vx, y, cfg["num_data"], cfg["p"], cfg["p2"],
-                                                  cfg["through_likelihood"], cfg.get("n_global"), want_grads=want)
+                                                  cfg["through_likelihood"], cfg.get("n_global"), want_grads=want,
+                                                  objective=cfg.get("objective", "elbo"))
         ctx.grads = grads
         ctx.mark_non_differentiable(mean, var)
         return elbo.to(x.dtype), mean, var
@@ -338,13 +339,14 @@ class PredictiveDistribution:
     covariance).  Only what the reference's callers consume is offered: .mean / .loc, .variance, .stddev
     (directional_vi.py:256-257, :297-298).  The full predictive covariance (.covariance_matrix) and .sample / .rsample are evaluated without autograd."""
 
-    def __init__(self, strategy, x, Vx, likelihood=None):
+    def __init__(self, strategy, x, Vx, likelihood=None, noise_mult=0):
         self._strategy, self._x, self._Vx, self._likelihood = strategy, x, Vx, likelihood
+        self._noise_mult = noise_mult       # how many times likelihood() has been applied: each adds sigma^2 I (Q3)
         self._cache = None
         self._full = None
 
     def _with_likelihood(self, likelihood):
-        return PredictiveDistribution(self._strategy, self._x, self._Vx, likelihood)
+        return PredictiveDistribution(self._strategy, self._x, self._Vx, likelihood, self._noise_mult + 1)
 
     @property
     def event_shape(self):
@@ -356,7 +358,7 @@ class PredictiveDistribution:
     def _evaluate(self):
         if self._cache is None:
             st = self._strategy
-            cfg = dict(p=st._p(), p2=st._p2(), add_noise=self._likelihood is not None)
+            cfg = dict(p=st._p(), p2=st._p2(), add_noise=self._noise_mult)
             params = self._params()
             if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params):
                 self._cache = _Predictive.apply(cfg, self._x, self._Vx, *params)
@@ -386,7 +388,7 @@ class PredictiveDistribution:
             st = self._strategy
             P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, (t.detach() if t is not None else None for t in self._params()))))
             with torch.no_grad():
-                self._full = ENGINE.predict_full(P, self._x, self._Vx, st._p(), st._p2(), self._likelihood is not None,
+                self._full = ENGINE.predict_full(P, self._x, self._Vx, st._p(), st._p2(), self._noise_mult,
                                                  reuse_factor=not st.training)
         return self._full
 
@@ -427,7 +429,7 @@ class VariationalELBO(Module):
             raise TypeError("VariationalELBO expects the distribution returned by model(x, ...) or likelihood(model(x, ...))")
         st = dist._strategy
         cfg = dict(p=st._p(), p2=st._p2(), num_data=float(self.num_data) / float(self.beta),
-                   through_likelihood=dist._likelihood is not None, n_global=st._n_global)
+                   through_likelihood=dist._noise_mult, n_global=st._n_global)
         params = st._param_list(self.likelihood)
         elbo, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, target.contiguous(), *params)
         dist._cache = (mean, var)      # train loops print output.mean / output.variance (directional_vi.py:256-257)
@@ -435,19 +437,27 @@ class VariationalELBO(Module):
 
 
 class PredictiveLogLikelihood(Module):
-    """gpytorch.mlls.PredictiveLogLikelihood (mll_type="PLL", directional_vi.py:218-219): log N(y; mu, var + noise)
-    summed with weight 1/n', minus KL/num_data.  Uses the differentiable mean / variance path."""
+    """gpytorch.mlls.PredictiveLogLikelihood (mll_type="PLL", directional_vi.py:218-219):
+    (1/n') sum_j log N(y_j; mu_j, v_j) - KL/num_data, where v is the variance of likelihood(dist) -- log_marginal
+    applies the likelihood itself, so in the reference loop (which already passes likelihood(model(x)), :245) the
+    noise is counted twice (quirk Q3).  Runs as ONE fused forward+backward pass like VariationalELBO."""
 
     def __init__(self, likelihood, model, num_data, beta=1.0):
         super().__init__()
         self.likelihood, self.model, self.num_data, self.beta = likelihood, model, num_data, beta
 
     def forward(self, dist, target, **kwargs):
-        marginal = self.likelihood(dist)
-        mean, var = marginal.mean, marginal.variance
-        ll = -0.5 * ((target - mean) ** 2 / var + var.log() + math.log(2 * math.pi))
-        kl = self.model.variational_strategy.kl_divergence()
-        return ll.sum(-1) / mean.shape[-1] - kl / (self.num_data / self.beta)
+        if not isinstance(dist, PredictiveDistribution):
+            raise TypeError("PredictiveLogLikelihood expects the distribution returned by model(x, ...) or likelihood(model(x, ...))")
+        st = dist._strategy
+        cfg = dict(p=st._p(), p2=st._p2(), num_data=float(self.num_data) / float(self.beta), objective="pll",
+                   through_likelihood=dist._noise_mult + 1, n_global=st._n_global)
+        params = st._param_list(self.likelihood)
+        val, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, target.contiguous(), *params)
+        # the step's variance carries log_marginal's extra noise; `dist` itself (what the loop prints, :256-257) does not
+        dist._cache = (mean, (var - self.likelihood.noise.detach().to(var.dtype)).clamp_min(
+            1e-10 if var.dtype == torch.float64 else 1e-6))
+        return val
 
 
 # ---------------------------------------------------------------------------------------------------- models

@@ -227,6 +227,11 @@ def elbo_terms(mu, var, y, hyp, w, gmu, gvar, sc, ws):
     call("dsvgp_elbo_terms_" + suffix(mu.dtype), mu, var, y, mu.numel(), hyp, float(w), min_var, gmu, gvar, sc, ws)
 
 
+def pll_terms(mu, var, y, w, gmu, gvar, sc, ws):
+    min_var = 1e-10 if mu.dtype == F64 else 1e-6
+    call("dsvgp_pll_terms_" + suffix(mu.dtype), mu, var, y, mu.numel(), float(w), min_var, gmu, gvar, sc, ws)
+
+
 def pred_bwd_scalars(gmu, gvar, p2, hyp, add_noise, gsc, ws):
     call("dsvgp_pred_bwd_scalars_" + suffix(gmu.dtype), gmu, gvar, gmu.numel(), p2, hyp, int(add_noise), gsc, ws)
 

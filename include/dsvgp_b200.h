@@ -163,6 +163,13 @@ int dsvgp_predict_finish_f64(const double* pm, const double* pv, int nslab, int 
 int dsvgp_elbo_terms_f32(const float* mu, const float* var, const float* y, int nq, const double* hyp, double w, double min_var, float* gmu, float* gvar, double* sc, double* ws, dsvgp_stream_t s);
 int dsvgp_elbo_terms_f64(const double* mu, const double* var, const double* y, int nq, const double* hyp, double w, double min_var, double* gmu, double* gvar, double* sc, double* ws, dsvgp_stream_t s);
 
+/* PredictiveLogLikelihood data term (mll_type="PLL", directional_vi.py:218-219):
+ * sc[0] += w * sum_j log N(y_j; mu_j, var_j) and its gradient w.r.t. mu, var; `var` already holds the marginal
+ * variance (noise added once per likelihood() application, i.e. twice in the reference loop -- quirk Q3).
+ * sc[1] += 0 (the noise gradient flows through var).  ws: 2*ceil(nq/256) doubles. */
+int dsvgp_pll_terms_f32(const float* mu, const float* var, const float* y, int nq, double w, double min_var, float* gmu, float* gvar, double* sc, double* ws, dsvgp_stream_t s);
+int dsvgp_pll_terms_f64(const double* mu, const double* var, const double* y, int nq, double w, double min_var, double* gmu, double* gvar, double* sc, double* ws, dsvgp_stream_t s);
+
 /* gsc[0..3] += {d lengthscale, d outputscale, d noise, d constant} flowing through +c and the K_xx diagonal.
  * ws: 4*296 doubles. */
 int dsvgp_pred_bwd_scalars_f32(const float* gmu, const float* gvar, int nq, int p2, const double* hyp, int add_noise, double* gsc, double* ws, dsvgp_stream_t s);

@@ -321,6 +321,25 @@ def elbo(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", through_likel
     return ell_terms.sum() / mean.numel() - kl_divergence(P) / num_data
 
 
+def pll(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", noise_mult=2):
+    """PredictiveLogLikelihood(likelihood, model, num_data)(dist, y) (mll_type="PLL", directional_vi.py:218-219):
+    (1/n') sum_j log N(y_j; mu_j, v_j) - KL/num_data with v = var_f + noise_mult * sigma^2.  gpytorch's log_marginal
+    applies the likelihood to the distribution it is given, and the reference loop already hands it
+    likelihood(model(x)) (:245-246) -- hence noise_mult = 2 there (Q3), 1 when the bare model(x) is passed."""
+    mean, var = predictive(P, x, Vx, variant, structure)
+    var = clamp_variance(var + noise_mult * noise(P))
+    ll = -0.5 * ((y - mean) ** 2 / var + var.log() + math.log(2 * math.pi))
+    return ll.sum() / mean.numel() - kl_divergence(P) / num_data
+
+
+def pll_and_grads(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", noise_mult=2):
+    Q = P.clone().requires_grad_(True)
+    val = pll(Q, x, Vx, y, num_data, variant, structure, noise_mult)
+    names = [k for k, t in Q.tensors().items() if not (variant == "grad" and k == "Vz")]
+    grads = torch.autograd.grad(val, [getattr(Q, k) for k in names], allow_unused=True)
+    return val.detach(), {k: g for k, g in zip(names, grads) if g is not None}
+
+
 def elbo_and_grads(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", through_likelihood=True):
     """One training step's forward + backward (loss = -ELBO is what the reference differentiates; this
     returns the ELBO and dELBO/dparam so signs are unambiguous)."""

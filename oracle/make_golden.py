@@ -113,10 +113,19 @@ def strategy_case(variant, n, d, M, p, dtype, seed, perturb_dirs=True):
         res = dict(variant=variant, n=n, d=d, M=M, p=p, seed=seed, perturb_dirs=perturb_dirs, num_data=num_data,
                    x=x, Vx=Vx, y=y, params=P.tensors(), elbo=(-loss).detach().clone(), grads=grads,
                    train_mean=output.mean.detach().clone(), train_variance=output.variance.detach().clone())
+        # the same step with mll_type="PLL" (directional_vi.py:218-219): PredictiveLogLikelihood on likelihood(model(x))
+        for q in list(model.parameters()) + list(likelihood.parameters()):
+            q.grad = None
+        pll = gpytorch.mlls.PredictiveLogLikelihood(likelihood, model, num_data=num_data)
+        val = pll(likelihood(model(x, **kwargs)), y)
+        (-val).backward()
+        res["pll"] = val.detach().clone()
+        res["pll_grads"] = {k: -v for k, v in _grads(model, likelihood, variant).items()}
         model.eval(), likelihood.eval()
         with torch.no_grad():
             preds = likelihood(model(x, **kwargs))
             res["pred_mean"], res["pred_variance"] = preds.mean.clone(), preds.variance.clone()
+            res["pred_covariance"] = preds.covariance_matrix.clone()      # what preds.sample factorises (test_turbo.py:138)
         return res
     finally:
         torch.set_default_dtype(torch.float32)

@@ -56,6 +56,21 @@ def test_step_matches_reference_files(name, structure):
     assert rel(mean, c["train_mean"]) < (1e-9 if f64 else 1e-4)
 
 
+@pytest.mark.parametrize("name", sorted(SCASES))
+def test_pll_and_full_covariance_match_reference_files(name):
+    """mll_type="PLL" on likelihood(model(x)) (double noise, Q3) and the dense predictive covariance, against the
+    unmodified reference strategy files."""
+    c, P = _case(name)
+    f64 = c["x"].dtype == torch.float64
+    tol_v, tol_g = (1e-9, 1e-7) if f64 else (1e-4, 1e-4)
+    val, grads = O.pll_and_grads(P, c["x"], c["Vx"], c["y"], c["num_data"], c["variant"], noise_mult=2)
+    assert abs(float(val - c["pll"])) / abs(float(c["pll"])) < tol_v
+    for k, g in c["pll_grads"].items():
+        assert rel(grads[k].reshape(g.shape), g) < tol_g, (k, rel(grads[k].reshape(g.shape), g))
+    mean, cov = O.predictive_full(P, c["x"], c["Vx"], c["variant"], add_noise=True)
+    assert rel(cov, c["pred_covariance"]) < (1e-9 if f64 else 1e-4)
+
+
 def test_kernel_is_directional_derivative_of_rbf():
     """8c(1): K equals value / directional derivatives / mixed second derivative of the scalar RBF by autograd."""
     torch.manual_seed(0)
