@@ -42,28 +42,150 @@ __device__ __forceinline__ void rsqrt_sqrt_f64(double d, double& rinv, double& r
   root = l;
 }
 
-// Factorise the nb x nb block at A (lower part read) and invert the factor, both inside one CTA in shared memory,
-// blocked by 8 columns so that almost all work is rank-8 updates (8 FMAs per shared-memory element touched) and only
-// 2 block barriers per 8 columns are on the critical path:
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// 8-byte asynchronous global -> shared copy; bytes = 0 writes a zero instead (the source is not read).  The loads of a
+// whole operand block are in flight together instead of one L2 round trip per loop iteration.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Factorise the nb x nb diagonal block k and invert the factor, both inside one CTA in shared memory.
+//
+// Prologue (Aleft != null, i.e. k >= 1): the step-(k-1) update of THIS block is applied here instead of by separate
+// panel / column-update launches, so that the chain  potrf(k-1) -> potrf(k)  is the whole critical path and the panel
+// solve + trailing update of step k-1 run beside it on another stream (chol_factor_inverse):
+//     Z = A[k,k-1] * W11(k-1)^T          (= L[k,k-1]; DMMA from shared memory, k-range cut by the triangle of W11)
+//     A[k,k] <- A[k,k] - Z Z^T           (lower 8x8 tiles only)
+// Operands are staged with a row stride of nbp+4 doubles (bank pair (4g + t) mod 16: conflict-free DMMA fragments).
+//
+// Factor / inverse, blocked by 8 columns so that almost all work is rank-8 updates and only 2 block barriers per 8
+// columns are on the critical path:
 //   factor : (A) one warp factors the 8x8 diagonal block in registers (pivots and multipliers move by shuffles),
 //            (B) one thread per row solves the 8-column panel, (C) all threads apply the rank-8 trailing update.
 //   inverse: block row I:  T = L[I,0:I] * W[0:I,0:I],  D = inv(L[I,I]) (one warp),  W[I,0:I] = -D * T,  W[I,I] = D.
 // The block is padded to a multiple of 8 with the identity.  Writes L (upper part zeroed) and W = L^-1.
+constexpr int POTRF_MAXBLK = 5;      // (nbp/8) * ceil(nbp/24) 8x24 output blocks over 16 warps, nbp <= 112
+
 __global__ void __launch_bounds__(POTRF_THREADS)
 potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl,
-                double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset) {
+                double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset,
+                const double* __restrict__ Aleft, const double* __restrict__ Wprev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nbp = (nb + 7) & ~7, ld = nbp + 1;
-  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
-  double* Ws = Ls + nbp * ld;                         // [nbp][ld]
-  double* rdg = Ws + nbp * ld;                        // [nbp] reciprocals of the diagonal of L
+  const int nbp = (nb + 7) & ~7, ld = nbp + 1, ldp = nbp + 4;
+  double* R1 = reinterpret_cast<double*>(smem_raw);   // [nbp][ldp]  prologue: A[k,k-1] then Z ; afterwards Ws
+  double* R2 = R1 + nbp * ldp;                        // [nbp][ldp]  prologue: W11(k-1)       ; afterwards Ls
+  double* rdg = R2 + nbp * ldp;                       // [nbp] reciprocals of the diagonal of L
+  double* Ls = R2;                                    // [nbp][ld]
+  double* Ws = R1;                                    // [nbp][ld]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 31, ty = tid >> 5;             // 32 x 16 mapping of the trailing update
-  for (int i = ty; i < nbp; i += 16)
-    for (int c = tx; c < nbp; c += 32) {
-      Ls[i * ld + c] = (c <= i) ? ((i < nb) ? A[(int64_t)i * lda + c] : (i == c ? 1.0 : 0.0)) : 0.0;
-      Ws[i * ld + c] = 0.0;
+  if (Aleft != nullptr) {
+    for (int i = ty; i < nbp; i += 16)
+      for (int c = tx; c < nbp; c += 32) {
+        const bool in = i < nb && c < nb;
+        cp_async8(R1 + i * ldp + c, in ? Aleft + (int64_t)i * lda + c : Aleft, in);
+        cp_async8(R2 + i * ldp + c, (in && c <= i) ? Wprev + (int64_t)i * ldw + c : Wprev, in && c <= i);
+      }
+    cp_async_wait_all();
+    __syncthreads();
+    const int T = nbp >> 3, groups = (T + 2) / 3, nblocks = T * groups;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[POTRF_MAXBLK][3][2];
+#pragma unroll
+    for (int b = 0; b < POTRF_MAXBLK; ++b) {            // Z = X Y^T, 8 x 24 blocks round-robin over the warps
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[b][q][0] = acc[b][q][1] = 0.0;
+      const int blk = warp + 16 * b;
+      if (blk < nblocks) {
+        const int ri = blk / groups, cg = blk % groups;
+        const int kmax = 8 * min(3 * cg + 3, T);       // W11 is lower triangular: Y[j][k] = 0 for k > j
+        const double* xa = R1 + (8 * ri + g) * ldp + t;
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+          const double a = xa[k0];
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (3 * cg + q < T) dmma884(acc[b][q], a, R2[(8 * (3 * cg + q) + g) * ldp + k0 + t]);
+        }
+      }
     }
+    __syncthreads();                                   // X and Y are dead
+    for (int i = ty; i < nbp; i += 16)                 // A[k,k] (lower) streams into the Ls region underneath the SYRK
+      for (int c = tx; c < nbp; c += 32) {
+        const bool in = i < nb && c <= i;
+        cp_async8(Ls + i * ld + c, in ? A + (int64_t)i * lda + c : A, in);
+      }
+#pragma unroll
+    for (int b = 0; b < POTRF_MAXBLK; ++b) {
+      const int blk = warp + 16 * b;
+      if (blk < nblocks) {
+        const int ri = blk / groups, cg = blk % groups;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (3 * cg + q < T) {
+            double* z = R1 + (8 * ri + g) * ldp + 8 * (3 * cg + q) + 2 * t;
+            z[0] = acc[b][q][0];
+            z[1] = acc[b][q][1];
+          }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < POTRF_MAXBLK; ++b) {            // D = Z Z^T on the lower tiles (reuses acc)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[b][q][0] = acc[b][q][1] = 0.0;
+      const int blk = warp + 16 * b;
+      if (blk < nblocks) {
+        const int ri = blk / groups, cg = blk % groups;
+        if (3 * cg <= ri) {
+          const double* za = R1 + (8 * ri + g) * ldp + t;
+          for (int k0 = 0; k0 < nbp; k0 += 4) {
+            const double a = za[k0];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (3 * cg + q <= ri) dmma884(acc[b][q], a, R1[(8 * (3 * cg + q) + g) * ldp + k0 + t]);
+          }
+        }
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();                                   // A[k,k] has landed in Ls; Z is dead: its region becomes Ws
+#pragma unroll
+    for (int b = 0; b < POTRF_MAXBLK; ++b) {            // Ls = A[k,k] - D below / on the diagonal, identity on the padding
+      const int blk = warp + 16 * b;
+      if (blk < nblocks) {
+        const int ri = blk / groups, cg = blk % groups;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (3 * cg + q <= ri) {
+            const int r = 8 * ri + g;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * (3 * cg + q) + 2 * t + e;
+              if (c <= r) Ls[r * ld + c] = (r < nb) ? Ls[r * ld + c] - acc[b][q][e] : (r == c ? 1.0 : 0.0);
+            }
+          }
+      }
+    }
+    for (int i = ty; i < nbp; i += 16)
+      for (int c = tx; c < nbp; c += 32) Ws[i * ld + c] = 0.0;
+  } else {
+    for (int i = ty; i < nbp; i += 16)
+      for (int c = tx; c < nbp; c += 32) {
+        const bool in = i < nb && c <= i;
+        cp_async8(Ls + i * ld + c, in ? A + (int64_t)i * lda + c : A, in);
+        Ws[i * ld + c] = 0.0;
+      }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int i = nb + tid; i < nbp; i += POTRF_THREADS) Ls[i * ld + i] = 1.0;      // identity on the padding
+  }
   // ------------------------------------------------------------------------------------------------ factor
   for (int k0 = 0; k0 < nbp; k0 += 8) {
     __syncthreads();
@@ -190,17 +312,20 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st) {
   if (Mp <= 0) return DSVGP_OK;
-  if (!Awork || !L || !W || !info || nb0 <= 0 || nb0 > 128 || (nb0 << nlev) != Mp) return DSVGP_ERR_ARG;
+  if (!Awork || !L || !W || !info || nb0 <= 0 || nb0 > 112 || (nb0 << nlev) != Mp) return DSVGP_ERR_ARG;
   const int nblk = 1 << nlev;
   const int nbp = (nb0 + 7) & ~7;
-  const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 1) + nbp);
+  if ((nbp >> 3) * (((nbp >> 3) + 2) / 3) > 16 * POTRF_MAXBLK) return DSVGP_ERR_ARG;
+  const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 4) + nbp);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(potrf_inv_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(info, 0, sizeof(int), st);
-  // Look-ahead: after the panel of step k, the main stream updates only block column k+1 (all the next diagonal
-  // block and panel need) and goes straight to the next diagonal block; the rest of the trailing update runs on a side
-  // stream.  Events order (a) side(k) after panel(k), (b) the column update of step k+1 after side(k) (both write block
-  // column k+2).  Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
+  // Two chains.  Main stream: the diagonal blocks only -- potrf(k) applies the step-(k-1) update to its own block in
+  // its prologue, so it needs W11(k-1) (stream order) and block row k updated through step k-2 (event from the side
+  // stream).  Side stream, per step k: panel  L[k+1:, k] = A[k+1:, k] W11(k)^T  (after potrf(k)), then the trailing
+  // update of everything below block row k+1 (a lower trapezoid: block column k+1 included, the diagonal block (k+1,k+1)
+  // excluded -- potrf(k+1) owns it).  The 32 latency-bound single-CTA kernels overlap the throughput-bound GEMMs.
+  // Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
   struct SideCtx { cudaStream_t side = nullptr; cudaEvent_t ev_main[64], ev_side[64]; bool ready = false; };
   static SideCtx ctxs[16];                              // one side stream + event pool per device
   int dev = 0;
@@ -215,47 +340,45 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     sc.ready = true;
   }
   cudaStream_t side = sc.side;
-  cudaEvent_t* ev_main = sc.ev_main;
-  cudaEvent_t* ev_side = sc.ev_side;
-  const bool lookahead = nblk >= 4 && nblk <= 64;
+  const bool two_chains = nblk <= 64;
   int last_side = -1;
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
-    potrf_inv_block<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o,
-                                                    ldw, nb0, info, (int)o);
+    // (more than 64 blocks: more steps than pooled events -- everything goes on the caller's stream, in order)
+    if (two_chains && k >= 2 && last_side >= k - 2) cudaStreamWaitEvent(st, sc.ev_side[k - 2], 0);
+    const double* Aleft = k > 0 ? Awork + o * lda + (o - nb0) : nullptr;
+    const double* Wprev = k > 0 ? W + (o - nb0) * ldw + (o - nb0) : nullptr;
+    potrf_inv_block<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o, ldw,
+                                                    nb0, info, (int)o, Aleft, Wprev);
     CHECK_LAUNCH();
     const int m = Mp - (int)o - nb0;
     if (m > 0) {
+      cudaStream_t gs = two_chains ? side : st;
+      if (two_chains) {
+        cudaEventRecord(sc.ev_main[k], st);
+        cudaStreamWaitEvent(side, sc.ev_main[k], 0);
+      }
       double* L21 = L + (o + nb0) * ldl + o;
       // panel  L21 = A21 * W11^T   (op(B) = W11^T is upper triangular)
       int rc = gemm1<double>(false, true, m, nb0, nb0, 1.0, Awork + (o + nb0) * lda + o, lda, W + o * ldw + o, ldw, 0.0,
-                             L21, ldl, TRI_NONE, TRI_UPPER, 0, st);
+                             L21, ldl, TRI_NONE, TRI_UPPER, 0, gs);
       if (rc) return rc;
-      double* A22 = Awork + (o + nb0) * lda + (o + nb0);
-      if (!lookahead) {
-        // trailing update  A22 -= L21 * L21^T  (lower tiles only)
-        rc = gemm1<double>(false, true, m, m, nb0, -1.0, L21, ldl, L21, ldl, 1.0, A22, lda, TRI_NONE, TRI_NONE, 1, st);
+      const int m2 = m - nb0;
+      if (m2 > 0) {
+        // trailing update below block row k+1:  A22[nb0:, :] -= L21[nb0:, :] * L21^T  on the tiles with col <= row + nb0
+        const double* L21b = L21 + (int64_t)nb0 * ldl;
+        double* A22b = Awork + (o + 2 * nb0) * lda + (o + nb0);
+        rc = gemm<double>(false, true, m2, m, nb0, -1.0, L21b, ldl, L21, ldl, 1.0, A22b, lda, TRI_NONE, TRI_NONE, 1, 1, 0, 0, 0,
+                          gs, nullptr, 0, nullptr, 0, nullptr, 0, nb0);
         if (rc) return rc;
-      } else {
-        if (last_side >= 0) cudaStreamWaitEvent(st, ev_side[last_side], 0);
-        // block column k+1:  A22[:, 0:nb0] -= L21 * L21[0:nb0, :]^T
-        rc = gemm1<double>(false, true, m, nb0, nb0, -1.0, L21, ldl, L21, ldl, 1.0, A22, lda, TRI_NONE, TRI_NONE, 0, st);
-        if (rc) return rc;
-        const int m2 = m - nb0;
-        if (m2 > 0) {
-          cudaEventRecord(ev_main[k], st);
-          cudaStreamWaitEvent(side, ev_main[k], 0);
-          const double* L21b = L21 + (int64_t)nb0 * ldl;
-          rc = gemm1<double>(false, true, m2, m2, nb0, -1.0, L21b, ldl, L21b, ldl, 1.0, A22 + (int64_t)nb0 * lda + nb0, lda,
-                             TRI_NONE, TRI_NONE, 1, side);
-          if (rc) return rc;
-          cudaEventRecord(ev_side[k], side);
-          last_side = k;
-        }
+      }
+      if (two_chains) {
+        cudaEventRecord(sc.ev_side[k], side);
+        last_side = k;
       }
     }
   }
-  if (lookahead && last_side >= 0) cudaStreamWaitEvent(st, ev_side[last_side], 0);
+  if (two_chains && last_side >= 0) cudaStreamWaitEvent(st, sc.ev_side[last_side], 0);
   // recursive inverse; Awork (no longer needed) is the scratch for T = L21 * W11
   for (int lev = 0; lev < nlev; ++lev) {
     const int b = nb0 << lev, npairs = nblk >> (lev + 1);

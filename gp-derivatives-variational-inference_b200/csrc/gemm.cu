@@ -42,6 +42,7 @@ struct GemmParams {
   int64_t lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC;
   T alpha, beta;
   int a_tri, b_tri, c_tri;
+  int c_off;   // c_tri == 1: tiles with n0 >= m0 + BM + c_off are skipped (c_off > 0: lower trapezoid)
 };
 
 // element (r, k) of op(A) (r in M, k in K) lives at A[r*lda + k] (TA=false) or A[k*lda + r] (TA=true)
@@ -52,7 +53,7 @@ gemm_kernel(GemmParams<T> p) {
   __shared__ __align__(16) T Bs[2][BN * LDS_];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (p.c_tri == 1 && n0 >= m0 + BM) return;     // tile strictly above the diagonal
+  if (p.c_tri == 1 && n0 >= m0 + BM + p.c_off) return;     // tile strictly above the (shifted) diagonal
   const T* A = p.A + (int64_t)blockIdx.z * p.sA;
   const T* B = p.B + (int64_t)blockIdx.z * p.sB;
   T* C = p.C + (int64_t)blockIdx.z * p.sC;
@@ -249,10 +250,10 @@ gemm_kernel(GemmParams<T> p) {
 template <typename T>
 int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
          T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
-         cudaStream_t st, const T* D, int64_t ldd, T* C2, int64_t ldc2, const T* D2, int64_t ldd2) {
+         cudaStream_t st, const T* D, int64_t ldd, T* C2, int64_t ldc2, const T* D2, int64_t ldd2, int c_off) {
   if (M <= 0 || N <= 0 || batch <= 0) return DSVGP_OK;
   if (!A || !B || !C || K < 0 || (C2 && !D2)) return DSVGP_ERR_ARG;
-  GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri};
+  GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri, c_off};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
   if (!ta && !tb) gemm_kernel<T, false, false><<<grid, GEMM_THREADS, 0, st>>>(p);
   else if (!ta && tb) gemm_kernel<T, false, true><<<grid, GEMM_THREADS, 0, st>>>(p);
@@ -264,9 +265,9 @@ int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda
 
 template int gemm<float>(bool, bool, int, int, int, float, const float*, int64_t, const float*, int64_t, float, float*,
                          int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const float*, int64_t, float*, int64_t,
-                         const float*, int64_t);
+                         const float*, int64_t, int);
 template int gemm<double>(bool, bool, int, int, int, double, const double*, int64_t, const double*, int64_t, double,
                           double*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, cudaStream_t, const double*, int64_t,
-                          double*, int64_t, const double*, int64_t);
+                          double*, int64_t, const double*, int64_t, int);
 
 }  // namespace dsvgp

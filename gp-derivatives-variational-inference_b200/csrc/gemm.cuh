@@ -13,7 +13,8 @@ template <typename T>
 int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
          T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
          cudaStream_t st, const T* D = nullptr, int64_t ldd = 0,    // D != null: C = alpha*AB + beta*D
-         T* C2 = nullptr, int64_t ldc2 = 0, const T* D2 = nullptr, int64_t ldd2 = 0);   // C2 = C + D2
+         T* C2 = nullptr, int64_t ldc2 = 0, const T* D2 = nullptr, int64_t ldd2 = 0,    // C2 = C + D2
+         int c_off = 0);   // c_tri == 1 with c_off > 0: lower trapezoid, tiles up to c_off columns right of the diagonal
 
 template <typename T>
 inline int gemm1(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
