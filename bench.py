@@ -300,7 +300,15 @@ def main():
         return e0.elapsed_time(e1) / k
     from dsvgp_b200 import engine as _eng
     use_tc = bool(getattr(ws, "tc", False) and getattr(fac, "tc", False))
-    if use_tc:
+    use_tch = bool(getattr(ws, "tch", False) and getattr(fac, "tch", False))
+    if use_tch:
+        ops.kdir_fwd_half(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, ws.Kh, ws.Kl, fac.scales[1:2], canon=ws.canon)
+        whiten = lambda: ops.gemm_tch((fac.Wh, fac.Wl), (ws.Kh, ws.Kl), ws.A, Mq, nq, Mq, fac.scales[8:9], a_tri=ops.TRI_LOWER,
+                                      chunk=_eng.TCH_CHUNK, Ch=(ws.Ah, ws.Al), c_scale=fac.scales[3:4])
+        kname = ("gemm_tch2_kernel (A = L^-1 K_zx: tcgen05.mma kind::f16 x3 (3xFP16 on power-of-two-scaled two-half operands, "
+                 f"22 significand bits), TMA-fed, CTA pairs, TMEM accumulators restarted every {_eng.TCH_CHUNK} k-block(s) of 64, "
+                 "fp32 master sums; epilogue also writes the split of A for the next product)")
+    elif use_tc:
         ops.split_lo(ws.Kzx, ws.lo1, Mq, nq)
         whiten = lambda: ops.gemm_tc(fac.Wt, fac.Wt_lo, ws.Kzx, ws.lo1, ws.A, Mq, nq, Mq, a_tri=ops.TRI_LOWER,
                                      chunk=_eng.TC_CHUNK, C_lo=ws.lo2)
@@ -312,14 +320,21 @@ def main():
                  else "gemm_kernel (A = L^-1 K_zx, 3xTF32 mma.sync, fp64 master accumulation)")
     ms_gemm = timed_local(whiten, reps)
     # kernel assembly as the step runs it (K_zx plus, on the tcgen05 path, its TF32 "lo" companion) and K only
-    asm_lo = ws.lo1 if use_tc else None
-    ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon, out_lo=asm_lo), reps)
+    if use_tch:
+        ms_asm = timed_local(lambda: ops.kdir_fwd_half(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, ws.Kh, ws.Kl, fac.scales[1:2],
+                                                       canon=ws.canon), reps)
+    else:
+        asm_lo = ws.lo1 if use_tc else None
+        ms_asm = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon, out_lo=asm_lo), reps)
     ms_asm_k = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, canon=ws.canon), reps)
     ms_asm_general = timed_local(lambda: ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx), reps)
     s = 8 if dtype == torch.float64 else 4
     gemm_flops = float(Mq) * Mq * nq
     if dtype == torch.float64:
         tensor_peak, peak_note = 40.0, "nominal B200 fp64 (DMMA) 40 TFLOP/s -- no measured fp64 peak in MEASURED_PEAKS.json"
+    elif use_tch:
+        tensor_peak = pk["bf16_sustained"] / 3
+        peak_note = f"{pk['src']} bf16 dense sustained {pk['bf16_sustained']} TFLOP/s (fp16 runs at the bf16 rate) / 3 (3xFP16 passes)"
     else:
         tensor_peak = pk["bf16_sustained"] / 2 / 3
         peak_note = f"{pk['src']} bf16 dense sustained {pk['bf16_sustained']} TFLOP/s / 2 (TF32 rate) / 3 (3xTF32 passes)"
@@ -343,10 +358,12 @@ def main():
                               "path": "canonical data-side directions (detected on device)" if ws.canon is not None else "general directions",
                               "general_directions_ms": ms_asm_general,
                               "general_directions_frac": asm_bytes / (ms_asm_general * 1e-3) / 1e9 / pk["hbm"],
-                              "in_step": {"note": "inside the training step the same launch also writes the TF32 lo companion of K_zx "
-                                                  "(fused, replaces a separate split pass): twice the bytes",
-                                          "ms": ms_asm, "bytes_written": asm_bytes * (2 if use_tc else 1),
-                                          "hbm_frac": asm_bytes * (2 if use_tc else 1) / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
+                              "in_step": {"note": ("inside the training step the same kernel writes only the two-half (fp16 hi, lo) split of "
+                                                   "K_zx * scale, the operand of the 3xFP16 product: the same bytes as K alone") if use_tch
+                                                  else ("inside the training step the same launch also writes the TF32 lo companion of "
+                                                        "K_zx (fused, replaces a separate split pass): twice the bytes"),
+                                          "ms": ms_asm, "bytes_written": asm_bytes * (2 if (use_tc and not use_tch) else 1),
+                                          "hbm_frac": asm_bytes * (2 if (use_tc and not use_tch) else 1) / (ms_asm * 1e-3) / 1e9 / pk["hbm"],
                                           "traffic": ncu_traffic("kdir_fwd")},
                               "peak_note": f"{pk['src']} copy bandwidth"},
     }

@@ -7,6 +7,7 @@
 #include "kdir.cuh"
 #include "misc.cuh"
 #include "optim.cuh"
+#include "tc_prep.cuh"
 #include "trmm_tc.cuh"
 
 using namespace dsvgp;
@@ -84,6 +85,23 @@ int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const doub
   return gemm<double>(ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd, C2, ldc2, D2, ldd2);
 }
 
+int dsvgp_absmax_f32(const float* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s) { return absmax<float>(x, ld, rows, cols, mode, out_bits, ST(s)); }
+int dsvgp_absmax_f64(const double* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s) { return absmax<double>(x, ld, rows, cols, mode, out_bits, ST(s)); }
+int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* maxbits, int Mq, float* scales, int stage, dsvgp_stream_t s) { return tc_scales(hyp, jitter, maxbits, Mq, scales, stage, ST(s)); }
+int dsvgp_split_half_f32(const float* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<float>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
+int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<double>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
+int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s) {
+  if (!x1 || !x2 || !hyp || !K || !Kh || !Kl || !hscale || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;
+  return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag, nullptr, Kh, Kl, ldkh, hscale);
+}
+int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s) {
+  if (!A || !C || !m || !gmu || !gvar || !tp || !t || !dAh || !dAl || !Agh || !Agl || !s_dA || !s_Ag) return DSVGP_ERR_ARG;
+  return dA_apply_half(A, C, ld, rows, nq, m, gmu, gvar, tp, nslab, t, dAh, dAl, Agh, Agl, ldh, s_dA, s_Ag, ST(s));
+}
+int dsvgp_gemm_tch_supported_f32(const void* A, int64_t lda, const void* B, int64_t ldb, int b_kmajor, int N) { return gemm_tch_supported(A, lda, B, ldb, b_kmajor, N); }
+int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* Bh, const void* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, const float* ab_inv, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, void* Ch, void* Cl, int64_t ldch, const float* c_scale, void* C2h, void* C2l, int64_t ldc2h, const float* c2_scale, int a_tri, int c_lower, int chunk, int nsplit, float* split_ws, dsvgp_stream_t s) {
+  return gemm_tch(Ah, Al, lda, Bh, Bl, ldb, b_kmajor, M, N, K, (float)alpha, (float)beta, ab_inv, C, ldc, D, ldd, C2, ldc2, D2, ldd2, Ch, Cl, ldch, c_scale, C2h, C2l, ldc2h, c2_scale, a_tri, c_lower, chunk, nsplit, split_ws, ST(s));
+}
 int dsvgp_gemm_tc_supported_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N) { return gemm_tc_supported(A, lda, B, ldb, b_kmajor, N); }
 int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo, int nsplit, float* split_ws, dsvgp_stream_t s) {
   return gemm_tc(Ah, Al, lda, Bh, Bl, ldb, b_kmajor, M, N, K, (float)alpha, (float)beta, C, ldc, D, ldd, C2, ldc2, D2, ldd2, a_tri, c_lower, chunk, Clo, C2lo, nsplit, split_ws, ST(s));

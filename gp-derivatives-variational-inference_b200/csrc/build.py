@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "dsvgp_b200", "libdsvgp_b200.so")
-SOURCES = ["kdir.cu", "gemm.cu", "chol.cu", "misc.cu", "optim.cu", "data.cu", "trmm_tc.cu", "api.cu"]
+SOURCES = ["kdir.cu", "gemm.cu", "chol.cu", "misc.cu", "optim.cu", "data.cu", "tc_prep.cu", "trmm_tc.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -13,6 +13,8 @@
 //
 // T  = dtype of x (model dtype); TK = dtype of K / dK and of all arithmetic (double for K_zz always, because
 // the reference factorises K_zz in fp64, DirectionalGradVariationalStrategy.py:74).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kdir.cuh"
 
@@ -210,12 +212,16 @@ size_t fwd_v4_smem_bytes(int dpad, int tib = V4_TIB) {
 // MODE 0: general directions only (returns at once if the device flag says canonical); MODE 1: canonical only (returns
 // at once otherwise).  Both are launched back to back when a flag is supplied: the choice is made on the device without
 // a host synchronisation, and the canonical variant compiles to far fewer registers (3 CTAs per SM instead of 2).
-template <int P1, int P2, bool WITH_LO, int MODE>
+// OUT 0: K (fp32).  OUT 1: K and its TF32 lo part (operands of the 3xTF32 product).  OUT 2: no fp32 matrix at all, only
+// the two-half split (Kh, Kl) of K * *hscale -- the operands of the 3xFP16 product (trmm_tc.cu), same bytes as K alone.
+template <int P1, int P2, int OUT, int MODE>
 __global__ void __launch_bounds__(256, MODE == 1 ? 3 : 2)
 kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
             const float* __restrict__ w2, const int* __restrict__ cidx2, const int* __restrict__ canon_flag, int n2, int d,
             const double* __restrict__ hyp, int use_os, float diag_add, float* __restrict__ K, int64_t ldk,
-            float* __restrict__ Klo, int TIB, int stream_stores) {
+            float* __restrict__ Klo, int TIB, int stream_stores, __half* __restrict__ Kh, __half* __restrict__ Kl,
+            int64_t ldkh, const float* __restrict__ hscale) {
+  constexpr bool WITH_LO = OUT == 1;
   constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ;
   const int dpad = (d + 3) & ~3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -266,7 +272,9 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
   const float ell = (float)hyp[0], os = use_os ? (float)hyp[1] : 1.f;
   const float il2 = 1.f / (ell * ell);
   float* mystrip = strip + warp * (TJ * Q2);
-  const bool vec_ok = ((ldk & 3) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+  const bool vec_ok = OUT == 2 ? (((ldkh & 3) == 0) && (((reinterpret_cast<uintptr_t>(Kh) | reinterpret_cast<uintptr_t>(Kl)) & 7) == 0))
+                               : (((ldk & 3) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0));
+  const float hs = OUT == 2 ? *hscale : 1.f;
   const int cols = min(TJ * Q2, (n2 - j0) * Q2);
 
   for (int it = 0; it < TIB / 8; ++it) {
@@ -381,6 +389,38 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
       for (int v = 0; v < Q2; ++v)
         *reinterpret_cast<float4*>(mystrip + lane * 4 * Q2 + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
       __syncwarp();
+      if constexpr (OUT == 2) {
+        __half* hrow = Kh + (int64_t)(gi * Q1 + a) * ldkh + (int64_t)j0 * Q2;
+        __half* lrow = Kl + (int64_t)(gi * Q1 + a) * ldkh + (int64_t)j0 * Q2;
+#pragma unroll
+        for (int v = 0; v < Q2; ++v) {
+          const int col = v * 128 + 4 * lane;
+          const float4 t = *reinterpret_cast<const float4*>(mystrip + col);
+          const float tv[4] = {t.x * hs, t.y * hs, t.z * hs, t.w * hs};
+          __half h[4], l[4];
+#pragma unroll
+          for (int z = 0; z < 4; ++z) {
+            h[z] = __float2half_rn(tv[z]);
+            l[z] = __float2half_rn(tv[z] - __half2float(h[z]));
+          }
+          if (vec_ok && col + 3 < cols) {
+            if (stream_stores) {
+              __stcs(reinterpret_cast<uint2*>(hrow + col), *reinterpret_cast<const uint2*>(h));
+              __stcs(reinterpret_cast<uint2*>(lrow + col), *reinterpret_cast<const uint2*>(l));
+            } else {
+              *reinterpret_cast<uint2*>(hrow + col) = *reinterpret_cast<const uint2*>(h);
+              *reinterpret_cast<uint2*>(lrow + col) = *reinterpret_cast<const uint2*>(l);
+            }
+          } else {
+            for (int z = 0; z < 4; ++z)
+              if (col + z < cols) {
+                hrow[col + z] = h[z];
+                lrow[col + z] = l[z];
+              }
+          }
+        }
+        continue;
+      }
       float* grow = K + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2;
       float* lrow = WITH_LO ? Klo + (int64_t)(gi * Q1 + a) * ldk + (int64_t)j0 * Q2 : nullptr;   // same leading dimension
 #pragma unroll
@@ -1087,31 +1127,32 @@ static int launch_fwd_blocked(const T* x1, const TK* u1, int n1, const T* x2, co
 template <int P1, int P2>
 static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* x2, const float* w2, const int* cidx2,
                          const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
-                         int64_t ldk, float* Klo, cudaStream_t st) {
+                         int64_t ldk, float* Klo, cudaStream_t st, __half* Kh = nullptr, __half* Kl = nullptr,
+                         int64_t ldkh = 0, const float* hscale = nullptr) {
   const int tib = g_fwd_tib;
   const int64_t out_bytes = (int64_t)n1 * (P1 + 1) * n2 * (P2 + 1) * 4 * (Klo ? 2 : 1);
   const int stream_stores = g_fwd_stream_stores == 2 ? (out_bytes > (int64_t)(64 << 20)) : g_fwd_stream_stores;
   const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3, tib);
   dim3 grid(ceil_div(n2, V4_TJ), ceil_div(n1, tib));
-  auto gen = Klo ? kdir_fwd_v4<P1, P2, true, 0> : kdir_fwd_v4<P1, P2, false, 0>;
+  auto gen = Kh ? kdir_fwd_v4<P1, P2, 2, 0> : Klo ? kdir_fwd_v4<P1, P2, 1, 0> : kdir_fwd_v4<P1, P2, 0, 0>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   gen<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo, tib,
-                               stream_stores);
+                               stream_stores, Kh, Kl, ldkh, hscale);
   CHECK_LAUNCH();
   if (P2 > 0 && cidx2 && canon_flag) {
-    auto can = Klo ? kdir_fwd_v4<P1, P2, true, 1> : kdir_fwd_v4<P1, P2, false, 1>;
+    auto can = Kh ? kdir_fwd_v4<P1, P2, 2, 1> : Klo ? kdir_fwd_v4<P1, P2, 1, 1> : kdir_fwd_v4<P1, P2, 0, 1>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(can, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     can<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, (float)diag_add, K, ldk, Klo, tib,
-                                 stream_stores);
+                                 stream_stores, Kh, Kl, ldkh, hscale);
     CHECK_LAUNCH();
   }
-  return Klo ? 1 : DSVGP_OK;       // 1: the lo companion was written too
+  return Kh ? 2 : Klo ? 1 : DSVGP_OK;       // 1: the lo companion was written too; 2: only the half split was written
 }
 
 template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
              const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st, const int* cidx2,
-             const int* canon_flag, TK* Klo) {
+             const int* canon_flag, TK* Klo, void* Kh, void* Kl, int64_t ldkh, const float* hscale) {
   if (n1 <= 0 || n2 <= 0) return DSVGP_OK;
   if (p1 < 0 || p2 < 0 || p1 > DSVGP_MAXP || p2 > DSVGP_MAXP || d <= 0) return DSVGP_ERR_ARG;
   if constexpr (sizeof(T) == 4 && sizeof(TK) == 4) {
@@ -1121,7 +1162,8 @@ int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w
     if (n2 >= 512 && need <= 200 * 1024) {
 #define V4_CASE(A, B)                                                                                          \
   if (p1 == A && p2 == B)                                                                                      \
-    return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, Klo, st);
+    return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, Klo, st,          \
+                               static_cast<__half*>(Kh), static_cast<__half*>(Kl), ldkh, hscale);
       V4_CASE(1, 1) V4_CASE(2, 2) V4_CASE(1, 0) V4_CASE(2, 0) V4_CASE(3, 0)
 #undef V4_CASE
     }
@@ -1272,7 +1314,8 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
 #define INST(T, TK)                                                                                             \
   template int normalize_dirs<T, TK>(const T*, int, int, TK*, TK*, cudaStream_t, int*, int*);                               \
   template int kdir_fwd<T, TK>(const T*, const TK*, int, int, const T*, const TK*, int, int, int, const double*, \
-                               int, double, TK*, int64_t, cudaStream_t, const int*, const int*, TK*);                                        \
+                               int, double, TK*, int64_t, cudaStream_t, const int*, const int*, TK*, void*, void*,  \
+                               int64_t, const float*);                                                          \
   template int kdir_bwd<T, TK>(const T*, const TK*, const TK*, int, int, const T*, const TK*, int, int, int,    \
                                const double*, int, const TK*, int64_t, int, double, double*, double*, double*,  \
                                void*, size_t, cudaStream_t);

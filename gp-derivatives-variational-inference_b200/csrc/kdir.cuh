@@ -16,7 +16,10 @@ template <typename T, typename TK>
 int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2, int d,
              const double* hyp, int use_os, double diag_add, TK* K, int64_t ldk, cudaStream_t st,
              const int* cidx2 = nullptr, const int* canon_flag = nullptr,   // canonical column-side fast path (fp32)
-             TK* Klo = nullptr);   // fp32 only: also write the TF32 'lo' companion of K; returns 1 if it was written
+             TK* Klo = nullptr,    // fp32 only: also write the TF32 'lo' companion of K; returns 1 if it was written
+             void* Kh = nullptr, void* Kl = nullptr, int64_t ldkh = 0, const float* hscale = nullptr);
+// Kh/Kl (fp32 only): write ONLY the two-half split of K * *hscale (operands of the 3xFP16 product); returns 2 if the
+// vectorised kernel took the shape and wrote them (K untouched), otherwise K is written as usual and 0/1 is returned.
 
 template <typename TK>
 int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t st);

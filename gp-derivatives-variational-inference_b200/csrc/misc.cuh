@@ -25,6 +25,9 @@ int predict_finish(const T* pm, const T* pv, int nslab, int nq, int p2, const do
 template <typename T>
 int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp, double w, double min_var, T* gmu,
                T* gvar, double* sc, double* ws, cudaStream_t st);
+int dA_apply_half(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu,
+                  const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh,
+                  const float* s_dA, const float* s_Ag, cudaStream_t st);
 template <typename T>
 int pll_terms(const T* mu, const T* var, const T* y, int nq, double w, double min_var, T* gmu, T* gvar, double* sc,
               double* ws, cudaStream_t st);

@@ -1,0 +1,158 @@
+// Operand preparation for the 3xFP16 tensor-core products (trmm_tc.cu, gemm_tch): power-of-two scales from a-priori
+// bounds, and the two-half split of the small square factors.
+//
+// fp16 keeps tf32's 11 significand bits but only 5 exponent bits, so every matrix is multiplied by a power of two that
+// maps a RIGOROUS upper bound of its entries to 2^15 (half of the largest finite half).  A loose bound costs nothing
+// until it is loose by ~2^10: entries below 2^-18 of the bound keep an absolute error of 2^-40 of the bound.  Bounds,
+// with a = sqrt(os * max(1, 1/ell^2)) (largest prior standard deviation) and e = M' * max|E| >= ||E||_2:
+//   W = L^-1            ||W||_2 = lambda_min(K_zz + jitter I)^-1/2 <= jitter^-1/2
+//   K_zx                os * max(1, 1/ell, 2/ell^2)   (value, first and second directional derivatives of the RBF)
+//   A = W K_zx          column norms: k_j^T (K_zz + jitter I)^-1 k_j <= k_jj  =>  |A_ij| <= a
+//   E = tril(L_s) - I   max|E| itself
+//   B = L_s^T A         (1 + e) a
+//   C = (S - I) A       e (2 + e) a ;   dA = m g_mu^T + 2 C diag(g_var):  max|m| max|g_mu| + 2 max|g_var| e (2 + e) a
+//   A_g = A diag(g_var) a max|g_var|
+// Maxima are order-independent (atomicMax on the bit pattern of |x|), so scales -- and results -- are deterministic.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_prep.cuh"
+
+namespace dsvgp {
+
+__device__ __forceinline__ void atomic_absmax(unsigned* out, float v) {
+  const float a = fabsf(v);
+  if (a == a) atomicMax(out, __float_as_uint(a));      // non-negative floats order like their bit patterns; NaN skipped
+  else atomicMax(out, 0x7f800000u);                    // NaN -> +inf: the scale kernel falls back to 1
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+absmax_kernel(const T* __restrict__ x, int64_t ld, int rows, int cols, int mode, unsigned* __restrict__ out) {
+  // mode 0: all entries; 2: entries of tril(x) - I
+  float m = 0.f;
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int i = (int)(e / cols), j = (int)(e - (int64_t)i * cols);
+    if (mode == 2 && j > i) continue;
+    float v = (float)x[(int64_t)i * ld + j];
+    if (mode == 2 && i == j) v -= 1.f;
+    const float a = fabsf(v);
+    m = (a == a) ? fmaxf(m, a) : __int_as_float(0x7f800000);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomic_absmax(out, m);
+}
+
+__device__ __forceinline__ float pow2_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int ex = 15 - (int)ceilf(log2f(bound));
+  ex = max(-60, min(60, ex));
+  return exp2f((float)ex);
+}
+
+// scales: [0] sW [1] sK [2] sE [3] sA [4] sB [5] sdA [6] sAg | [8] 1/(sW sK) [9] 1/(sE sA) [10] 1/(sE sB) [11] 1/(sW sdA)
+//         [12] 1/(sAg sA).   maxbits: [0] max|E| [1] max|m| [2] max|g_mu| [3] max|g_var|
+// stage 0 (forward, needs hyp and maxbits[0]): entries 0-4, 8-10.  stage 1 (backward, needs maxbits[1..3]): 5, 6, 11, 12.
+__global__ void tc_scales_kernel(const double* __restrict__ hyp, double jitter, const unsigned* __restrict__ maxbits, int Mq,
+                                 float* __restrict__ sc, int stage) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float ell = (float)hyp[0], os = (float)hyp[1];
+  const float a = 1.01f * sqrtf(os * fmaxf(1.f, 1.f / (ell * ell)));
+  const float e = (float)Mq * __uint_as_float(maxbits[0]);
+  if (stage == 0) {
+    sc[0] = pow2_scale(1.01f * rsqrtf((float)jitter));
+    sc[1] = pow2_scale(1.01f * os * fmaxf(1.f, fmaxf(1.f / ell, 2.f / (ell * ell))));
+    sc[2] = pow2_scale(__uint_as_float(maxbits[0]));
+    sc[3] = pow2_scale(a);
+    sc[4] = pow2_scale((1.f + e) * a);
+    sc[8] = 1.f / (sc[0] * sc[1]);
+    sc[9] = 1.f / (sc[2] * sc[3]);
+    sc[10] = 1.f / (sc[2] * sc[4]);
+  } else {
+    const float mm = __uint_as_float(maxbits[1]), gm = __uint_as_float(maxbits[2]), gv = __uint_as_float(maxbits[3]);
+    sc[5] = pow2_scale(1.01f * (mm * gm + 2.f * gv * e * (2.f + e) * a));
+    sc[6] = pow2_scale(1.01f * a * gv);
+    sc[11] = 1.f / (sc[0] * sc[5]);
+    sc[12] = 1.f / (sc[6] * sc[3]);
+  }
+}
+
+// (hi, lo) = split of op(src) * *scale, plus optionally the split of its transpose, in one pass over src.
+// mode 0: src as is; 1: tril(src); 2: tril(src) - I.   32 x 32 tiles, 32 x 8 threads.
+template <typename S>
+__global__ void split_half_kernel(const S* __restrict__ src, int64_t lds, int rows, int cols, int mode,
+                                  const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                  int64_t ldh, __half* __restrict__ hiT, __half* __restrict__ loT, int64_t ldhT) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;
+  const float s = *scale;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + r, j = bj + tx;
+    float v = 0.f;
+    if (i < rows && j < cols && !(mode != 0 && j > i)) {
+      v = (float)src[(int64_t)i * lds + j];
+      if (mode == 2 && i == j) v -= 1.f;
+      v *= s;
+    }
+    tile[r][tx] = v;
+    if (i < rows && j < cols) {
+      const __half h = __float2half_rn(v);
+      hi[(int64_t)i * ldh + j] = h;
+      lo[(int64_t)i * ldh + j] = __float2half_rn(v - __half2float(h));
+    }
+  }
+  if (hiT == nullptr) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj + r, j = bi + tx;                 // transposed output is cols x rows
+    if (i < cols && j < rows) {
+      const float v = tile[tx][r];
+      const __half h = __float2half_rn(v);
+      hiT[(int64_t)i * ldhT + j] = h;
+      loT[(int64_t)i * ldhT + j] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
+template <typename T>
+int absmax(const T* x, int64_t ld, int rows, int cols, int mode, unsigned* out, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return DSVGP_OK;
+  if (!x || !out) return DSVGP_ERR_ARG;
+  int64_t nb = ceil_div64((int64_t)rows * cols, 256 * 8);
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+  absmax_kernel<T><<<(int)nb, 256, 0, st>>>(x, ld, rows, cols, mode, out);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int tc_scales(const double* hyp, double jitter, const unsigned* maxbits, int Mq, float* scales, int stage, cudaStream_t st) {
+  if (!hyp || !maxbits || !scales || !(jitter > 0.0)) return DSVGP_ERR_ARG;
+  tc_scales_kernel<<<1, 32, 0, st>>>(hyp, jitter, maxbits, Mq, scales, stage);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template <typename S>
+int split_half(const S* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh,
+               void* hiT, void* loT, int64_t ldhT, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return DSVGP_OK;
+  if (!src || !scale || !hi || !lo || (hiT && !loT)) return DSVGP_ERR_ARG;
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
+  split_half_kernel<S><<<grid, block, 0, st>>>(src, lds, rows, cols, mode, scale, static_cast<__half*>(hi),
+                                               static_cast<__half*>(lo), ldh, static_cast<__half*>(hiT),
+                                               static_cast<__half*>(loT), ldhT);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+template int absmax<float>(const float*, int64_t, int, int, int, unsigned*, cudaStream_t);
+template int absmax<double>(const double*, int64_t, int, int, int, unsigned*, cudaStream_t);
+template int split_half<float>(const float*, int64_t, int, int, int, const float*, void*, void*, int64_t, void*, void*, int64_t,
+                               cudaStream_t);
+template int split_half<double>(const double*, int64_t, int, int, int, const float*, void*, void*, int64_t, void*, void*,
+                                int64_t, cudaStream_t);
+
+}  // namespace dsvgp

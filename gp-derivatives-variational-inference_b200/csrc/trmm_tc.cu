@@ -24,6 +24,7 @@
 // Triangular structure of A is exploited by trimming the k-range of each row tile; `c_lower` skips tiles above the
 // diagonal (Gram matrix).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "trmm_tc.cuh"
@@ -33,7 +34,8 @@ namespace dsvgp {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 32;               // BK fp32 = 128 bytes = one swizzle row
-constexpr int A_BYTES = BM * BK * 4;                     // 16 KB
+constexpr int BKH = 64;                                  // fp16 variant: 64 halves = the same 128-byte row, twice the K
+constexpr int A_BYTES = BM * BK * 4;                     // 16 KB (either element type)
 constexpr int THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's CTA 0
@@ -99,6 +101,14 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {           // arrive on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -134,6 +144,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -167,9 +185,27 @@ struct Params {
   int M, N, K;
   float alpha, beta;
   int a_tri, c_lower, b_kmajor, chunk;     // chunk: k-blocks per tensor-core accumulation chain
+  // fp16 variant only: operands are x*s split into two halves; the accumulators are multiplied by *ab_inv = 1/(sA*sB)
+  // first, and the optional outputs Ch/Cl (C2h/C2l) are the two-half split of C * *c_scale (C2 * *c2_scale)
+  const float* ab_inv; const float* c_scale; const float* c2_scale;
+  __half* Ch; __half* Cl; __half* C2h; __half* C2l;
+  int64_t ldch, ldc2h;
 };
 
-template <int CG>
+// x -> (hi, lo) fp16 with hi + lo = x to 2^-22 |x| (normal range): the same 22 significand bits as the tf32 split
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ void store_half4(__half* dst, const float (&x)[4], __half* dst_lo) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_half(x[i], h[i], l[i]);
+  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(dst_lo) = *reinterpret_cast<const uint2*>(l);
+}
+
+template <int CG, bool H>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUtensorMap& mapAl, const CUtensorMap& mapBh,
                                              const CUtensorMap& mapBl, const Params& p) {
   constexpr int STAGES = Geo<CG>::STAGES, STAGE_BYTES = Geo<CG>::STAGE_BYTES, B_BYTES = Geo<CG>::B_BYTES;
@@ -190,10 +226,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
   if (p.c_lower && n0 >= m0p + BM * CG) return;                  // tile strictly above the diagonal (pair-uniform)
 
   // k-block range that can be non-zero for this (pair of) row tile(s)
-  const int nkb = (p.K + BK - 1) / BK;
+  constexpr int BKE = H ? BKH : BK;                              // elements per k-block (128 bytes either way)
+  constexpr int CB = H ? 64 : 32;                                // columns per MN-major column block (128 bytes)
+  const int nkb = (p.K + BKE - 1) / BKE;
   int kb0 = 0, kb1 = nkb;
-  if (p.a_tri == 1) kb1 = min(nkb, (m0p + BM * CG + BK - 1) / BK);   // lower: k <= row
-  if (p.a_tri == 2) kb0 = m0p / BK;                                  // upper: k >= row
+  if (p.a_tri == 1) kb1 = min(nkb, (m0p + BM * CG + BKE - 1) / BKE);  // lower: k <= row
+  if (p.a_tri == 2) kb0 = m0p / BKE;                                  // upper: k >= row
   if (gridDim.z > 1) {                                           // split-K: this CTA takes an even share of the range
     const int tot = max(kb1 - kb0, 0), per = (tot + gridDim.z - 1) / gridDim.z;
     kb0 = kb0 + blockIdx.z * per;
@@ -238,25 +276,25 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
         const int nb = n0 + (int)rank * BNL;                    // this CTA's share of the B columns
         if constexpr (CG == 1) {
           mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(st, &mapAh, &full[s], kb * BK, m0);
-          tma_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BK, m0);
+          tma_load_2d(st, &mapAh, &full[s], kb * BKE, m0);
+          tma_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BKE, m0);
           if (p.b_kmajor) {
-            tma_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BK, nb);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BK, nb);
+            tma_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BKE, nb);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BKE, nb);
           } else {
-            tma_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BK, nb / 32);
-            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BK, nb / 32);
+            tma_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BKE, nb / CB);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BKE, nb / CB);
           }
         } else {
           if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
-          tma2_load_2d(st, &mapAh, &full[s], kb * BK, m0);
-          tma2_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BK, m0);
+          tma2_load_2d(st, &mapAh, &full[s], kb * BKE, m0);
+          tma2_load_2d(st + A_BYTES, &mapAl, &full[s], kb * BKE, m0);
           if (p.b_kmajor) {
-            tma2_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BK, nb);
-            tma2_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BK, nb);
+            tma2_load_2d(st + 2 * A_BYTES, &mapBh, &full[s], kb * BKE, nb);
+            tma2_load_2d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], kb * BKE, nb);
           } else {
-            tma2_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BK, nb / 32);
-            tma2_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BK, nb / 32);
+            tma2_load_3d(st + 2 * A_BYTES, &mapBh, &full[s], 0, kb * BKE, nb / CB);
+            tma2_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, &full[s], 0, kb * BKE, nb / CB);
           }
         }
       }
@@ -265,7 +303,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32, A=B=tf32, A K-major, B per flag, N=256, M=128 (256 for a CTA pair)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+      // (kind::f16: A = B = f16 is format 0)
+      const uint32_t fmt = H ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)((BM * CG) >> 4) << 24);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES, c = i / p.chunk, buf = c & 1;
@@ -287,20 +327,34 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
           if (p.b_kmajor) {
             bh = umma_desc(st + 2 * A_BYTES + ks * 32, 16, 1024);
             bl = umma_desc(st + 2 * A_BYTES + B_BYTES + ks * 32, 16, 1024);
+          } else if constexpr (H) {
+            // B: MN-major fp16, plain 128B swizzle: 64-half column blocks BKH*128 B apart (LBO); a k-step is 16 k-rows of
+            // 128 B = two 8-row swizzle atoms 1024 B apart (SBO)
+            bh = umma_desc(st + 2 * A_BYTES + ks * 2048, BKH * 128, 1024, 2);
+            bl = umma_desc(st + 2 * A_BYTES + B_BYTES + ks * 2048, BKH * 128, 1024, 2);
           } else {
             // B: MN-major (32B-atom swizzle): 32-float column blocks BK*128 B apart (LBO); a k-step is 8 k-rows of
             // 128 B = two 4-row swizzle atoms 512 B apart (SBO)
             bh = umma_desc(st + 2 * A_BYTES + ks * 1024, BK * 128, 512, 1);
             bl = umma_desc(st + 2 * A_BYTES + B_BYTES + ks * 1024, BK * 128, 512, 1);
           }
-          if constexpr (CG == 1) {
-            umma_tf32(d_tmem, al, bh, idesc, (chunk_start && ks == 0) ? 0u : 1u);   // small terms first
+          const uint32_t first = (chunk_start && ks == 0) ? 0u : 1u;
+          if constexpr (CG == 1 && !H) {
+            umma_tf32(d_tmem, al, bh, idesc, first);   // small terms first
             umma_tf32(d_tmem, ah, bl, idesc, 1u);
             umma_tf32(d_tmem, ah, bh, idesc, 1u);
-          } else {
-            umma2_tf32(d_tmem, al, bh, idesc, (chunk_start && ks == 0) ? 0u : 1u);
+          } else if constexpr (CG == 2 && !H) {
+            umma2_tf32(d_tmem, al, bh, idesc, first);
             umma2_tf32(d_tmem, ah, bl, idesc, 1u);
             umma2_tf32(d_tmem, ah, bh, idesc, 1u);
+          } else if constexpr (CG == 1) {
+            umma_f16(d_tmem, al, bh, idesc, first);
+            umma_f16(d_tmem, ah, bl, idesc, 1u);
+            umma_f16(d_tmem, ah, bh, idesc, 1u);
+          } else {
+            umma2_f16(d_tmem, al, bh, idesc, first);
+            umma2_f16(d_tmem, ah, bl, idesc, 1u);
+            umma2_f16(d_tmem, ah, bh, idesc, 1u);
           }
         }
         const bool chunk_end = (i % p.chunk) == p.chunk - 1 || i == nk - 1;
@@ -351,57 +405,82 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
       *reinterpret_cast<float4*>(stage + lane * LDE + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     __syncwarp();
     const int col = n0 + h * 128 + lane * 4;
-    float* Cb = p.C + (int64_t)blockIdx.z * p.split_stride;
+    float* Cb = p.C ? p.C + (int64_t)blockIdx.z * p.split_stride : nullptr;
     const bool raw = gridDim.z > 1;
-    const bool al16 = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && (col + 3 < p.N) &&
-                      (!p.D || (((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0))) &&
-                      (!p.C2 || (((p.ldc2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C2) & 15) == 0) &&
-                                 ((p.ldd2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D2) & 15) == 0)));
+    auto ok16 = [](const void* q, int64_t ld) { return q == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)); };
+    const bool al16 = (col + 3 < p.N) && ok16(Cb, p.ldc) && ok16(p.D, p.ldd) && ok16(p.C2, p.ldc2) && ok16(p.D2, p.ldd2) &&
+                      ok16(p.Clo, p.ldc) && ok16(p.C2lo, p.ldc2) && ok16(p.Ch, p.ldch) && ok16(p.Cl, p.ldch) &&
+                      ok16(p.C2h, p.ldc2h) && ok16(p.C2l, p.ldc2h);
+    float inv = 1.f, cs = 1.f, c2s = 1.f;
+    if constexpr (H) {
+      if (!raw) {
+        inv = *p.ab_inv;
+        if (p.Ch) cs = *p.c_scale;
+        if (p.C2h) c2s = *p.c2_scale;
+      }
+    }
     for (int r = 0; r < 32; ++r) {
       const int row = m0 + q * 32 + r;
       if (row >= p.M) break;
       const float4 a4 = *reinterpret_cast<const float4*>(stage + r * LDE + lane * 4);
       float v[4] = {a4.x, a4.y, a4.z, a4.w};
-      float* crow = Cb + (int64_t)row * p.ldc;
-      if (raw) {
+      if (raw) {                                  // split-K partial sums: unscaled, summed by splitk_reduce_kernel
+        float* crow = Cb + (int64_t)row * p.ldc;
         if (al16) *reinterpret_cast<float4*>(crow + col) = a4;
         else
           for (int i = 0; i < 4; ++i)
             if (col + i < p.N) crow[col + i] = v[i];
         continue;
       }
-      const float* drow = p.D ? p.D + (int64_t)row * p.ldd : crow;
+      const float* drow = p.D ? p.D + (int64_t)row * p.ldd : (Cb ? Cb + (int64_t)row * p.ldc : nullptr);
+      float o[4], o2[4];
       if (al16) {
-        float4 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = p.alpha * (H ? v[i] * inv : v[i]);
         if (p.beta != 0.f) {
           const float4 d4 = *reinterpret_cast<const float4*>(drow + col);
-          o = make_float4(p.alpha * v[0] + p.beta * d4.x, p.alpha * v[1] + p.beta * d4.y, p.alpha * v[2] + p.beta * d4.z,
-                          p.alpha * v[3] + p.beta * d4.w);
-        } else {
-          o = make_float4(p.alpha * v[0], p.alpha * v[1], p.alpha * v[2], p.alpha * v[3]);
+          o[0] += p.beta * d4.x; o[1] += p.beta * d4.y; o[2] += p.beta * d4.z; o[3] += p.beta * d4.w;
         }
-        *reinterpret_cast<float4*>(crow + col) = o;
+        if (Cb) *reinterpret_cast<float4*>(Cb + (int64_t)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
         if (p.Clo)
-          *reinterpret_cast<float4*>(p.Clo + (int64_t)row * p.ldc + col) = make_float4(lo_part(o.x), lo_part(o.y), lo_part(o.z), lo_part(o.w));
-        if (p.C2) {
+          *reinterpret_cast<float4*>(p.Clo + (int64_t)row * p.ldc + col) = make_float4(lo_part(o[0]), lo_part(o[1]), lo_part(o[2]), lo_part(o[3]));
+        if constexpr (H) {
+          if (p.Ch) {
+            const float xs[4] = {o[0] * cs, o[1] * cs, o[2] * cs, o[3] * cs};
+            store_half4(p.Ch + (int64_t)row * p.ldch + col, xs, p.Cl + (int64_t)row * p.ldch + col);
+          }
+        }
+        if (p.D2) {
           const float4 e4 = *reinterpret_cast<const float4*>(p.D2 + (int64_t)row * p.ldd2 + col);
-          const float4 o2 = make_float4(o.x + e4.x, o.y + e4.y, o.z + e4.z, o.w + e4.w);
-          *reinterpret_cast<float4*>(p.C2 + (int64_t)row * p.ldc2 + col) = o2;
+          o2[0] = o[0] + e4.x; o2[1] = o[1] + e4.y; o2[2] = o[2] + e4.z; o2[3] = o[3] + e4.w;
+          if (p.C2) *reinterpret_cast<float4*>(p.C2 + (int64_t)row * p.ldc2 + col) = make_float4(o2[0], o2[1], o2[2], o2[3]);
           if (p.C2lo)
             *reinterpret_cast<float4*>(p.C2lo + (int64_t)row * p.ldc2 + col) =
-                make_float4(lo_part(o2.x), lo_part(o2.y), lo_part(o2.z), lo_part(o2.w));
+                make_float4(lo_part(o2[0]), lo_part(o2[1]), lo_part(o2[2]), lo_part(o2[3]));
+          if constexpr (H) {
+            if (p.C2h) {
+              const float xs[4] = {o2[0] * c2s, o2[1] * c2s, o2[2] * c2s, o2[3] * c2s};
+              store_half4(p.C2h + (int64_t)row * p.ldc2h + col, xs, p.C2l + (int64_t)row * p.ldc2h + col);
+            }
+          }
         }
       } else {
         for (int i = 0; i < 4; ++i) {
           if (col + i >= p.N) break;
-          float o = p.alpha * v[i];
-          if (p.beta != 0.f) o += p.beta * drow[col + i];
-          crow[col + i] = o;
-          if (p.Clo) p.Clo[(int64_t)row * p.ldc + col + i] = lo_part(o);
-          if (p.C2) {
-            const float o2 = o + p.D2[(int64_t)row * p.ldd2 + col + i];
-            p.C2[(int64_t)row * p.ldc2 + col + i] = o2;
-            if (p.C2lo) p.C2lo[(int64_t)row * p.ldc2 + col + i] = lo_part(o2);
+          float oo = p.alpha * (H ? v[i] * inv : v[i]);
+          if (p.beta != 0.f) oo += p.beta * drow[col + i];
+          if (Cb) Cb[(int64_t)row * p.ldc + col + i] = oo;
+          if (p.Clo) p.Clo[(int64_t)row * p.ldc + col + i] = lo_part(oo);
+          if constexpr (H) {
+            if (p.Ch) split_half(oo * cs, p.Ch[(int64_t)row * p.ldch + col + i], p.Cl[(int64_t)row * p.ldch + col + i]);
+          }
+          if (p.D2) {
+            const float oo2 = oo + p.D2[(int64_t)row * p.ldd2 + col + i];
+            if (p.C2) p.C2[(int64_t)row * p.ldc2 + col + i] = oo2;
+            if (p.C2lo) p.C2lo[(int64_t)row * p.ldc2 + col + i] = lo_part(oo2);
+            if constexpr (H) {
+              if (p.C2h) split_half(oo2 * c2s, p.C2h[(int64_t)row * p.ldc2h + col + i], p.C2l[(int64_t)row * p.ldc2h + col + i]);
+            }
           }
         }
       }
@@ -420,13 +499,26 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
-  gemm_tc_body<1>(mapAh, mapAl, mapBh, mapBl, p);
+  gemm_tc_body<1, false>(mapAh, mapAl, mapBh, mapBl, p);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
-  gemm_tc_body<2>(mapAh, mapAl, mapBh, mapBl, p);
+  gemm_tc_body<2, false>(mapAh, mapAl, mapBh, mapBl, p);
+}
+
+// 3xFP16 variants: the same pipeline on tcgen05 kind::f16 (twice the K per 128-byte smem row and per MMA instruction)
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tch_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  gemm_tc_body<1, true>(mapAh, mapAl, mapBh, mapBl, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tch2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  gemm_tc_body<2, true>(mapAh, mapAl, mapBh, mapBl, p);
 }
 
 __global__ void split_lo_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ lo, int64_t ldl, int rows, int cols) {
@@ -450,11 +542,12 @@ __global__ void split_lo_kernel(const float* __restrict__ x, int64_t ldx, float*
 // C = alpha * sum_z part[z] + beta * D, summed in fp64; lower != 0: only col <= row is touched
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit, int64_t stride, int64_t ldp, int M, int N,
                                      float alpha, float beta, const float* __restrict__ D, int64_t ldd, float* __restrict__ C,
-                                     int64_t ldc, int lower) {
+                                     int64_t ldc, int lower, const float* __restrict__ inv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (i >= M || j >= N || (lower && j > i)) return;
   double s = 0.0;
   for (int z = 0; z < nsplit; ++z) s += (double)part[(int64_t)z * stride + (int64_t)i * ldp + j];
+  if (inv) s *= (double)*inv;
   float o = alpha * (float)s;
   if (beta != 0.f) o += beta * (D ? D[(int64_t)i * ldd + j] : C[(int64_t)i * ldc + j]);
   C[(int64_t)i * ldc + j] = o;
@@ -512,6 +605,27 @@ static bool map_mnmajor(CUtensorMap* m, const float* base, int64_t ld, int K, in
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp16 versions: box = 64 halves (128 B) x box_rows; K x N row-major viewed as [N/64][K][64], plain 128B swizzle
+static bool map_kmajor_h(CUtensorMap* m, const __half* base, int64_t ld, int rows, int cols, int box_rows) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool map_mnmajor_h(CUtensorMap* m, const __half* base, int64_t ld, int K, int N, int box_cols) {
+  cuuint64_t gdim[3] = {64, (cuuint64_t)K, (cuuint64_t)((N + 63) / 64)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)BKH, (cuuint32_t)(box_cols / 64)};
+  cuuint32_t es[3] = {1, 1, 1};
+  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace tc
 
 static int g_tc_cta_group = 2;   // CTA pairs by default: +9% over single-CTA tiles on the C3 whitening product
@@ -558,15 +672,81 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
   if (nsplit > 1) {
     const int64_t ldp = round_up64(N, 4), stride = (int64_t)M * ldp;
     tc::Params p{split_ws, nullptr, nullptr, nullptr, nullptr, nullptr, ldp, 0, 0, 0, stride, M, N, K, 1.f, 0.f,
-                 a_tri, c_lower, b_kmajor, chunk};
+                 a_tri, c_lower, b_kmajor, chunk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
     launch(p, nsplit);
     CHECK_LAUNCH();
     dim3 rgrid(ceil_div(N, 256), M);
-    tc::splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(split_ws, nsplit, stride, ldp, M, N, alpha, beta, D, ldd, C, ldc, c_lower);
+    tc::splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(split_ws, nsplit, stride, ldp, M, N, alpha, beta, D, ldd, C, ldc, c_lower,
+                                                    nullptr);
     CHECK_LAUNCH();
     return DSVGP_OK;
   }
-  tc::Params p{C, D, C2, D2, Clo, C2lo, ldc, ldd, ldc2, ldd2, 0, M, N, K, alpha, beta, a_tri, c_lower, b_kmajor, chunk};
+  tc::Params p{C, D, C2, D2, Clo, C2lo, ldc, ldd, ldc2, ldd2, 0, M, N, K, alpha, beta, a_tri, c_lower, b_kmajor, chunk,
+               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  launch(p, 1);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
+int gemm_tch_supported(const void* A, int64_t lda, const void* B, int64_t ldb, int b_kmajor, int N) {
+  if (!tc::encode_fn()) return 0;
+  if ((lda & 7) || (ldb & 7)) return 0;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
+  if (!b_kmajor && ldb < (int64_t)((N + 63) / 64) * 64) return 0;     // the last 64-column block must stay inside the row
+  return 1;
+}
+
+int gemm_tch(const void* Ah_, const void* Al_, int64_t lda, const void* Bh_, const void* Bl_, int64_t ldb, int b_kmajor, int M,
+             int N, int K, float alpha, float beta, const float* ab_inv, float* C, int64_t ldc, const float* D, int64_t ldd,
+             float* C2, int64_t ldc2, const float* D2, int64_t ldd2, void* Ch, void* Cl, int64_t ldch, const float* c_scale,
+             void* C2h, void* C2l, int64_t ldc2h, const float* c2_scale, int a_tri, int c_lower, int chunk, int nsplit,
+             float* split_ws, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return DSVGP_OK;
+  const __half *Ah = static_cast<const __half*>(Ah_), *Al = static_cast<const __half*>(Al_);
+  const __half *Bh = static_cast<const __half*>(Bh_), *Bl = static_cast<const __half*>(Bl_);
+  if (!Ah || !Al || !Bh || !Bl || !ab_inv || K <= 0 || chunk < 1) return DSVGP_ERR_ARG;
+  if (!C && !Ch && !C2h) return DSVGP_ERR_ARG;
+  if ((C2 || C2h) && !D2) return DSVGP_ERR_ARG;
+  if ((Ch && (!Cl || !c_scale)) || (C2h && (!C2l || !c2_scale))) return DSVGP_ERR_ARG;
+  if (beta != 0.f && !D && !C) return DSVGP_ERR_ARG;
+  if (nsplit > 1 && (!split_ws || !C || C2 || Ch || C2h)) return DSVGP_ERR_ARG;
+  if (!gemm_tch_supported(Ah, lda, Bh, ldb, b_kmajor, N) || !gemm_tch_supported(Al, lda, Bl, ldb, b_kmajor, N))
+    return DSVGP_ERR_ARG;
+  const int cg = g_tc_cta_group;
+  const int bnl = tc::BN / cg;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  bool ok = tc::map_kmajor_h(&mAh, Ah, lda, M, K, tc::BM) && tc::map_kmajor_h(&mAl, Al, lda, M, K, tc::BM);
+  if (b_kmajor) ok = ok && tc::map_kmajor_h(&mBh, Bh, ldb, N, K, bnl) && tc::map_kmajor_h(&mBl, Bl, ldb, N, K, bnl);
+  else ok = ok && tc::map_mnmajor_h(&mBh, Bh, ldb, K, N, bnl) && tc::map_mnmajor_h(&mBl, Bl, ldb, K, N, bnl);
+  if (!ok) return DSVGP_ERR_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc::gemm_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<1>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::gemm_tch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess)
+      return DSVGP_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int mtiles = cg == 2 ? ((ceil_div(M, tc::BM) + 1) & ~1) : ceil_div(M, tc::BM);
+  auto launch = [&](const tc::Params& pp, int nz) {
+    dim3 grid(mtiles, ceil_div(N, tc::BN), nz);
+    if (cg == 2) tc::gemm_tch2_kernel<<<grid, tc::THREADS, tc::Geo<2>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+    else tc::gemm_tch_kernel<<<grid, tc::THREADS, tc::Geo<1>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+  };
+  if (nsplit > 1) {
+    const int64_t ldp = round_up64(N, 4), stride = (int64_t)M * ldp;
+    tc::Params p{split_ws, nullptr, nullptr, nullptr, nullptr, nullptr, ldp, 0, 0, 0, stride, M, N, K, 1.f, 0.f,
+                 a_tri, c_lower, b_kmajor, chunk, ab_inv, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    launch(p, nsplit);
+    CHECK_LAUNCH();
+    dim3 rgrid(ceil_div(N, 256), M);
+    tc::splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(split_ws, nsplit, stride, ldp, M, N, alpha, beta, D, ldd, C, ldc, c_lower,
+                                                    ab_inv);
+    CHECK_LAUNCH();
+    return DSVGP_OK;
+  }
+  tc::Params p{C, D, C2, D2, nullptr, nullptr, ldc, ldd, ldc2, ldd2, 0, M, N, K, alpha, beta, a_tri, c_lower, b_kmajor, chunk,
+               ab_inv, c_scale, c2_scale, static_cast<__half*>(Ch), static_cast<__half*>(Cl), static_cast<__half*>(C2h),
+               static_cast<__half*>(C2l), ldch, ldc2h};
   launch(p, 1);
   CHECK_LAUNCH();
   return DSVGP_OK;

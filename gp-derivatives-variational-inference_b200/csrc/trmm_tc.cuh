@@ -19,6 +19,19 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
 // nsplit > 1: split-K over gridDim.z; raw partial sums go to split_ws (nsplit * M * round_up(N,4) floats) and are
 // summed in fp64 by a second kernel (needs C2 == Clo == null).
 
+// 3xFP16 variant (tcgen05 kind::f16): operands are the two-half splits (hi, lo) of x * s with a power-of-two scale s per
+// matrix (fp16 has the 11 significand bits of tf32 but 5 exponent bits; the scale comes from an a-priori bound so that
+// nothing overflows).  Same pipeline, twice the K per shared-memory byte and per MMA instruction.  *ab_inv (device) =
+// 1 / (sA * sB).  Outputs: any of C (fp32), C2 = C + D2 (fp32), and the two-half splits Ch/Cl of C * *c_scale and
+// C2h/C2l of C2 * *c2_scale for a following product.  Leading dimensions of half arrays % 8 == 0; a K x N row-major B
+// needs ldb >= round_up(N, 64).  Pointers to half arrays are passed as void*.
+int gemm_tch_supported(const void* A, int64_t lda, const void* B, int64_t ldb, int b_kmajor, int N);
+int gemm_tch(const void* Ah, const void* Al, int64_t lda, const void* Bh, const void* Bl, int64_t ldb, int b_kmajor, int M,
+             int N, int K, float alpha, float beta, const float* ab_inv, float* C, int64_t ldc, const float* D, int64_t ldd,
+             float* C2, int64_t ldc2, const float* D2, int64_t ldd2, void* Ch, void* Cl, int64_t ldch, const float* c_scale,
+             void* C2h, void* C2l, int64_t ldc2h, const float* c2_scale, int a_tri, int c_lower, int chunk, int nsplit,
+             float* split_ws, cudaStream_t st);
+
 // 1: one CTA per 128x256 tile (tcgen05 cta_group::1); 2: CTA pairs on 256x256 tiles (cta_group::2, 2-SM TMA, multicast commit)
 void set_tc_cta_group(int cg);
 int get_tc_cta_group();

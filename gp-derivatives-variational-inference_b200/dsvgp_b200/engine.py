@@ -28,7 +28,10 @@ KZZ_JITTER = 1e-3          # add_jitter() default            DGVS.py:144
 PRED_JITTER = 1e-4         # data_data_covar.add_jitter(1e-4) DGVS.py:198,203
 CHOL_RETRY = (1e-6, 1e-5, 1e-4)   # psd_safe_cholesky(jitter=1e-6): 1e-6 * 10**i, i < 3   DGVS.py:74
 USE_TC = True      # fp32 model: run the big whitening products on tcgen05 (set False to force the mma.sync kernels)
+USE_FP16 = True    # ... as 3xFP16 (kind::f16, scaled two-half operands) instead of 3xTF32: same 22 significand bits, 1.6x faster
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
+TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
+F16 = torch.float16
 
 
 class NanError(RuntimeError):
@@ -61,9 +64,17 @@ class Factor:
         self.Wt = e(self.Mq, self.ldm, dt=dtype)[:, : self.Mq] if dtype == F32 else self.W   # W in the model dtype
         # operands of the tcgen05 products (fp32 model): explicit transposes and "lo" parts (x - trunc_tf32(x))
         self.tc = dtype == F32 and USE_TC
+        self.tch = self.tc and USE_FP16
         if self.tc:
             mk = lambda: e(self.Mq, self.ldm, dt=dtype)[:, : self.Mq]
             self.Wt_lo, self.WtT, self.WtT_lo = mk(), mk(), mk()
+        if self.tch:
+            # two-half splits of W * sW and its transpose; power-of-two scales of every operand (layout: csrc/tc_prep.cu)
+            mh = lambda: e(self.Mq, self.ldm, dt=F16)[:, : self.Mq]
+            self.Wh, self.Wl, self.WTh, self.WTl = mh(), mh(), mh(), mh()
+            self.scales = torch.ones(16, dtype=F32, device=device)
+            self.maxbits = torch.zeros(4, dtype=torch.int32, device=device)
+        self.jitter = KZZ_JITTER
         self.uzT = self.invzT = self.uz64 = self.invz64 = None
         self.valid = False
         self.owner = None          # (strategy id, parameter versions) the memoised factor belongs to
@@ -77,16 +88,26 @@ class Workspace:
         self.n, self.d, self.M, self.p, self.p2 = n, d, M, p, p2
         self.Mq, self.nq = M * (p + 1), n * (p2 + 1)
         Mq, nq = self.Mq, self.nq
-        self.ldn = _round_up(max(nq, 1), 32)       # whole 32-column TMA blocks inside every row
+        self.ldn = _round_up(max(nq, 1), 64)       # whole 32-float / 64-half column blocks (128 B, TMA) inside every row
         self.ldm = _round_up(Mq, 8)
         self.ldg = _round_up(Mq, 32)
         e = lambda *s, dt=T: torch.empty(*s, dtype=dt, device=device)
-        self.Kzx, self.A, self.B, self.Bp, self.C = (e(Mq, self.ldn) for _ in range(5))
+        self.tc = T == F32 and USE_TC and Mq >= 128 and nq >= 256
+        self.tch = self.tc and USE_FP16
+        self.Kzx, self.A, self.Bp, self.C = (e(Mq, self.ldn) for _ in range(4))
+        self.B = None if self.tch else e(Mq, self.ldn)
         sq = lambda: e(Mq, self.ldm)[:, :Mq]
         self.E, self.Hp = sq(), sq()
-        self.tc = T == F32 and USE_TC and Mq >= 128 and nq >= 256
+        if self.tch:
+            # two-half operands of the 3xFP16 products.  (Kh, Kl) holds K_zx, then B = L_s^T A, then dA; (Ah, Al) holds A
+            # from the forward pass to the Gram product; (Agh, Agl) holds A diag(g_var).
+            hb = lambda: e(Mq, self.ldn, dt=F16)[:, :nq]
+            self.Kh, self.Kl, self.Ah, self.Al, self.Agh, self.Agl = (hb() for _ in range(6))
+            sh = lambda: e(Mq, self.ldm, dt=F16)[:, :Mq]
+            self.Eh, self.El, self.ETh, self.ETl = sh(), sh(), sh(), sh()
         if self.tc:
-            self.lo1, self.lo2, self.lo3 = (e(Mq, self.ldn) for _ in range(3))   # "lo" parts of the current big operands
+            if not self.tch:
+                self.lo1, self.lo2, self.lo3 = (e(Mq, self.ldn) for _ in range(3))   # "lo" parts of the current big operands
             self.E_lo, self.ET, self.ET_lo = sq(), sq(), sq()
             sg = lambda: e(Mq, self.ldg)[:, :Mq]
             self.G_lo, self.H_lo = sg(), sg()
@@ -162,6 +183,13 @@ class Engine:
             f.uz64, f.invz64 = (f.uzT, f.invzT) if T == F64 else ops.normalize_dirs(P.Vz, F64)
 
     @staticmethod
+    def _scales0(f, P, jitter=None):
+        """3xFP16 path: power-of-two operand scales of the forward pass from hyp, the jitter and max|tril(L_s) - I|"""
+        f.maxbits.zero_()
+        ops.absmax(P.Ls_raw, f.maxbits[0:1], mode=2)
+        ops.tc_scales(f.hyp, f.jitter if jitter is None else jitter, f.maxbits, f.Mq, f.scales, 0)
+
+    @staticmethod
     def _factorise(f, P, T, extra_jitter, prep=True):
         """[hyper-parameter transforms, direction normalisation,] K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
         if prep:
@@ -170,9 +198,14 @@ class Engine:
             ops.pad_identity(f.Kzz, f.Mq)
         ops.kdir_fwd(P.Z, f.uz64, f.p, P.Z, f.uz64, f.p, f.hyp, f.Kzz, diag_add=KZZ_JITTER + extra_jitter)
         ops.cholesky_inverse(f.Kzz, f.L, f.W, f.nb0, f.nlev, f.info)
+        f.jitter = KZZ_JITTER + extra_jitter
+        if f.tch:
+            if prep:
+                Engine._scales0(f, P)
+            ops.split_half(f.W, f.scales[0:1], f.Wh, f.Wl, mode=1, hiT=f.WTh, loT=f.WTl, rows=f.Mq, cols=f.Mq)
         if T == F32:
             ops.cast2d(f.W, f.Wt, f.Mq, f.Mq, tril=True)
-            if f.tc:
+            if f.tc and not f.tch:
                 ops.split_lo(f.Wt, f.Wt_lo)
                 ops.transpose(f.Wt, f.WtT)
                 ops.split_lo(f.WtT, f.WtT_lo)
@@ -208,6 +241,12 @@ class Engine:
         operands made from L_s.  elbo_step runs this on a side stream while K_zz is being factorised."""
         Mq, nq = ws.Mq, ws.nq
         tc = ws.tc and f.tc
+        if ws.tch and f.tch:
+            # 3xFP16 path: K_zx leaves the assembly kernel only as the two-half split of K * sK (no fp32 matrix at all)
+            if not ops.kdir_fwd_half(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, ws.Kh, ws.Kl, f.scales[1:2], canon=ws.canon):
+                ops.split_half(ws.Kzx, f.scales[1:2], ws.Kh, ws.Kl, rows=Mq, cols=nq)
+            ops.split_half(P.Ls_raw, f.scales[2:3], ws.Eh, ws.El, mode=2, hiT=ws.ETh, loT=ws.ETl, rows=Mq, cols=Mq)
+            return
         have_lo = ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1 if tc else None)
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
         ops.tril_minus_eye(P.Ls_raw, ws.E)
@@ -226,6 +265,21 @@ class Engine:
         tc = ws.tc and f.tc
         if not assembled:
             Engine._assemble(ws, f, P, x, wx)
+        if ws.tch and f.tch:
+            sc, H = f.scales, TCH_CHUNK
+            ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
+                         Ch=(ws.Ah, ws.Al), c_scale=sc[3:4])                                  # A = L^-1 K_zx (+ its split)
+            if need_C:
+                ops.gemm_tch((ws.ETh, ws.ETl), (ws.Ah, ws.Al), ws.Bp, Mq, nq, Mq, sc[9:10], a_tri=TRI_UPPER, chunk=H,
+                             D2=A, C2h=(ws.Kh, ws.Kl), c2_scale=sc[4:5])                      # B' = E^T A ; split of B = A + B'
+                ops.gemm_tch((ws.Eh, ws.El), (ws.Kh, ws.Kl), C, Mq, nq, Mq, sc[10:11], a_tri=TRI_LOWER, chunk=H, beta=1.0,
+                             D=ws.Bp)                                                          # C = E B + B'
+                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C)
+            else:
+                ops.gemm_tch((ws.ETh, ws.ETl), (ws.Ah, ws.Al), ws.Bp, Mq, nq, Mq, sc[9:10], a_tri=TRI_UPPER, chunk=H)
+                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, Bp=ws.Bp)
+            ops.predict_finish(ws.pm, ws.pv, nq, ws.p2, f.hyp, ws.mu, ws.var, add_noise, PRED_JITTER)
+            return
         if tc:
             ops.gemm_tc(f.Wt, f.Wt_lo, Kzx, ws.lo1, A, Mq, nq, Mq, a_tri=TRI_LOWER, chunk=TC_CHUNK,
                         C_lo=ws.lo2)                                                     # A = L^-1 K_zx  (+ A_lo)
@@ -256,14 +310,37 @@ class Engine:
         A, Ag, C, dKzx = ws.A, ws.B, ws.C, ws.Kzx
         ops.pred_bwd_scalars(gmu, gvar, ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)
         tc = ws.tc and f.tc
-        ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t,                      # C <- dA ; Ag ; t = A gmu
-                     C_lo=ws.lo1 if tc else None, Ag_lo=ws.lo3 if tc else None)          # (+ their lo parts)
-        if tc:
+        tch = ws.tch and f.tch
+        if tch:
+            sc = f.scales
+            f.maxbits[1:4].zero_()
+            ops.absmax(P.m, f.maxbits[1:2])
+            ops.absmax(gmu, f.maxbits[2:3])
+            ops.absmax(gvar, f.maxbits[3:4])
+            ops.tc_scales(f.hyp, f.jitter, f.maxbits, Mq, sc, 1)
+            ops.dA_apply_half(A, C, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t, ws.Kh, ws.Kl, ws.Agh, ws.Agl, sc[5:6], sc[6:7])
+            ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)
+            ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
+            ops.gemm_tch((ws.Agh, ws.Agl), (ws.Ah, ws.Al), ws.G, Mq, Mq, nq, sc[12:13], b_kmajor=True, c_lower=True,
+                         chunk=TCH_CHUNK, nsplit=ws.syrk_split, split_ws=ws.split_ws)
+            ops.tril_minus_eye(P.Ls_raw, ws.E)           # fp32 operands of the two M'^3 products of the tail (3xTF32)
+            ops.split_lo(ws.E, ws.E_lo)
+            ops.transpose(ws.E, ws.ET)
+            ops.split_lo(ws.ET, ws.ET_lo)
+        else:
+            ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t,                  # C <- dA ; Ag ; t = A gmu
+                         C_lo=ws.lo1 if tc else None, Ag_lo=ws.lo3 if tc else None)      # (+ their lo parts)
+        if tch:
+            pass
+        elif tc:
             ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
         else:
             ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
-        ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
-        if tc:                                                                           # G = A diag(gvar) A^T
+        if not tch:
+            ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
+        if tch:
+            pass
+        elif tc:                                                                         # G = A diag(gvar) A^T
             # (A_lo is still in ws.lo2 from the forward pass)
             ops.gemm_tc(Ag, ws.lo3, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
                         nsplit=ws.syrk_split, split_ws=ws.split_ws)
@@ -329,6 +406,8 @@ class Engine:
         nq_global = (n_global if n_global is not None else n) * (p2 + 1)
         wx = self._data_dirs(ws, Vx, T)
         self._prep(f, P, T)
+        if f.tch:
+            self._scales0(f, P, KZZ_JITTER)
         # K_zx assembly and the L_s operands do not depend on the factor: they run on a side stream underneath the
         # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle)
         cur, side = torch.cuda.current_stream(dev), self._side_stream(dev)
@@ -336,6 +415,8 @@ class Engine:
         with torch.cuda.stream(side):
             self._assemble(ws, f, P, x, wx)
         for extra in (0.0,) + CHOL_RETRY:
+            if f.tch and extra != 0.0:
+                self._scales0(f, P, KZZ_JITTER + extra)
             self._factorise(f, P, T, extra, prep=False)
             if extra == 0.0:
                 cur.wait_stream(side)
@@ -410,6 +491,8 @@ class Engine:
             f.owner = token
         else:
             self._hyp(f, P)        # the memoised factor does not depend on the noise / mean constant; hyp[2:4] do
+            if f.tch:
+                self._scales0(f, P)
         wx = self._data_dirs(ws, Vx, T)
         self._forward(ws, f, P, x, wx, add_noise, need_C=False)
         return ws.mu.clone(), ws.var.clone()
@@ -437,6 +520,8 @@ class Engine:
             f.owner = token
         else:
             self._hyp(f, P)
+            if f.tch:
+                self._scales0(f, P)
         wx = self._data_dirs(ws, Vx, T)
         self._forward(ws, f, P, x, wx, add_noise, need_C=True)
         nq, Mq = ws.nq, ws.Mq

@@ -136,6 +136,47 @@ def set_tc_cta_group(cg):
     return call_raw("dsvgp_set_tc_cta_group", int(cg))
 
 
+def gemm_tch(A, B, C, M, N, K, ab_inv, b_kmajor=False, alpha=1.0, beta=0.0, D=None, C2=None, D2=None, Ch=None, c_scale=None,
+             C2h=None, c2_scale=None, a_tri=TRI_NONE, c_lower=False, chunk=1, nsplit=1, split_ws=None):
+    """tcgen05 3xFP16 product.  A, B, Ch, C2h are (hi, lo) pairs of float16 matrices holding the split of x * scale;
+    ab_inv / c_scale / c2_scale are 1-element float32 device tensors.  C (fp32) may be None when only Ch is wanted."""
+    ld = lambda t: _ld(t) if t is not None else 0
+    call("dsvgp_gemm_tch_f32", A[0], A[1], _ld(A[0]), B[0], B[1], _ld(B[0]), int(b_kmajor), M, N, K, float(alpha), float(beta),
+         ab_inv, C, ld(C), D, ld(D), C2, ld(C2), D2, ld(D2), Ch[0] if Ch else None, Ch[1] if Ch else None,
+         _ld(Ch[0]) if Ch else 0, c_scale, C2h[0] if C2h else None, C2h[1] if C2h else None, _ld(C2h[0]) if C2h else 0, c2_scale,
+         a_tri, int(c_lower), chunk, int(nsplit), split_ws)
+    return C
+
+
+def absmax(x, out_bits, mode=0):
+    """out_bits (uint32/int32[1] device tensor, zeroed by the caller) = max(out_bits, bits of max|x|); mode 2: tril(x) - I."""
+    x2 = x if x.dim() == 2 else x.reshape(1, -1)
+    call("dsvgp_absmax_" + suffix(x.dtype), x2, _ld(x2), x2.shape[0], x2.shape[1], mode, out_bits)
+
+
+def tc_scales(hyp, jitter, maxbits, Mq, scales, stage):
+    call("dsvgp_tc_scales_f32", hyp, float(jitter), maxbits, int(Mq), scales, int(stage))
+
+
+def split_half(src, scale, hi, lo, mode=0, hiT=None, loT=None, rows=None, cols=None):
+    call("dsvgp_split_half_" + suffix(src.dtype), src, _ld(src), src.shape[0] if rows is None else rows,
+         src.shape[1] if cols is None else cols, mode, scale, hi, lo, _ld(hi), hiT, loT, _ld(hiT) if hiT is not None else 0)
+
+
+def kdir_fwd_half(x1, u1, p1, x2, w2, p2, hyp, K, Kh, Kl, hscale, canon=None, use_os=True):
+    """K_zx assembly that writes only the two-half split of K * hscale; returns True if it did (else K was written)."""
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    cidx, flag = canon if (canon is not None and p2) else (None, None)
+    rc = call("dsvgp_kdir_fwd_half_f32", x1, u1 if p1 else None, n1, p1, x2, w2 if p2 else None, cidx, flag, n2, p2, d, hyp,
+              int(use_os), 0.0, K, _ld(K), Kh, Kl, _ld(Kh), hscale)
+    return rc == 2
+
+
+def dA_apply_half(A, C, rows, nq, m, gmu, gvar, tp, t, dAh, dAl, Agh, Agl, s_dA, s_Ag):
+    call("dsvgp_dA_half_f32", A, C, _ld(A), rows, nq, m, gmu, gvar, tp, tp.shape[0], t, dAh, dAl, Agh, Agl, _ld(dAh), s_dA, s_Ag)
+
+
 def set_kdir_fwd_knobs(tib=-1, stream_stores=-1):
     """benchmarking knobs of the fp32 assembly kernel (row points per CTA, evict-first stores)."""
     return call_raw("dsvgp_set_kdir_fwd_knobs", int(tib), int(stream_stores))

@@ -123,6 +123,33 @@ int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const doub
  * meet the TMA constraints (otherwise use dsvgp_gemm_f32). */
 int dsvgp_gemm_tc_supported_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kmajor, int N);
 int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, int a_tri, int c_lower, int chunk, float* Clo, float* C2lo, int nsplit, float* split_ws, dsvgp_stream_t s);
+/* 3xFP16 variant of dsvgp_gemm_tc_f32 (tcgen05 kind::f16, twice the tensor throughput of kind::tf32): every operand is
+ * the two-half split (hi, lo: fp16 arrays, passed as void*) of x * s with a power-of-two scale s per matrix chosen from an
+ * a-priori bound (dsvgp_tc_scales_f32) so that fp16's 5-bit exponent never overflows; hi + lo carry the same 22
+ * significand bits as the tf32 split.  ab_inv (device float) = 1/(sA*sB).  Outputs, each optional: C (fp32),
+ * C2 = C + D2 (fp32), Ch/Cl = split of C * *c_scale, C2h/C2l = split of C2 * *c2_scale.  Half leading dimensions % 8 == 0;
+ * a K x N row-major B needs ldb >= round_up(N, 64). */
+int dsvgp_gemm_tch_supported_f32(const void* A, int64_t lda, const void* B, int64_t ldb, int b_kmajor, int N);
+int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* Bh, const void* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, const float* ab_inv, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, void* Ch, void* Cl, int64_t ldch, const float* c_scale, void* C2h, void* C2l, int64_t ldc2h, const float* c2_scale, int a_tri, int c_lower, int chunk, int nsplit, float* split_ws, dsvgp_stream_t s);
+/* Operand preparation for dsvgp_gemm_tch_f32.
+ * dsvgp_absmax_*: *out_bits = max(*out_bits, max|x_ij|) as the bit pattern of a non-negative float (zero it first; NaN
+ *   gives +inf); mode 0: all entries, 2: the entries of tril(x) - I.
+ * dsvgp_tc_scales_f32: power-of-two scales (device float[16]) of every operand of a step from rigorous a-priori bounds
+ *   (list in csrc/tc_prep.cu): [0] W [1] K_zx [2] E [3] A [4] B [5] dA [6] A_g, [8..12] the reciprocal products
+ *   1/(sW sK), 1/(sE sA), 1/(sE sB), 1/(sW sdA), 1/(sAg sA).  maxbits (device uint[4]) = absmax bits of E, m, g_mu, g_var.
+ *   stage 0 fills what the forward pass needs (hyp, jitter, maxbits[0]), stage 1 the rest.
+ * dsvgp_split_half_*: (hi, lo) = two-half split of op(src) * *scale, optionally also of its transpose (hiT, loT);
+ *   mode 0: src, 1: tril(src), 2: tril(src) - I.
+ * dsvgp_kdir_fwd_half_f32: dsvgp_kdir_fwd_canon_f32 that writes ONLY the split (Kh, Kl) of K * *hscale; returns 2 when
+ *   it did, otherwise K (fp32) was written instead (shape not taken by the vectorised kernel) and 0 is returned.
+ * dsvgp_dA_half_f32: dsvgp_dA_f32 whose outputs are only the splits of dA * *s_dA and A_g * *s_Ag (C is not modified). */
+int dsvgp_absmax_f32(const float* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s);
+int dsvgp_absmax_f64(const double* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s);
+int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* maxbits, int Mq, float* scales, int stage, dsvgp_stream_t s);
+int dsvgp_split_half_f32(const float* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s);
+int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s);
+int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s);
+int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s);
 /* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles
  * (cta_group::2: each CTA stages half of the operands, 2-SM TMA loads, multicast commits).  Returns the value in force. */
 int dsvgp_set_tc_cta_group(int cg);

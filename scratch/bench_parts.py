@@ -72,7 +72,10 @@ if dtype == torch.float32 and p2:
         for ss in (0, 1):
             ops.set_kdir_fwd_knobs(tib, ss)
             res[f"asm_k_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx, canon=ws.canon), 20)
-            res[f"asm_klo_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1), 20)
+            if getattr(ws, "tch", False):
+                res[f"asm_half_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd_half(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx, ws.Kh, ws.Kl, f.scales[1:2], canon=ws.canon), 20)
+            else:
+                res[f"asm_klo_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1), 20)
             res[f"asm_gen_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx), 20)
     ops.set_kdir_fwd_knobs(64, 0)
 res["asm_bytes"] = 4 * (Mq * nq + (M + n) * d + (M * p + n * p2) * d)
