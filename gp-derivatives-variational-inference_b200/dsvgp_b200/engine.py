@@ -310,19 +310,20 @@ class Engine:
         A, Ag, C, dKzx = ws.A, ws.B, ws.C, ws.Kzx
         ops.pred_bwd_scalars(gmu, gvar, ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)
         tc = ws.tc and f.tc
-        tch = ws.tch and f.tch
-        if tch:
+        if ws.tch and f.tch:
+            # 3xFP16: scales of dA and A_g from max|m|, max|g_mu|, max|g_var| (order-independent maxima: deterministic)
             sc = f.scales
             f.maxbits[1:4].zero_()
             ops.absmax(P.m, f.maxbits[1:2])
             ops.absmax(gmu, f.maxbits[2:3])
             ops.absmax(gvar, f.maxbits[3:4])
             ops.tc_scales(f.hyp, f.jitter, f.maxbits, Mq, sc, 1)
+            # dA = m g_mu^T + 2 C diag(g_var) and A_g = A diag(g_var) leave only as two-half splits; t = A g_mu
             ops.dA_apply_half(A, C, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t, ws.Kh, ws.Kl, ws.Agh, ws.Agl, sc[5:6], sc[6:7])
-            ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)
+            ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             ops.gemm_tch((ws.Agh, ws.Agl), (ws.Ah, ws.Al), ws.G, Mq, Mq, nq, sc[12:13], b_kmajor=True, c_lower=True,
-                         chunk=TCH_CHUNK, nsplit=ws.syrk_split, split_ws=ws.split_ws)
+                         chunk=TCH_CHUNK, nsplit=ws.syrk_split, split_ws=ws.split_ws)                                     # G = A_g A^T
             ops.tril_minus_eye(P.Ls_raw, ws.E)           # fp32 operands of the two M'^3 products of the tail (3xTF32)
             ops.split_lo(ws.E, ws.E_lo)
             ops.transpose(ws.E, ws.ET)
@@ -330,22 +331,17 @@ class Engine:
         else:
             ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t,                  # C <- dA ; Ag ; t = A gmu
                          C_lo=ws.lo1 if tc else None, Ag_lo=ws.lo3 if tc else None)      # (+ their lo parts)
-        if tch:
-            pass
-        elif tc:
-            ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
-        else:
-            ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
-        if not tch:
+            if tc:
+                ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
+            else:
+                ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
-        if tch:
-            pass
-        elif tc:                                                                         # G = A diag(gvar) A^T
-            # (A_lo is still in ws.lo2 from the forward pass)
-            ops.gemm_tc(Ag, ws.lo3, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
-                        nsplit=ws.syrk_split, split_ws=ws.split_ws)
-        else:
-            ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)
+            if tc:                                                                       # G = A diag(gvar) A^T
+                # (A_lo is still in ws.lo2 from the forward pass)
+                ops.gemm_tc(Ag, ws.lo3, A, ws.lo2, ws.G, Mq, Mq, nq, b_kmajor=True, c_lower=True, chunk=TC_CHUNK,
+                            nsplit=ws.syrk_split, split_ws=ws.split_ws)
+            else:
+                ops.gemm(Ag, A, ws.G, tb=True, c_tri=1, M=Mq, N=Mq, K=nq)
         ops.mirror_lower(ws.G, Mq)
         if self.reduce_hook is not None:
             self.reduce_hook(ws.big, ws.small)

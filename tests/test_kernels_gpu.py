@@ -362,3 +362,96 @@ def test_elbo_terms_kl_and_small_kernels(ops, dtype):
     dst = torch.empty(50, 50, dtype=F32 if dtype == F64 else F64, device="cuda")
     ops.cast2d(d(Y), dst, tril=True)
     assert rel(dst, Y.tril()) < 1e-6
+
+
+# ------------------------------------------------------------------------- 3xFP16 tensor-core product and its operands
+def _split_ref(x, s):
+    xs = x.float() * s
+    hi = xs.half()
+    return hi, (xs - hi.float()).half()
+
+
+def _padded(t, ld):
+    out = torch.zeros(t.shape[0], ld, device=t.device, dtype=t.dtype)
+    out[:, :t.shape[1]] = t
+    return out[:, :t.shape[1]]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K,kw", [
+    (128, 256, 64, {}), (200, 300, 100, {}), (384, 1000, 384, dict(a_tri=1)), (384, 1000, 384, dict(a_tri=2)),
+    (384, 1000, 384, dict(a_tri=1, alpha=2.0, beta=-2.0, dual=True)), (300, 300, 1000, dict(b_kmajor=True)),
+    (512, 512, 2048, dict(b_kmajor=True, c_lower=True)), (512, 512, 8192, dict(b_kmajor=True, c_lower=True, nsplit=4)),
+    (256, 700, 512, dict(chunk=2))])
+def test_gemm_tch_matches_fp64(ops, cg, M, N, K, kw):
+    """tcgen05 kind::f16 x3 on scaled two-half operands against an fp64 product of the SAME quantised operands (so the
+    tolerance measures the kernel: fp32 accumulation + the dropped lo*lo term), every epilogue output included."""
+    F16 = torch.float16
+    b_kmajor, a_tri, c_lower = kw.get("b_kmajor", False), kw.get("a_tri", 0), kw.get("c_lower", False)
+    alpha, beta, dual, nsplit, chunk = kw.get("alpha", 1.0), kw.get("beta", 0.0), kw.get("dual", False), kw.get("nsplit", 1), kw.get("chunk", 1)
+    prev = ops.set_tc_cta_group(cg)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(M + N + K)
+        A = torch.randn(M, K, device="cuda", dtype=F64, generator=g)
+        A = A.tril() if a_tri == 1 else A.triu() if a_tri == 2 else A
+        B = torch.randn((N, K) if b_kmajor else (K, N), device="cuda", dtype=F64, generator=g)
+        sA, sB = 2.0 ** 11, 2.0 ** 12
+        lda, ldn = (K + 7) // 8 * 8, (N + 63) // 64 * 64
+        Ah, Al = (_padded(t, lda) for t in _split_ref(A, sA))
+        Bh, Bl = (_padded(t, lda if b_kmajor else ldn) for t in _split_ref(B, sB))
+        D, D2 = (_padded(torch.randn(M, N, device="cuda", dtype=F32, generator=g), ldn) for _ in range(2))
+        C, C2 = (_padded(torch.full((M, N), float("nan"), device="cuda", dtype=F32), ldn) for _ in range(2))
+        Ch, C2h = (tuple(_padded(torch.zeros(M, N, device="cuda", dtype=F16), ldn) for _ in range(2)) for _ in range(2))
+        inv = torch.tensor([1.0 / (sA * sB)], device="cuda", dtype=F32)
+        cs, c2s = torch.tensor([8.0], device="cuda"), torch.tensor([4.0], device="cuda")
+        Aq, Bq = (Ah.double() + Al.double()) / sA, (Bh.double() + Bl.double()) / sB
+        ref = alpha * (Aq @ (Bq.T if b_kmajor else Bq)) + beta * D.double()
+        ws = torch.empty(nsplit * M * ((N + 3) // 4 * 4), device="cuda") if nsplit > 1 else None
+        ops.gemm_tch((Ah, Al), (Bh, Bl), C, M, N, K, inv, b_kmajor=b_kmajor, alpha=alpha, beta=beta, D=D if beta else None,
+                     C2=C2 if dual else None, D2=D2 if dual else None, Ch=Ch if dual else None, c_scale=cs,
+                     C2h=C2h if dual else None, c2_scale=c2s, a_tri=a_tri, c_lower=c_lower, chunk=chunk, nsplit=nsplit, split_ws=ws)
+        assert (rel(C.tril(), ref.tril()) if c_lower else rel(C, ref)) < 2e-6
+        if dual:
+            assert rel(C2, ref + D2.double()) < 2e-6
+            assert rel((Ch[0].double() + Ch[1].double()) / 8.0, ref) < 2e-6
+            assert rel((C2h[0].double() + C2h[1].double()) / 4.0, ref + D2.double()) < 2e-6
+    finally:
+        ops.set_tc_cta_group(prev)
+
+
+def test_tc_operand_scales_and_splits(ops):
+    """absmax (order-independent), power-of-two scales from the a-priori bounds, and the two-half split kernels."""
+    F16 = torch.float16
+    g = torch.Generator().manual_seed(5)
+    n = 150
+    Ls = (torch.eye(n) + 0.02 * torch.randn(n, n, generator=g)).cuda()
+    bits = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ops.absmax(Ls, bits[0:1], mode=2)
+    E = Ls.tril() - torch.eye(n, device="cuda")
+    assert float(bits[0:1].view(torch.float32)) == float(E.abs().max())
+    v = torch.randn(1000, generator=g).cuda()
+    ops.absmax(v, bits[1:2])
+    assert float(bits[1:2].view(torch.float32)) == float(v.abs().max())
+    hyp = torch.tensor([0.5, 1.7, 0.3, 0.0, 0, 0, 0, 0], dtype=F64, device="cuda")
+    sc = torch.zeros(16, device="cuda")
+    ops.tc_scales(hyp, 1e-3, bits, n, sc, 0)
+    s = sc.cpu()
+    for k in (0, 1, 2, 3, 4):
+        assert float(torch.log2(s[k])) == round(float(torch.log2(s[k])))                 # exact powers of two
+    a = (1.7 * 4.0) ** 0.5
+    assert 1.7 * 8.0 * float(s[1]) <= 2.0 ** 15 < 1.7 * 8.0 * 2.2 * float(s[1])          # K bound os*2/ell^2 -> (2^14, 2^15]
+    assert a * float(s[3]) <= 2.0 ** 15 and 1e-3 ** -0.5 * float(s[0]) <= 2.0 ** 15
+    assert float(E.abs().max()) * float(s[2]) <= 2.0 ** 15
+    assert abs(float(s[8]) * float(s[0]) * float(s[1]) - 1.0) < 1e-6
+    # split of tril(Ls) - I and of its transpose
+    mk = lambda: torch.zeros(n, 152, dtype=F16, device="cuda")[:, :n]
+    hi, lo, hiT, loT = mk(), mk(), mk(), mk()
+    ops.split_half(Ls, sc[2:3], hi, lo, mode=2, hiT=hiT, loT=loT)
+    back = (hi.double() + lo.double()) / float(s[2])
+    assert rel(back, E) < 2.0 ** -21 and float(back.triu(1).abs().max()) == 0
+    assert torch.equal(hiT, hi.T) and torch.equal(loT, lo.T)
+    W = torch.randn(70, 70, generator=g, dtype=F64).cuda()
+    mk2 = lambda: torch.zeros(70, 72, dtype=F16, device="cuda")[:, :70]
+    wh, wl = mk2(), mk2()
+    ops.split_half(W, sc[0:1], wh, wl, mode=1)
+    assert rel((wh.double() + wl.double()) / float(s[0]), W.tril()) < 2.0 ** -21
