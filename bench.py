@@ -179,7 +179,24 @@ def build_model(wl, dtype, device):
     return model, lik
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner, ...)
+    has been diverted to stderr by _guard_stdout()."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -205,7 +222,7 @@ def main():
         cb = cpu_reference_arm(wl, args.steps, args.warmup)
         config["n_per_gpu"] = config["global_batch"] = wl["n_ref"]
         config["parallelism"] = "cpu"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
+        _emit(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"],
                           "data": "synthetic", "config": config,
@@ -372,7 +389,7 @@ def main():
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 if __name__ == "__main__":
