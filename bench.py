@@ -214,7 +214,11 @@ def main():
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     config = {"workload": f"{args.workload} {wl['desc']}: d={wl['d']} M={wl['M']} p={wl['p']} M'={wl['M'] * (wl['p'] + 1)} "
                           f"{wl['dtype']} N={wl['N']}", "n_per_gpu": wl["n"], "global_batch": wl["n"] * world,
-              "variant": wl["variant"], "parallelism": f"dp{world}", "l2_policy": "inputs_exceed_l2"}
+              "variant": wl["variant"], "parallelism": f"dp{world}", "l2_policy": "inputs_exceed_l2",
+              "arithmetic": ("fp64 throughout (DMMA)" if wl["dtype"] == "f64" else
+                             "fp32 model; K_zz / Cholesky / Cholesky-backward in fp64; whitening products on tensor cores as 3xFP16 "
+                             "(two-half operands = 22 significand bits, fp32 accumulation in chains of K=64, fp32 master sums): "
+                             "fp32-grade, parity-tested at 1e-4 against the fp64 oracle")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -222,6 +226,7 @@ def main():
         cb = cpu_reference_arm(wl, args.steps, args.warmup)
         config["n_per_gpu"] = config["global_batch"] = wl["n_ref"]
         config["parallelism"] = "cpu"
+        config["arithmetic"] = "torch CPU ops in the model dtype, fp64 Cholesky and triangular solves (as the reference, DGVS.py:74,181,183)"
         _emit(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"],
