@@ -194,29 +194,49 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
       double a[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = Ls[(k0 + r) * ld + k0 + c];
+      // Two pivots per step: with det = a11 a22 - a21^2 the second pivot is d2 = det / a11, so rsqrt(a11) and rsqrt(det)
+      // are two INDEPENDENT chains (they overlap in the fp64 pipe) and 1/l22 = rsqrt(det) * l11 -- the sequential
+      // pivot chain, a third of this kernel's time, has 4 links per 8x8 block instead of 8.  det has the same
+      // cancellation as d2 = a22 - l21^2 (both lose log2(cond of the 2x2 block) bits).
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double d = __shfl_sync(0xffffffffu, a[k], k);
-        double ljj, rinv;
-        if (!(d > 0.0)) {                              // also catches NaN
-          if (lane == 0) atomicCAS(info, 0, row_offset + k0 + k + 1);
-          ljj = rinv = nan("");
-        } else if (d > 1e-30 && d < 1e30) {
-          rsqrt_sqrt_f64(d, rinv, ljj);
+      for (int k = 0; k < 8; k += 2) {
+        const double a11 = __shfl_sync(0xffffffffu, a[k], k);
+        const double a21 = __shfl_sync(0xffffffffu, a[k], k + 1);
+        const double a22 = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+        const double det = fma(a11, a22, -(a21 * a21));
+        const bool ok1 = a11 > 0.0, ok2 = ok1 && det > 0.0;          // also false for NaN
+        double l11, r1, sdet, rdet;
+        if (ok2 && a11 > 1e-30 && a11 < 1e30 && det > 1e-30 && det < 1e30) {
+          rsqrt_sqrt_f64(a11, r1, l11);
+          rsqrt_sqrt_f64(det, rdet, sdet);
+        } else if (ok2) {
+          l11 = sqrt(a11);
+          r1 = 1.0 / l11;
+          sdet = sqrt(det);
+          rdet = 1.0 / sdet;
         } else {
-          ljj = sqrt(d);
-          rinv = 1.0 / ljj;
+          if (lane == 0) atomicCAS(info, 0, row_offset + k0 + k + (ok1 ? 2 : 1));
+          l11 = r1 = sdet = rdet = nan("");
         }
+        const double l21 = a21 * r1;
+        const double r2 = rdet * l11;                                // 1 / l22
+        const double l22 = sdet * r1;                                // sqrt(det / a11)
         if (r == k) {
-          a[k] = ljj;
-          if (lane < 8) rdg[k0 + k] = rinv;
-        } else if (r > k) {
-          a[k] = a[k] * rinv;
+          a[k] = l11;
+        } else if (r == k + 1) {
+          a[k] = l21;
+          a[k + 1] = l22;
+        } else if (r > k + 1) {
+          a[k] = a[k] * r1;
+          a[k + 1] = (a[k + 1] - a[k] * l21) * r2;
         }
+        if (lane == k) rdg[k0 + k] = r1;
+        if (lane == k + 1) rdg[k0 + k + 1] = r2;
 #pragma unroll
-        for (int c = k + 1; c < 8; ++c) {
+        for (int c = k + 2; c < 8; ++c) {
           const double lck = __shfl_sync(0xffffffffu, a[k], c);
-          if (r >= c) a[c] -= a[k] * lck;
+          const double lck1 = __shfl_sync(0xffffffffu, a[k + 1], c);
+          if (r >= c) a[c] = fma(-a[k + 1], lck1, fma(-a[k], lck, a[c]));
         }
       }
       if (lane < 8) {
