@@ -186,10 +186,12 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
     __syncthreads();
     for (int i = nb + tid; i < nbp; i += POTRF_THREADS) Ls[i * ld + i] = 1.0;      // identity on the padding
   }
-  // ------------------------------------------------------------------------------------------------ factor
-  for (int k0 = 0; k0 < nbp; k0 += 8) {
-    __syncthreads();
-    if (warp == 0) {                                   // (A) lanes r = lane & 7 hold row r of the diagonal block
+  // ------------------------------------------------------------------------------- factor + inverse, pipelined
+  // The sequential pivot chain (A) runs on warp 0 only; instead of leaving the other 15 warps idle, block k+1's chain is
+  // started as soon as its 8 columns are up to date ("thin" update), and the rest of step k's rank-8 update (C) plus the
+  // inversion of block row k run beside it on warps 1-15 (their own named barrier).  Per 8 columns: thin | (A)(k+1) ||
+  // (C)(k) + inverse row k | (B)(k+1), three block barriers as before, and no separate inverse phase afterwards.
+  auto factor_diag = [&](int k0) {                     // (A) lanes r = lane & 7 hold row r of the diagonal block
       const int r = lane & 7;
       double a[8];
 #pragma unroll
@@ -244,9 +246,9 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
         for (int c = 0; c < 8; ++c)
           if (c <= r) Ls[(k0 + r) * ld + k0 + c] = a[c];
       }
-    }
-    __syncthreads();
-    for (int i = k0 + 8 + tid; i < nbp; i += POTRF_THREADS) {      // (B) panel: x L11^T = a
+  };
+  auto panel_solve = [&](int k0) {                     // (B) rows below the diagonal block: x L11^T = a
+    for (int i = k0 + 8 + tid; i < nbp; i += POTRF_THREADS) {
       double x[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) x[c] = Ls[i * ld + k0 + c];
@@ -260,52 +262,65 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
 #pragma unroll
       for (int c = 0; c < 8; ++c) Ls[i * ld + k0 + c] = x[c];
     }
-    __syncthreads();
-    const int t0 = k0 + 8;                                         // (C) rank-8 trailing update
-    for (int i = t0 + ty; i < nbp; i += 16) {
-      double li[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) li[q] = Ls[i * ld + k0 + q];
-      for (int c = t0 + tx; c <= i; c += 32) {
+  };
+  __syncthreads();
+  if (warp == 0) factor_diag(0);
+  __syncthreads();
+  panel_solve(0);
+  __syncthreads();
+  for (int k0 = 0; k0 < nbp; k0 += 8) {
+    const int t0 = k0 + 8;
+    // thin: rank-8 update of block column [t0, t0+8) only (all that (A) and (B) of the next step read)
+    for (int e = tid; e < (nbp - t0) * 8; e += POTRF_THREADS) {
+      const int i = t0 + (e >> 3), c = t0 + (e & 7);
+      if (c <= i) {
         double sacc = Ls[i * ld + c];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sacc -= li[q] * Ls[c * ld + k0 + q];
+        for (int q = 0; q < 8; ++q) sacc -= Ls[i * ld + k0 + q] * Ls[c * ld + k0 + q];
         Ls[i * ld + c] = sacc;
       }
     }
-  }
-  // ----------------------------------------------------------------------------------------------- inverse
-  __syncthreads();
-  if (tid < nbp) {                                     // D = inv(L[I,I]) for every 8x8 diagonal block: thread = column
-    const int I0 = tid & ~7, j = tid & 7;
-    double x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      double sacc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < i; ++k)
-        if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
-      x[i] = (i >= j) ? sacc * rdg[I0 + i] : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
-  }
-  for (int I0 = 0; I0 < nbp; I0 += 8) {
     __syncthreads();
-    {                                                  // T[r][c] -> Ws[I0+r][c], c < I0
-      const int r = tid & 7;
-      for (int c = tid >> 3; c < I0; c += POTRF_THREADS / 8) {
+    if (warp == 0) {
+      if (t0 < nbp) factor_diag(t0);
+    } else {
+      // (C) rest of the rank-8 update of step k0: rows >= t0 + 8, columns [t0 + 8, i]
+      for (int i = t0 + 8 + (warp - 1); i < nbp; i += 15) {
+        double li[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) li[q] = Ls[i * ld + k0 + q];
+        for (int c = t0 + 8 + lane; c <= i; c += 32) {
+          double sacc = Ls[i * ld + c];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sacc -= li[q] * Ls[c * ld + k0 + q];
+          Ls[i * ld + c] = sacc;
+        }
+      }
+      // inverse, block row I0 = k0:  D = inv(L[I,I]),  T = L[I,0:I] * W[0:I,0:I],  W[I,0:I] = -D * T,  W[I,I] = D
+      const int I0 = k0, u = tid - 32, r = u & 7;      // u: 0..479
+      if (u < 8) {                                     // D: thread = column j of the 8x8 inverse
+        const int j = u;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < i; ++k)
+            if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
+          x[i] = (i >= j) ? sacc * rdg[I0 + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
+      }
+      for (int c = u >> 3; c < I0; c += 60) {          // T[r][c] -> Ws[I0+r][c], c < I0
         double sacc = 0.0;
         for (int k = c & ~7; k < I0; ++k) sacc += Ls[(I0 + r) * ld + k] * Ws[k * ld + c];
         Ws[(I0 + r) * ld + c] = sacc;
       }
-    }
-    __syncthreads();
-    {                                                  // W[I0+r][c] = -sum_{q<=r} D[r][q] T[q][c]  (in place, per 8-lane group)
-      const int r = tid & 7;
-      for (int c0 = 0; c0 < I0; c0 += POTRF_THREADS / 8) {
-        const int c = c0 + (tid >> 3);
+      asm volatile("bar.sync 1, 480;" ::: "memory");  // warps 1-15 only: D and T complete
+      for (int c0 = 0; c0 < I0; c0 += 60) {            // W[I0+r][c] = -sum_{q<=r} D[r][q] T[q][c]  (in place, per 8-lane group)
+        const int c = c0 + (u >> 3);
         double t[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) t[q] = (c < I0) ? Ws[(I0 + q) * ld + c] : 0.0;
@@ -320,6 +335,9 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
         __syncwarp();
       }
     }
+    __syncthreads();
+    if (t0 < nbp) panel_solve(t0);
+    __syncthreads();
   }
   __syncthreads();
   for (int i = ty; i < nb; i += 16)
