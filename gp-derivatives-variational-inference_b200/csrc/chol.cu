@@ -300,23 +300,29 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
       const int I0 = k0, u = tid - 32, r = u & 7;      // u: 0..479
       if (u < 8) {                                     // D: thread = column j of the 8x8 inverse
         const int j = u;
-        double x[8];
+        double x[8], acc[8];                           // right-looking substitution: 8 x (mul + fma) on the critical path
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          double sacc = (i == j) ? 1.0 : 0.0;
+        for (int i = 0; i < 8; ++i) acc[i] = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-          for (int k = 0; k < i; ++k)
-            if (k >= j) sacc -= Ls[(I0 + i) * ld + I0 + k] * x[k];
-          x[i] = (i >= j) ? sacc * rdg[I0 + i] : 0.0;
+        for (int k = 0; k < 8; ++k) {
+          x[k] = (k >= j) ? acc[k] * rdg[I0 + k] : 0.0;
+#pragma unroll
+          for (int i = k + 1; i < 8; ++i) acc[i] = fma(-Ls[(I0 + i) * ld + I0 + k], x[k], acc[i]);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (i >= j) Ws[(I0 + i) * ld + I0 + j] = x[i];
       }
       for (int c = u >> 3; c < I0; c += 60) {          // T[r][c] -> Ws[I0+r][c], c < I0
-        double sacc = 0.0;
-        for (int k = c & ~7; k < I0; ++k) sacc += Ls[(I0 + r) * ld + k] * Ws[k * ld + c];
-        Ws[(I0 + r) * ld + c] = sacc;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // 4 independent chains (the range is a multiple of 8)
+        const double* lrow = Ls + (I0 + r) * ld;
+        for (int k = c & ~7; k < I0; k += 4) {
+          s0 = fma(lrow[k], Ws[k * ld + c], s0);
+          s1 = fma(lrow[k + 1], Ws[(k + 1) * ld + c], s1);
+          s2 = fma(lrow[k + 2], Ws[(k + 2) * ld + c], s2);
+          s3 = fma(lrow[k + 3], Ws[(k + 3) * ld + c], s3);
+        }
+        Ws[(I0 + r) * ld + c] = (s0 + s1) + (s2 + s3);
       }
       asm volatile("bar.sync 1, 480;" ::: "memory");  // warps 1-15 only: D and T complete
       for (int c0 = 0; c0 < I0; c0 += 60) {            // W[I0+r][c] = -sum_{q<=r} D[r][q] T[q][c]  (in place, per 8-lane group)
