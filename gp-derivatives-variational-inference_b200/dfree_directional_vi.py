@@ -25,8 +25,8 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
              verbose=True, **args):
     """reference dfree_directional_vi.py:93-257.  num_data = (dim+1)*N as in the reference (:130, quirk Q4)."""
     assert num_directions == minibatch_dim
-    if use_ngd or use_ciq:
-        raise NotImplementedError("use_ngd / use_ciq are outside the B200 hot path")
+    if use_ciq:
+        raise NotImplementedError("use_ciq (contour-integral-quadrature whitening) is outside the B200 hot path")
     device = _dvi._require_cuda()
     dim = len(train_dataset[0][0])
     n_samples = len(train_dataset)
@@ -34,14 +34,16 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
     inducing_points, inducing_directions = _dvi._initial_inducing(train_dataset, num_inducing, num_directions, dim,
                                                                   inducing_data_initialization)
     dtype = train_dataset[0][0].dtype
-    model = GPModel(inducing_points.to(dtype), inducing_directions.to(dtype), dim).to(device=device, dtype=dtype)
+    model = GPModel(inducing_points.to(dtype), inducing_directions.to(dtype), dim,
+                    **({"variational_distribution": "NGD"} if use_ngd else {})).to(device=device, dtype=dtype)
     likelihood = gp.GaussianLikelihood().to(device=device, dtype=dtype)
     model.train()
     likelihood.train()
     if verbose:
         count_params(model, likelihood)
     vopt, hopt, vsched, hsched = _dvi._optimizers(model, likelihood, learning_rate_hypers, lr_sched, n_samples,
-                                                  minibatch_size, num_epochs, gamma)
+                                                  minibatch_size, num_epochs, gamma,
+                                                  ngd=dict(num_data=num_data, lr=learning_rate_ngd) if use_ngd else None)
     mll_cls = {"ELBO": gp.VariationalELBO, "PLL": gp.PredictiveLogLikelihood}[mll_type]
     mll = mll_cls(likelihood, model, num_data=num_data)
     total_step, loss = 0, None

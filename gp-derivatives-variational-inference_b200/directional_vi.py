@@ -5,7 +5,8 @@ B200 engine.  The minibatch loop is host Python exactly as in the reference; eac
 Differences that are deliberate and visible:
   * a CUDA device is required (no CPU path); tensors of a TensorDataset are moved to the GPU once and minibatches
     are sliced there instead of going through a per-sample DataLoader (other Dataset types still use DataLoader);
-  * use_ngd / use_ciq (NaturalVariationalDistribution, CIQ strategy) are outside the hot path -> NotImplementedError.
+  * use_ciq (the contour-integral-quadrature strategy) is outside the hot path -> NotImplementedError; use_ngd
+    (NaturalVariationalDistribution + NGD) is supported.
 """
 import random
 import sys
@@ -29,9 +30,11 @@ class GPModel(gp.ApproximateGP):
     def __init__(self, inducing_points, inducing_directions, dim, learn_inducing_locations=True, **kwargs):
         self.num_inducing = len(inducing_points)
         self.num_directions = int(len(inducing_directions) / self.num_inducing)
-        if kwargs.get("variational_distribution") == "NGD" or kwargs.get("variational_strategy") == "CIQ":
-            raise NotImplementedError("NGD / CIQ variants are outside the B200 hot path (SURVEY.md section 2, rows 7 and 8f)")
-        variational_distribution = gp.CholeskyVariationalDistribution(self.num_inducing * (self.num_directions + 1))
+        if kwargs.get("variational_strategy") == "CIQ":
+            raise NotImplementedError("the CIQ strategy is outside the B200 hot path (SURVEY.md section 2, row 7)")
+        vd_class = gp.NaturalVariationalDistribution if kwargs.get("variational_distribution") == "NGD" \
+            else gp.CholeskyVariationalDistribution                                     # reference :38-43
+        variational_distribution = vd_class(self.num_inducing * (self.num_directions + 1))
         variational_strategy = self.strategy_class(self, inducing_points, inducing_directions, variational_distribution,
                                                    learn_inducing_locations=learn_inducing_locations)
         super().__init__(variational_strategy)
@@ -101,11 +104,14 @@ def _initial_inducing(train_dataset, num_inducing, num_directions, dim, inducing
     return inducing_points, inducing_directions
 
 
-def _optimizers(model, likelihood, lr, lr_sched, n_samples, minibatch_size, num_epochs, gamma):
-    # same two optimisers and parameter groups as the reference (:192-199); each step() is one fused launch
+def _optimizers(model, likelihood, lr, lr_sched, n_samples, minibatch_size, num_epochs, gamma, ngd=None):
+    # same two optimisers and parameter groups as the reference (:186-199); each FusedAdam.step() is one fused launch
     vd = model.variational_strategy._variational_distribution
-    variational_optimizer = FusedAdam([{"params": model.variational_parameters()}], lr=lr,
-                                      lower_triangular=[vd.chol_variational_covar])
+    if ngd is not None:                       # use_ngd: natural-gradient steps on the natural parameters (:187)
+        variational_optimizer = gp.NGD(model.variational_parameters(), num_data=ngd["num_data"], lr=ngd["lr"])
+    else:
+        variational_optimizer = FusedAdam([{"params": model.variational_parameters()}], lr=lr,
+                                          lower_triangular=[vd.chol_variational_covar])
     hyperparameter_optimizer = FusedAdam([{"params": model.hyperparameters()},
                                           {"params": likelihood.parameters()}], lr=lr)
     if lr_sched == "step_lr":
@@ -124,8 +130,8 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
              verbose=True, fixed_inducing_locations=None, **args):
     """Train a DSVGP (reference :93-268).  Returns (model, likelihood)."""
     assert num_directions == minibatch_dim
-    if use_ngd or use_ciq:
-        raise NotImplementedError("use_ngd / use_ciq are outside the B200 hot path")
+    if use_ciq:
+        raise NotImplementedError("use_ciq (contour-integral-quadrature whitening) is outside the B200 hot path")
     device = _require_cuda()
     dim = len(train_dataset[0][0])
     n_samples = len(train_dataset)
@@ -138,7 +144,8 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
         inducing_points, learn_inducing_locations = fixed_inducing_locations, False
     dtype = train_dataset[0][0].dtype
     model = GPModel(inducing_points.to(dtype), inducing_directions.to(dtype), dim,
-                    learn_inducing_locations=learn_inducing_locations).to(device=device, dtype=dtype)
+                    learn_inducing_locations=learn_inducing_locations,
+                    **({"variational_distribution": "NGD"} if use_ngd else {})).to(device=device, dtype=dtype)
     likelihood = gp.GaussianLikelihood().to(device=device, dtype=dtype)
     model.train()
     likelihood.train()
@@ -146,7 +153,8 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
         count_params(model, likelihood)
 
     variational_optimizer, hyperparameter_optimizer, variational_scheduler, hyperparameter_scheduler = _optimizers(
-        model, likelihood, learning_rate_hypers, lr_sched, n_samples, minibatch_size, num_epochs, gamma)
+        model, likelihood, learning_rate_hypers, lr_sched, n_samples, minibatch_size, num_epochs, gamma,
+        ngd=dict(num_data=num_data, lr=learning_rate_ngd) if use_ngd else None)
     if mll_type == "ELBO":
         mll = gp.VariationalELBO(likelihood, model, num_data=num_data)
     elif mll_type == "PLL":

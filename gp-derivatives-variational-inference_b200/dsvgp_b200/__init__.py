@@ -8,12 +8,12 @@ from . import _lib, ops  # noqa: F401  (fails loudly if the extension is missing
 from .engine import ENGINE, NanError, NotPSDError
 from .optim import FusedAdam
 from .gp import (ApproximateGP, CholeskyVariationalDistribution, ConstantMean, DFreeDirectionalGradVariationalStrategy,
-                 DirectionalGradVariationalStrategy, GaussianLikelihood, GradVariationalStrategy, MultivariateNormal,
+                 DirectionalGradVariationalStrategy, GaussianLikelihood, GradVariationalStrategy, MultivariateNormal, NGD, NaturalVariationalDistribution,
                  PredictiveDistribution, PredictiveLogLikelihood, RBFKernelDirectionalGrad, RBFKernelGrad, ScaleKernel,
                  VariationalELBO)
 
 __all__ = ["ENGINE", "NanError", "NotPSDError", "ApproximateGP", "CholeskyVariationalDistribution", "ConstantMean",
            "DFreeDirectionalGradVariationalStrategy", "DirectionalGradVariationalStrategy", "FusedAdam", "GaussianLikelihood",
-           "GradVariationalStrategy", "MultivariateNormal", "PredictiveDistribution", "PredictiveLogLikelihood",
+           "GradVariationalStrategy", "MultivariateNormal", "NGD", "NaturalVariationalDistribution", "PredictiveDistribution", "PredictiveLogLikelihood",
            "RBFKernelDirectionalGrad", "RBFKernelGrad", "ScaleKernel", "VariationalELBO"]
 __version__ = "0.1.0"

@@ -240,6 +240,117 @@ class CholeskyVariationalDistribution(_VariationalDistribution):
             self.chol_variational_covar.copy_(torch.eye(self.num_inducing_points, dtype=self.chol_variational_covar.dtype,
                                                         device=self.chol_variational_covar.device))
 
+    def mean_and_chol(self):
+        return self.variational_mean, self.chol_variational_covar
+
+
+class _NaturalToMeanChol(torch.autograd.Function):
+    """gpytorch 1.4.0 `_NaturalToMuVarSqrt`: (natural_vec, natural_mat) = (S^-1 m, -1/2 S^-1) -> (m, chol(S)), with the
+    backward returning the gradient w.r.t. the EXPECTATION parameters, i.e. the natural gradient `gpytorch.optim.NGD`
+    applies (directional_vi.py:38-40,187,251).  Everything is M'^3 work on the library's own fp64 kernels: two blocked
+    Cholesky + inverse, three triangular products forward; the Cholesky-backward chain W^T Phi(L^T dL) W backward."""
+
+    @staticmethod
+    def _chol_inv(A64, n, what):
+        """(L, L^-1) of the n x n SPD matrix A64 (fp64, on the device) with the psd_safe_cholesky jitter ladder"""
+        dev = A64.device
+        Mp, nb0, nlev = ops.chol_plan(n)
+        work, L, W = (torch.empty(Mp, Mp, dtype=torch.float64, device=dev) for _ in range(3))
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        for extra in (0.0, 1e-8, 1e-6, 1e-5, 1e-4):
+            if Mp > n:
+                ops.pad_identity(work, n)
+            work[:n, :n] = A64
+            if extra:
+                work.diagonal()[:n].add_(extra)
+            ops.cholesky_inverse(work, L, W, nb0, nlev, info)
+            if int(info.item()) == 0:
+                return L, W
+        if not bool(torch.isfinite(A64).all()):
+            raise NanError(f"NaN/inf in {what}")
+        raise NotPSDError(f"{what} is not positive definite after adding jitter up to 1e-4")
+
+    @staticmethod
+    def forward(ctx, nat_vec, nat_mat):
+        T, n = nat_vec.dtype, nat_vec.numel()
+        F64 = torch.float64
+        _, Lm = _NaturalToMeanChol._chol_inv(-2.0 * nat_mat.detach().to(F64), n, "-2 * natural_mat")     # Lm = chol(S^-1)^-1
+        S = torch.empty(n, n, dtype=F64, device=nat_vec.device)
+        ops.gemm(Lm, Lm, S, ta=True, a_tri=ops.TRI_UPPER, b_tri=ops.TRI_LOWER, M=n, N=n, K=n)              # S = Lm^T Lm
+        mu = torch.empty(n, 1, dtype=F64, device=nat_vec.device)
+        ops.gemm(S, nat_vec.detach().to(F64).reshape(n, 1).contiguous(), mu, M=n, N=1, K=n)                 # m = S theta1
+        Ls, Ws = _NaturalToMeanChol._chol_inv(S, n, "the variational covariance")
+        ctx.save_for_backward(mu, Ls, Ws)
+        ctx.n, ctx.T = n, T
+        return mu.reshape(n).to(T), Ls[:n, :n].tril().to(T)
+
+    @staticmethod
+    def backward(ctx, dmu, dLs):
+        mu, Ls, Ws = ctx.saved_tensors
+        n, T, F64 = ctx.n, ctx.T, torch.float64
+        dev = mu.device
+        e = lambda: torch.empty(n, n, dtype=F64, device=dev)
+        dL64 = dLs.to(F64).contiguous()
+        Y, Phi, T1, G = e(), e(), e(), e()
+        ops.gemm(Ls, dL64, Y, ta=True, a_tri=ops.TRI_UPPER, b_tri=ops.TRI_LOWER, c_tri=1, M=n, N=n, K=n)   # tril(L^T dL)
+        ops.phi_lower(Y, Phi, n)
+        ops.gemm(Phi, Ws, T1, a_tri=ops.TRI_LOWER, b_tri=ops.TRI_LOWER, c_tri=1, M=n, N=n, K=n)             # Phi W (lower)
+        ops.gemm(Ws, T1, G, ta=True, a_tri=ops.TRI_UPPER, b_tri=ops.TRI_LOWER, M=n, N=n, K=n)               # W^T Phi W
+        ops.symmetrize(G, n)                                                                                # dS
+        d1 = torch.empty(n, 1, dtype=F64, device=dev)
+        ops.gemm(G, mu, d1, alpha=-2.0, beta=1.0, D=dmu.to(F64).reshape(n, 1).contiguous(), M=n, N=1, K=n)  # dmu - 2 dS m
+        return d1.reshape(n).to(T), G.to(T)
+
+
+class NaturalVariationalDistribution(_VariationalDistribution):
+    """gpytorch.variational.NaturalVariationalDistribution: keys `natural_vec` (M') and `natural_mat` (M', M');
+    q(u) = N(m, S) with natural_vec = S^-1 m, natural_mat = -1/2 S^-1; trained with `NGD` (use_ngd=True)."""
+
+    def __init__(self, num_inducing_points, batch_shape=torch.Size([]), mean_init_std=1e-3, **kwargs):
+        super().__init__()
+        self.num_inducing_points = num_inducing_points
+        self.mean_init_std = mean_init_std
+        self.register_parameter("natural_vec", Parameter(torch.zeros(num_inducing_points)))
+        self.register_parameter("natural_mat", Parameter(torch.eye(num_inducing_points).mul(-0.5)))
+
+    def shape(self):
+        return torch.Size([self.num_inducing_points])
+
+    def initialize_from_prior(self):
+        """Against the whitened prior N(0, I): natural_vec <- 1e-3 * randn, natural_mat <- -1/2 I."""
+        with torch.no_grad():
+            self.natural_vec.zero_().add_(torch.randn_like(self.natural_vec), alpha=self.mean_init_std)
+            self.natural_mat.copy_(-0.5 * torch.eye(self.num_inducing_points, dtype=self.natural_mat.dtype,
+                                                    device=self.natural_mat.device))
+
+    def mean_and_chol(self):
+        """(m, chol(S)) as differentiable functions of the natural parameters.  Without autograd (eval loops) the
+        M'^3 conversion is memoised on the parameters' identity and in-place version."""
+        if torch.is_grad_enabled() and (self.natural_vec.requires_grad or self.natural_mat.requires_grad):
+            return _NaturalToMeanChol.apply(self.natural_vec, self.natural_mat)
+        key = (self.natural_vec.data_ptr(), self.natural_vec._version, self.natural_mat.data_ptr(), self.natural_mat._version)
+        if getattr(self, "_memo", None) is None or self._memo[0] != key:
+            with torch.no_grad():
+                self._memo = (key, _NaturalToMeanChol.apply(self.natural_vec, self.natural_mat))
+        return self._memo[1]
+
+
+class NGD(torch.optim.Optimizer):
+    """gpytorch.optim.NGD: p <- p - lr * num_data * p.grad on the natural parameters (whose .grad is already the natural
+    gradient of the per-datum objective, see _NaturalToMeanChol)."""
+
+    def __init__(self, params, num_data, lr=0.1):
+        self.num_data = num_data
+        super().__init__(params, defaults=dict(lr=lr))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    p.add_(p.grad, alpha=-group["lr"] * self.num_data)
+        return None
+
 
 # ------------------------------------------------------------------------------------------------- likelihood
 class _HomoskedasticNoise(Module):
@@ -521,7 +632,8 @@ class _DirectionalStrategyBase(Module):
     def _param_list(self, likelihood):
         vd, model = self._variational_distribution, self.model
         raw_noise = likelihood.noise_covar.raw_noise if likelihood is not None else None
-        return (self.inducing_points, self._directions(), vd.variational_mean, vd.chol_variational_covar,
+        m, Ls = vd.mean_and_chol()      # the parameters themselves, or (natural parameterisation) differentiable functions of them
+        return (self.inducing_points, self._directions(), m, Ls,
                 model.mean_module.constant, model.covar_module.raw_outputscale,
                 model.covar_module.base_kernel.raw_lengthscale, raw_noise)
 
@@ -531,9 +643,8 @@ class _DirectionalStrategyBase(Module):
 
     def kl_divergence(self):
         """KL(q(u) || N(0, I)) of the whitened parameterisation (differentiable, small: plain torch on device)."""
-        vd = self._variational_distribution
-        Ls = vd.chol_variational_covar.tril()
-        m = vd.variational_mean
+        m, Ls = self._variational_distribution.mean_and_chol()
+        Ls = Ls.tril()
         return 0.5 * ((Ls * Ls).sum() + (m * m).sum() - m.numel() - Ls.diagonal().pow(2).log().sum())
 
     def _data_directions(self, x, kwargs):
@@ -583,7 +694,7 @@ class _DirectionalStrategyBase(Module):
                 self.variational_params_initialized.fill_(1)
             self._flags_checked = True
         vd = self._variational_distribution
-        return self.forward(x, self.inducing_points, vd.variational_mean, None, **kwargs)
+        return self.forward(x, self.inducing_points, getattr(vd, "variational_mean", None), None, **kwargs)
 
 
 class DirectionalGradVariationalStrategy(_DirectionalStrategyBase):

@@ -351,6 +351,55 @@ def elbo_and_grads(P, x, Vx, y, num_data, variant="dsvgp", structure="lean", thr
     return val.detach(), out
 
 
+# ------------------------------------------------------------------------- natural parameterisation (NGD)
+class _NaturalToMeanChol(torch.autograd.Function):
+    """gpytorch 1.4.0 `_NaturalToMuVarSqrt` (variational/natural_variational_distribution.py; third-party, restated):
+    (theta1 = S^-1 m, theta2 = -1/2 S^-1) -> (m, chol(S)).  The backward does NOT return the ordinary gradient: it
+    returns the gradient with respect to the expectation parameters (eta1 = m, eta2 = S + m m^T), which IS the natural
+    gradient with respect to (theta1, theta2) -- what `gpytorch.optim.NGD` then applies as p <- p - lr*num_data*grad
+    (directional_vi.py:38-40,187,251)."""
+
+    @staticmethod
+    def forward(ctx, nat_vec, nat_mat):
+        L_inv = psd_safe_cholesky(-2.0 * nat_mat)
+        eye = torch.eye(L_inv.shape[-1], dtype=L_inv.dtype)
+        Lm = torch.linalg.solve_triangular(L_inv, eye, upper=False)
+        S = Lm.T @ Lm
+        mu = S @ nat_vec
+        Ls = psd_safe_cholesky(S)
+        ctx.save_for_backward(mu, Ls)
+        return mu, Ls
+
+    @staticmethod
+    def backward(ctx, dmu, dLs):
+        mu, Ls = ctx.saved_tensors
+        eye = torch.eye(Ls.shape[-1], dtype=Ls.dtype)
+        Wi = torch.linalg.solve_triangular(Ls, eye, upper=False)
+        phi = (Ls.T @ dLs).tril()
+        phi = phi - 0.5 * torch.diag(phi.diagonal())
+        dS = Wi.T @ phi @ Wi
+        dS = 0.5 * (dS + dS.T)
+        return dmu - 2.0 * (dS @ mu), dS
+
+
+def natural_to_mean_chol(nat_vec, nat_mat):
+    return _NaturalToMeanChol.apply(nat_vec, nat_mat)
+
+
+def ngd_elbo_and_grads(P, nat_vec, nat_mat, x, Vx, y, num_data, variant="dsvgp"):
+    """ELBO of the model whose q(u) is given in natural parameters, and the (natural) gradients of everything.
+    P.m / P.Ls_raw are ignored."""
+    Q = P.clone().requires_grad_(True)
+    nv, nm = nat_vec.detach().clone().requires_grad_(True), nat_mat.detach().clone().requires_grad_(True)
+    Q.m, Q.Ls_raw = natural_to_mean_chol(nv, nm)
+    val = elbo(Q, x, Vx, y, num_data, variant)
+    names = [k for k in ("Z", "Vz", "c", "raw_os", "raw_ell", "raw_noise") if not (variant == "grad" and k == "Vz")]
+    grads = torch.autograd.grad(val, [nv, nm] + [getattr(Q, k) for k in names], allow_unused=True)
+    out = {"natural_vec": grads[0], "natural_mat": grads[1]}
+    out.update({k: g for k, g in zip(names, grads[2:])})
+    return val.detach(), out
+
+
 # ------------------------------------------------------------------------------------ synthetic inputs
 def testfun(x):
     """tests/testfun.py:4-11: f = sin(2 pi |x|^2) with its analytic gradient, columns [f, df/dx_1..d]."""

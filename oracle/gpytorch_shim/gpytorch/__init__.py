@@ -695,9 +695,81 @@ class CholeskyVariationalDistribution(_VariationalDistribution):
         self.chol_variational_covar.data.copy_(prior_dist.lazy_covariance_matrix.cholesky().evaluate())
 
 
+def _phi_for_cholesky_(A):
+    """Modifies A to be the phi function used in differentiating through Cholesky (lower triangle, halved diagonal)."""
+    A.tril_().diagonal(offset=0, dim1=-2, dim2=-1).mul_(0.5)
+    return A
+
+
+def _cholesky_backward(dout_dL, L, L_inverse):
+    # gpytorch/variational/natural_variational_distribution.py (1.4.0), after torch's cholesky_backward
+    A = L.transpose(-1, -2) @ dout_dL
+    phi = _phi_for_cholesky_(A)
+    grad_input = (L_inverse.transpose(-1, -2) @ phi) @ L_inverse
+    return grad_input.add(grad_input.transpose(-1, -2)).mul_(0.5)
+
+
+class _NaturalToMuVarSqrt(torch.autograd.Function):
+    """gpytorch 1.4.0 _NaturalToMuVarSqrt: natural parameters -> (mean, Cholesky factor of the covariance); the
+    backward returns the gradient with respect to the EXPECTATION parameters, i.e. the natural gradient."""
+
+    @staticmethod
+    def _forward(nat_mean, nat_covar):
+        L_inv = psd_safe_cholesky(-2.0 * nat_covar, upper=False)
+        eye = torch.eye(L_inv.size(-1), dtype=L_inv.dtype, device=L_inv.device)
+        L = torch.linalg.solve_triangular(L_inv, eye, upper=False)
+        S = L.transpose(-1, -2) @ L
+        mu = (S @ nat_mean.unsqueeze(-1)).squeeze(-1)
+        return mu, psd_safe_cholesky(S, upper=False)
+
+    @staticmethod
+    def forward(ctx, nat_mean, nat_covar):
+        mu, L = _NaturalToMuVarSqrt._forward(nat_mean, nat_covar)
+        ctx.save_for_backward(mu, L)
+        return mu, L
+
+    @staticmethod
+    def backward(ctx, dout_dmu, dout_dL):
+        mu, L = ctx.saved_tensors
+        eye = torch.eye(L.size(-1), dtype=L.dtype, device=L.device)
+        C = torch.linalg.solve_triangular(L, eye, upper=False)
+        dout_dSigma = _cholesky_backward(dout_dL, L, C)
+        dout_deta1 = dout_dmu - 2 * (dout_dSigma @ mu.unsqueeze(-1)).squeeze(-1)
+        return dout_deta1, dout_dSigma
+
+
 class NaturalVariationalDistribution(_VariationalDistribution):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("NGD is outside the hot path (SURVEY.md section 8f)")
+    """gpytorch.variational.NaturalVariationalDistribution (1.4.0): parameters natural_vec = S^-1 m and
+    natural_mat = -1/2 S^-1; used with gpytorch.optim.NGD (directional_vi.py:38-40, :187)."""
+
+    def __init__(self, num_inducing_points, batch_shape=torch.Size([]), mean_init_std=1e-3, **kwargs):
+        super().__init__()
+        self.num_inducing_points = num_inducing_points
+        self.mean_init_std = mean_init_std
+        self.register_parameter("natural_vec", Parameter(torch.zeros(num_inducing_points)))
+        self.register_parameter("natural_mat", Parameter(torch.eye(num_inducing_points).mul(-0.5)))
+
+    @property
+    def dtype(self):
+        return self.natural_vec.dtype
+
+    @property
+    def device(self):
+        return self.natural_vec.device
+
+    def shape(self):
+        return torch.Size([self.num_inducing_points])
+
+    def forward(self):
+        mean, chol_covar = _NaturalToMuVarSqrt.apply(self.natural_vec, self.natural_mat)
+        return MultivariateNormal(mean, CholLazyTensor(chol_covar))
+
+    def initialize_variational_distribution(self, prior_dist):
+        prior_prec = prior_dist.covariance_matrix.inverse()
+        prior_mean = prior_dist.mean
+        noise = torch.randn_like(prior_mean).mul_(self.mean_init_std)
+        self.natural_vec.data.copy_((prior_prec @ prior_mean).add_(noise))
+        self.natural_mat.data.copy_(prior_prec.mul(-0.5))
 
 
 class _VariationalStrategy(Module):
@@ -842,4 +914,24 @@ class PredictiveLogLikelihood(_ApproximateMLL):
 
 
 mlls.VariationalELBO, mlls.PredictiveLogLikelihood = VariationalELBO, PredictiveLogLikelihood
-optim.NGD = None
+
+
+class NGD(torch.optim.Optimizer):
+    """gpytorch.optim.NGD (1.4.0): natural-gradient step  p <- p - lr * num_data * p.grad  (the gradients of a
+    NaturalVariationalDistribution are already natural gradients of the per-datum objective)."""
+
+    def __init__(self, params, num_data, lr=0.1):
+        self.num_data = num_data
+        super().__init__(params, defaults=dict(lr=lr))
+
+    @torch.no_grad()
+    def step(self):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                p.add_(p.grad, alpha=(-group["lr"] * self.num_data))
+        return None
+
+
+optim.NGD = NGD

@@ -131,6 +131,51 @@ def strategy_case(variant, n, d, M, p, dtype, seed, perturb_dirs=True):
         torch.set_default_dtype(torch.float32)
 
 
+def ngd_case(n, d, M, p, dtype, seed):
+    """The reference model with variational_distribution="NGD" (directional_vi.py:38-40): one training step through
+    NaturalVariationalDistribution; the gradients of natural_vec / natural_mat are the natural gradients that
+    gpytorch.optim.NGD applies (:187, :251).  Also the parameters after one NGD step."""
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed, "dsvgp", True)
+    torch.set_default_dtype(dtype)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref_dsvgp.GPModel(P.Z, P.Vz, d, variational_distribution="NGD")
+        likelihood = gpytorch.likelihoods.GaussianLikelihood()
+        model, likelihood = model.to(dtype), likelihood.to(dtype)
+        vs = model.variational_strategy
+        vd = vs._variational_distribution
+        g = torch.Generator().manual_seed(seed)
+        Mq = M * (p + 1)
+        R = torch.randn(Mq, Mq, generator=g, dtype=torch.float64) / Mq ** 0.5
+        prec = (torch.eye(Mq, dtype=torch.float64) + 0.3 * R @ R.T).to(dtype)          # S^-1, SPD
+        nat_vec = (0.1 * torch.randn(Mq, generator=g, dtype=torch.float64)).to(dtype)
+        with torch.no_grad():
+            vs.inducing_points.data = P.Z.clone()
+            vs.inducing_directions.data = P.Vz.clone()
+            vd.natural_vec.data = nat_vec.clone()
+            vd.natural_mat.data = (-0.5 * prec).clone()
+            vs.variational_params_initialized.fill_(1)
+            model.mean_module.constant.data = P.c.clone()
+            model.covar_module.raw_outputscale.data = P.raw_os.clone()
+            model.covar_module.base_kernel.raw_lengthscale.data = P.raw_ell.clone()
+            likelihood.noise_covar.raw_noise.data = P.raw_noise.clone()
+        model.train(), likelihood.train()
+        mll = gpytorch.mlls.VariationalELBO(likelihood, model, num_data=num_data)
+        opt = gpytorch.optim.NGD(model.variational_parameters(), num_data=num_data, lr=0.1)
+        loss = -mll(likelihood(model(x, derivative_directions=Vx)), y)
+        loss.backward()
+        res = dict(n=n, d=d, M=M, p=p, seed=seed, num_data=num_data, x=x, Vx=Vx, y=y,
+                   params={k: v for k, v in P.tensors().items() if k not in ("m", "Ls_raw")},
+                   natural_vec=nat_vec, natural_mat=(-0.5 * prec), elbo=(-loss).detach().clone(),
+                   grad_natural_vec=-vd.natural_vec.grad.detach().clone(), grad_natural_mat=-vd.natural_mat.grad.detach().clone(),
+                   grad_Z=-vs.inducing_points.grad.detach().clone(), grad_raw_noise=-likelihood.noise_covar.raw_noise.grad.detach().clone())
+        opt.step()
+        res["natural_vec_after"], res["natural_mat_after"] = vd.natural_vec.detach().clone(), vd.natural_mat.detach().clone()
+        return res
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -156,6 +201,9 @@ def main():
         "grad_d3_f32": strategy_case("grad", 16, 3, 6, 3, f32, 16),
     }
     torch.save(steps, os.path.join(out_dir, "step_cases.pt"))
+    ngd = {"ngd_d3_p1_f64": ngd_case(40, 3, 16, 1, f64, 21), "ngd_c1_f32": ngd_case(50, 2, 20, 2, f32, 22)}
+    torch.save(ngd, os.path.join(out_dir, "ngd_cases.pt"))
+    print("ngd_cases.pt", {k: float(v["elbo"]) for k, v in ngd.items()})
     for name, blob in (("kernel_cases.pt", kernels), ("step_cases.pt", steps)):
         print(name, {k: (tuple(v["K"].shape) if "K" in v else float(v["elbo"])) for k, v in blob.items()},
               os.path.getsize(os.path.join(out_dir, name)), "bytes")

@@ -181,3 +181,25 @@ def test_full_covariance_oracle_agrees_with_diagonal_path(variant):
     assert torch.allclose(cov.diagonal(), v2, rtol=1e-11, atol=1e-13)
     assert torch.allclose(cov, cov.T, rtol=1e-11, atol=1e-13)
     assert float(torch.linalg.eigvalsh(0.5 * (cov + cov.T)).min()) > 0
+
+
+NCASES = torch.load(os.path.join(GOLD, "ngd_cases.pt"))
+
+
+@pytest.mark.parametrize("name", sorted(NCASES))
+def test_ngd_natural_gradients_match_reference_model(name):
+    """variational_distribution="NGD" (directional_vi.py:38-40): ELBO and natural gradients of the oracle's restatement
+    against the unmodified reference model run on the gpytorch stand-in, and the NGD update p - lr*num_data*grad."""
+    c = NCASES[name]
+    f64 = c["x"].dtype == torch.float64
+    z = torch.zeros(1, dtype=c["x"].dtype)
+    P = O.Params(m=z, Ls_raw=z, **{k: v.clone() for k, v in c["params"].items()})
+    val, g = O.ngd_elbo_and_grads(P, c["natural_vec"], c["natural_mat"], c["x"], c["Vx"], c["y"], c["num_data"])
+    tv, tg = (1e-9, 1e-7) if f64 else (1e-4, 2e-4)
+    assert abs(float(val - c["elbo"])) / abs(float(c["elbo"])) < tv
+    assert rel(g["natural_vec"], c["grad_natural_vec"]) < tg
+    assert rel(g["natural_mat"], c["grad_natural_mat"]) < tg
+    assert rel(g["Z"], c["grad_Z"]) < tg
+    # gpytorch.optim.NGD.step with lr = 0.1 (loss = -ELBO, so the step adds lr*num_data*dELBO)
+    after = c["natural_vec"] + 0.1 * c["num_data"] * c["grad_natural_vec"]
+    assert rel(after, c["natural_vec_after"]) < (1e-12 if f64 else 1e-5)

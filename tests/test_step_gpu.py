@@ -403,3 +403,88 @@ def test_memoised_factor_refreshes_noise_and_mean_constant():
         assert rel(noisy.variance - v0, O.noise(P).expand(v0.numel())) < 1e-9
         model.mean_module.constant.add_(0.5)
         assert rel(model(x.cuda(), derivative_directions=Vx).mean - m0, torch.full((m0.numel(),), 0.5, dtype=F64)) < 1e-9
+
+
+# ------------------------------------------------------------------ natural-gradient variant (section 8f rank 2, NGD)
+def _ngd_model(c, dtype):
+    import directional_vi
+    from dsvgp_b200 import gp
+    p = c["params"]
+    model = directional_vi.GPModel(p["Z"], p["Vz"], c["d"], variational_distribution="NGD").to("cuda", dtype)
+    lik = gp.GaussianLikelihood().to("cuda", dtype)
+    vs, vd = model.variational_strategy, model.variational_strategy._variational_distribution
+    assert isinstance(vd, gp.NaturalVariationalDistribution)
+    assert {"variational_strategy._variational_distribution.natural_vec",
+            "variational_strategy._variational_distribution.natural_mat"} <= set(model.state_dict())
+    with torch.no_grad():
+        vd.natural_vec.copy_(c["natural_vec"])
+        vd.natural_mat.copy_(c["natural_mat"])
+        vs.variational_params_initialized.fill_(1)
+        model.mean_module.constant.copy_(p["c"])
+        model.covar_module.raw_outputscale.copy_(p["raw_os"])
+        model.covar_module.base_kernel.raw_lengthscale.copy_(p["raw_ell"])
+        lik.noise_covar.raw_noise.copy_(p["raw_noise"])
+    return model, lik
+
+
+@pytest.mark.parametrize("name", ["ngd_d3_p1_f64", "ngd_c1_f32"])
+def test_ngd_step_matches_unmodified_reference_golden(name):
+    """GPModel(variational_distribution="NGD") + gp.NGD: ELBO, natural gradients and the NGD update against the
+    unmodified reference model (fixture from oracle/make_golden.py)."""
+    from dsvgp_b200 import gp
+    c = torch.load(os.path.join(GOLD, "ngd_cases.pt"))[name]
+    dtype, f64 = c["x"].dtype, c["x"].dtype == F64
+    model, lik = _ngd_model(c, dtype)
+    model.train(), lik.train()
+    vd = model.variational_strategy._variational_distribution
+    mll = gp.VariationalELBO(lik, model, num_data=c["num_data"])
+    opt = gp.NGD(model.variational_parameters(), num_data=c["num_data"], lr=0.1)
+    loss = -mll(lik(model(c["x"].cuda(), derivative_directions=c["Vx"])), c["y"].cuda())
+    loss.backward()
+    tv, tg = (1e-10, 1e-9) if f64 else (1e-4, 2e-4)
+    assert abs(float(-loss) - float(c["elbo"])) < tv * abs(float(c["elbo"]))
+    assert rel(-vd.natural_vec.grad, c["grad_natural_vec"]) < tg
+    assert rel(-vd.natural_mat.grad, c["grad_natural_mat"]) < tg
+    assert rel(-model.variational_strategy.inducing_points.grad, c["grad_Z"]) < tg
+    assert rel(-lik.noise_covar.raw_noise.grad, c["grad_raw_noise"]) < tg
+    if not f64:      # the fp32 fixture is the reference's own fp32 arithmetic; the kernels are gated against the fp64 oracle
+        z = torch.zeros(1, dtype=F64)
+        P = O.Params(m=z, Ls_raw=z, **{k: v.double() for k, v in c["params"].items()})
+        val, g = O.ngd_elbo_and_grads(P, c["natural_vec"].double(), c["natural_mat"].double(), c["x"].double(),
+                                      c["Vx"].double(), c["y"].double(), c["num_data"])
+        assert abs(float(-loss) - float(val)) < 1e-4 * abs(float(val))
+        assert rel(-vd.natural_vec.grad, g["natural_vec"]) < 1e-4 and rel(-vd.natural_mat.grad, g["natural_mat"]) < 1e-4
+    opt.step()
+    assert rel(vd.natural_vec, c["natural_vec_after"]) < (1e-9 if f64 else 2e-4)
+    assert rel(vd.natural_mat, c["natural_mat_after"]) < (1e-9 if f64 else 2e-4)
+    model.eval(), lik.eval()
+    with torch.no_grad():        # eval: the memoised natural -> (m, chol S) conversion follows the updated parameters
+        a = lik(model(c["x"].cuda(), derivative_directions=c["Vx"])).mean.clone()
+        b = lik(model(c["x"].cuda(), derivative_directions=c["Vx"])).mean
+        assert torch.equal(a, b) and bool(torch.isfinite(a).all())
+
+
+def test_train_gp_with_ngd_reduces_loss():
+    import math
+    import random
+    import directional_vi
+    torch.manual_seed(1), random.seed(1)
+    n, d = 400, 2
+    x = torch.rand(n, d)
+    f = torch.sin(2 * math.pi * (x ** 2).sum(1, keepdim=True))
+    df = 4 * math.pi * x * torch.cos(2 * math.pi * (x ** 2).sum(1, keepdim=True))
+    ds = torch.utils.data.TensorDataset(x, torch.cat([f, df], 1))
+    import builtins
+    losses, real_print = [], builtins.print
+
+    def spy(*a, **k):
+        s = " ".join(str(t) for t in a)
+        if "loss:" in s and "total_step" in s:
+            losses.append(float(s.split("loss:")[1].split(",")[0]))
+    builtins.print = spy
+    try:
+        model, lik = directional_vi.train_gp(ds, num_inducing=16, num_directions=2, minibatch_size=200, minibatch_dim=2,
+                                             num_epochs=60, learning_rate_hypers=0.01, learning_rate_ngd=0.1, use_ngd=True)
+    finally:
+        builtins.print = real_print
+    assert len(losses) >= 3 and losses[-1] < losses[0] - 0.1 and all(math.isfinite(v) for v in losses), losses
