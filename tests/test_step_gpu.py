@@ -488,3 +488,51 @@ def test_train_gp_with_ngd_reduces_loss():
     finally:
         builtins.print = real_print
     assert len(losses) >= 3 and losses[-1] < losses[0] - 0.1 and all(math.isfinite(v) for v in losses), losses
+
+
+def test_training_trajectory_agrees_across_tensor_core_paths():
+    """40 Adam steps with a large learning rate at a size that takes the tcgen05 path (M' = 192, n' = 1536): the
+    3xFP16 products (scales recomputed from the moving parameters every step), the 3xTF32 products and the mma.sync
+    kernels with fp64 master sums give the same loss trajectory; nothing overflows fp16 as L_s, the lengthscale and
+    the inducing points move."""
+    import math
+    import bench
+    from dsvgp_b200 import engine, gp
+    from dsvgp_b200.optim import FusedAdam
+
+    def run(use_tc, use_fp16):
+        old = (engine.USE_TC, engine.USE_FP16)
+        engine.USE_TC, engine.USE_FP16 = use_tc, use_fp16
+        engine.ENGINE._ws.clear(), engine.ENGINE._fac.clear()
+        try:
+            wl = dict(bench.WORKLOADS["C3"], M=64, n=512, N=5000)
+            dev = torch.device("cuda", 0)
+            model, lik = bench.build_model(wl, F32, dev)
+            d, p = wl["d"], wl["p"]
+            mll = gp.VariationalELBO(lik, model, num_data=(d + 1) * wl["N"])
+            vd = model.variational_strategy._variational_distribution
+            opt = FusedAdam([{"params": list(model.parameters()) + list(lik.parameters())}], lr=0.05,
+                            lower_triangular=[vd.chol_variational_covar])
+            losses = []
+            for it in range(40):
+                x, V, y = (t.to(dev) for t in bench.synth_batch(wl["n"], d, p, "dsvgp", F32, "cpu", 100 + it))
+                opt.zero_grad()
+                loss = -mll(lik(model(x, derivative_directions=V)), y)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+            ws = next(iter(engine.ENGINE._ws.values()))
+            assert ws.tc == use_tc and ws.tch == (use_tc and use_fp16)
+            return losses, float(model.covar_module.base_kernel.lengthscale), float(vd.chol_variational_covar.abs().max())
+        finally:
+            engine.USE_TC, engine.USE_FP16 = old
+            engine.ENGINE._ws.clear(), engine.ENGINE._fac.clear()
+
+    ref, ell_ref, _ = run(False, False)            # mma.sync 3xTF32 with fp64 master sums
+    assert all(math.isfinite(v) for v in ref) and ref[-1] < ref[0] - 1.0
+    for mode in ((True, True), (True, False)):
+        got, ell, lmax = run(*mode)
+        assert all(math.isfinite(v) for v in got), mode
+        dev_rel = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(got, ref))
+        assert dev_rel < 2e-3, (mode, dev_rel)
+        assert abs(ell - ell_ref) < 2e-3 * ell_ref
