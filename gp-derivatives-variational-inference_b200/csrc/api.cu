@@ -90,6 +90,7 @@ int dsvgp_absmax_f64(const double* x, int64_t ld, int rows, int cols, int mode, 
 int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* maxbits, int Mq, float* scales, int stage, dsvgp_stream_t s) { return tc_scales(hyp, jitter, maxbits, Mq, scales, stage, ST(s)); }
 int dsvgp_split_half_f32(const float* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<float>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
 int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<double>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
+int dsvgp_build_d_split_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo, int64_t ldh, dsvgp_stream_t s) { return build_d_split(E, lde, P, ldp, n, scale, hi, lo, ldh, ST(s)); }
 int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s) {
   if (!x1 || !x2 || !hyp || !K || !Kh || !Kl || !hscale || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;
   return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag, nullptr, Kh, Kl, ldkh, hscale);

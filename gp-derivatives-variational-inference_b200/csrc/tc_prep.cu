@@ -10,6 +10,7 @@
 //   A = W K_zx          column norms: k_j^T (K_zz + jitter I)^-1 k_j <= k_jj  =>  |A_ij| <= a
 //   E = tril(L_s) - I   max|E| itself
 //   B = L_s^T A         (1 + e) a
+//   D = S - I = E + E^T + E E^T    2 max|E| + M' max|E|^2
 //   C = (S - I) A       e (2 + e) a ;   dA = m g_mu^T + 2 C diag(g_var):  max|m| max|g_mu| + 2 max|g_var| e (2 + e) a
 //   A_g = A diag(g_var) a max|g_var|
 // Maxima are order-independent (atomicMax on the bit pattern of |x|), so scales -- and results -- are deterministic.
@@ -52,8 +53,8 @@ __device__ __forceinline__ float pow2_scale(float bound) {
   return exp2f((float)ex);
 }
 
-// scales: [0] sW [1] sK [2] sE [3] sA [4] sB [5] sdA [6] sAg | [8] 1/(sW sK) [9] 1/(sE sA) [10] 1/(sE sB) [11] 1/(sW sdA)
-//         [12] 1/(sAg sA).   maxbits: [0] max|E| [1] max|m| [2] max|g_mu| [3] max|g_var|
+// scales: [0] sW [1] sK [2] sE [3] sA [4] sB [5] sdA [6] sAg [7] sD | [8] 1/(sW sK) [9] 1/(sE sA) [10] 1/(sE sB)
+//         [11] 1/(sW sdA) [12] 1/(sAg sA) [13] 1/(sD sA).   maxbits: [0] max|E| [1] max|m| [2] max|g_mu| [3] max|g_var|
 // stage 0 (forward, needs hyp and maxbits[0]): entries 0-4, 8-10.  stage 1 (backward, needs maxbits[1..3]): 5, 6, 11, 12.
 __global__ void tc_scales_kernel(const double* __restrict__ hyp, double jitter, const unsigned* __restrict__ maxbits, int Mq,
                                  float* __restrict__ sc, int stage) {
@@ -67,9 +68,12 @@ __global__ void tc_scales_kernel(const double* __restrict__ hyp, double jitter, 
     sc[2] = pow2_scale(__uint_as_float(maxbits[0]));
     sc[3] = pow2_scale(a);
     sc[4] = pow2_scale((1.f + e) * a);
+    const float em = __uint_as_float(maxbits[0]);
+    sc[7] = pow2_scale(1.01f * (2.f * em + (float)Mq * em * em));
     sc[8] = 1.f / (sc[0] * sc[1]);
     sc[9] = 1.f / (sc[2] * sc[3]);
     sc[10] = 1.f / (sc[2] * sc[4]);
+    sc[13] = 1.f / (sc[7] * sc[3]);
   } else {
     const float mm = __uint_as_float(maxbits[1]), gm = __uint_as_float(maxbits[2]), gv = __uint_as_float(maxbits[3]);
     sc[5] = pow2_scale(1.01f * (mm * gm + 2.f * gv * e * (2.f + e) * a));
@@ -114,6 +118,32 @@ __global__ void split_half_kernel(const S* __restrict__ src, int64_t lds, int ro
       loT[(int64_t)i * ldhT + j] = __float2half_rn(v - __half2float(h));
     }
   }
+}
+
+// D = S - I = E + E^T + E E^T (symmetric, dense) from the lower triangles of E and of P = E E^T, and its two-half split
+// (hi, lo) of D * *scale: the operand of the ONE dense product C = D A that replaces B' = E^T A, C = E B + B' in training.
+__global__ void __launch_bounds__(256)
+build_d_split_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ P, int64_t ldp, int n,
+                     const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldh) {
+  const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  const int r = max(i, j), c = min(i, j);
+  float v = P[(int64_t)r * ldp + c] + E[(int64_t)r * lde + c];
+  if (i == j) v += E[(int64_t)r * lde + c];
+  v *= *scale;
+  const __half h = __float2half_rn(v);
+  hi[(int64_t)i * ldh + j] = h;
+  lo[(int64_t)i * ldh + j] = __float2half_rn(v - __half2float(h));
+}
+
+int build_d_split(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo,
+                  int64_t ldh, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  if (!E || !P || !scale || !hi || !lo) return DSVGP_ERR_ARG;
+  dim3 grid(ceil_div(n, 256), n);
+  build_d_split_kernel<<<grid, 256, 0, st>>>(E, lde, P, ldp, n, scale, static_cast<__half*>(hi), static_cast<__half*>(lo), ldh);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
 }
 
 template <typename T>

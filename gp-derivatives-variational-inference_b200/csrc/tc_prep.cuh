@@ -16,4 +16,8 @@ template <typename S>
 int split_half(const S* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh,
                void* hiT, void* loT, int64_t ldhT, cudaStream_t st);
 
+// (hi, lo) halves of (E + E^T + E E^T) * *scale from the lower triangles of E and P = E E^T (n x n, fp32)
+int build_d_split(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo,
+                  int64_t ldh, cudaStream_t st);
+
 }  // namespace dsvgp

@@ -29,6 +29,7 @@ PRED_JITTER = 1e-4         # data_data_covar.add_jitter(1e-4) DGVS.py:198,203
 CHOL_RETRY = (1e-6, 1e-5, 1e-4)   # psd_safe_cholesky(jitter=1e-6): 1e-6 * 10**i, i < 3   DGVS.py:74
 USE_TC = True      # fp32 model: run the big whitening products on tcgen05 (set False to force the mma.sync kernels)
 USE_FP16 = True    # ... as 3xFP16 (kind::f16, scaled two-half operands) instead of 3xTF32: same 22 significand bits, 1.6x faster
+DENSE_D = True     # 3xFP16 training path: (S - I) A as ONE dense product with D = E + E^T + E E^T (False: B' = E^T A, C = E B + B')
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
 F16 = torch.float16
@@ -99,12 +100,14 @@ class Workspace:
         sq = lambda: e(Mq, self.ldm)[:, :Mq]
         self.E, self.Hp = sq(), sq()
         if self.tch:
-            # two-half operands of the 3xFP16 products.  (Kh, Kl) holds K_zx, then B = L_s^T A, then dA; (Ah, Al) holds A
+            # two-half operands of the 3xFP16 products.  (Kh, Kl) holds K_zx, then dA; (Ah, Al) holds A
             # from the forward pass to the Gram product; (Agh, Agl) holds A diag(g_var).
             hb = lambda: e(Mq, self.ldn, dt=F16)[:, :nq]
             self.Kh, self.Kl, self.Ah, self.Al, self.Agh, self.Agl = (hb() for _ in range(6))
             sh = lambda: e(Mq, self.ldm, dt=F16)[:, :Mq]
             self.Eh, self.El, self.ETh, self.ETl = sh(), sh(), sh(), sh()
+            self.Dh, self.Dl = sh(), sh()               # split of D = S - I = E + E^T + E E^T (training: C = D A)
+            self.P = e(Mq, self.ldg)[:, :Mq]            # E E^T (lower tiles)
         if self.tc:
             if not self.tch:
                 self.lo1, self.lo2, self.lo3 = (e(Mq, self.ldn) for _ in range(3))   # "lo" parts of the current big operands
@@ -236,7 +239,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ forward
     @staticmethod
-    def _assemble(ws, f, P, x, wx):
+    def _assemble(ws, f, P, x, wx, need_C=True):
         """Everything of the forward pass that does not need the Cholesky factor: K_zx (+ its TF32 lo part) and the
         operands made from L_s.  elbo_step runs this on a side stream while K_zz is being factorised."""
         Mq, nq = ws.Mq, ws.nq
@@ -245,7 +248,24 @@ class Engine:
             # 3xFP16 path: K_zx leaves the assembly kernel only as the two-half split of K * sK (no fp32 matrix at all)
             if not ops.kdir_fwd_half(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, ws.Kh, ws.Kl, f.scales[1:2], canon=ws.canon):
                 ops.split_half(ws.Kzx, f.scales[1:2], ws.Kh, ws.Kl, rows=Mq, cols=nq)
-            ops.split_half(P.Ls_raw, f.scales[2:3], ws.Eh, ws.El, mode=2, hiT=ws.ETh, loT=ws.ETl, rows=Mq, cols=Mq)
+            if need_C and DENSE_D:
+                # training: D = S - I = E + E^T + E E^T explicitly (every term is small when S ~ I: no cancellation), so
+                # that (S - I) A is ONE dense product instead of B' = E^T A, C = E B + B'.  E and E^T (fp32 + lo) are also
+                # the operands of the two M'^3 products of the backward tail.
+                ops.tril_minus_eye(P.Ls_raw, ws.E)
+                ops.split_lo(ws.E, ws.E_lo)
+                ops.transpose(ws.E, ws.ET)
+                ops.split_lo(ws.ET, ws.ET_lo)
+                ops.gemm_tc(ws.E, ws.E_lo, ws.E, ws.E_lo, ws.P, Mq, Mq, Mq, b_kmajor=True, a_tri=TRI_LOWER, c_lower=True,
+                            chunk=TC_CHUNK)                                                   # lower tiles of E E^T
+                ops.build_d_split(ws.E, ws.P, f.scales[7:8], ws.Dh, ws.Dl, Mq)
+            else:
+                ops.split_half(P.Ls_raw, f.scales[2:3], ws.Eh, ws.El, mode=2, hiT=ws.ETh, loT=ws.ETl, rows=Mq, cols=Mq)
+                if need_C:                            # (DENSE_D off) fp32 operands of the two M'^3 products of the tail
+                    ops.tril_minus_eye(P.Ls_raw, ws.E)
+                    ops.split_lo(ws.E, ws.E_lo)
+                    ops.transpose(ws.E, ws.ET)
+                    ops.split_lo(ws.ET, ws.ET_lo)
             return
         have_lo = ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1 if tc else None)
         # L_s = I + E:  B' = E^T A, B = L_s^T A = A + B', C = (S - I) A = E B + B'   (no cancellation against A)
@@ -264,12 +284,15 @@ class Engine:
         Kzx, A, B, C = ws.Kzx, ws.A, ws.B, ws.C
         tc = ws.tc and f.tc
         if not assembled:
-            Engine._assemble(ws, f, P, x, wx)
+            Engine._assemble(ws, f, P, x, wx, need_C)
         if ws.tch and f.tch:
             sc, H = f.scales, TCH_CHUNK
             ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
                          Ch=(ws.Ah, ws.Al), c_scale=sc[3:4])                                  # A = L^-1 K_zx (+ its split)
-            if need_C:
+            if need_C and DENSE_D:
+                ops.gemm_tch((ws.Dh, ws.Dl), (ws.Ah, ws.Al), C, Mq, nq, Mq, sc[13:14], chunk=H)   # C = (S - I) A, dense
+                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C)
+            elif need_C:
                 ops.gemm_tch((ws.ETh, ws.ETl), (ws.Ah, ws.Al), ws.Bp, Mq, nq, Mq, sc[9:10], a_tri=TRI_UPPER, chunk=H,
                              D2=A, C2h=(ws.Kh, ws.Kl), c2_scale=sc[4:5])                      # B' = E^T A ; split of B = A + B'
                 ops.gemm_tch((ws.Eh, ws.El), (ws.Kh, ws.Kl), C, Mq, nq, Mq, sc[10:11], a_tri=TRI_LOWER, chunk=H, beta=1.0,
@@ -324,10 +347,7 @@ class Engine:
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             ops.gemm_tch((ws.Agh, ws.Agl), (ws.Ah, ws.Al), ws.G, Mq, Mq, nq, sc[12:13], b_kmajor=True, c_lower=True,
                          chunk=TCH_CHUNK, nsplit=ws.syrk_split, split_ws=ws.split_ws)                                     # G = A_g A^T
-            ops.tril_minus_eye(P.Ls_raw, ws.E)           # fp32 operands of the two M'^3 products of the tail (3xTF32)
-            ops.split_lo(ws.E, ws.E_lo)
-            ops.transpose(ws.E, ws.ET)
-            ops.split_lo(ws.ET, ws.ET_lo)
+            # (E, E^T as fp32 + lo for the two M'^3 products of the tail were made by _assemble)
         else:
             ops.dA_apply(A, C, Ag, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t,                  # C <- dA ; Ag ; t = A gmu
                          C_lo=ws.lo1 if tc else None, Ag_lo=ws.lo3 if tc else None)      # (+ their lo parts)

@@ -163,6 +163,11 @@ def split_half(src, scale, hi, lo, mode=0, hiT=None, loT=None, rows=None, cols=N
          src.shape[1] if cols is None else cols, mode, scale, hi, lo, _ld(hi), hiT, loT, _ld(hiT) if hiT is not None else 0)
 
 
+def build_d_split(E, P, scale, hi, lo, n=None):
+    """(hi, lo) = split of (E + E^T + E E^T) * scale from the lower triangles of E and P = E E^T."""
+    call("dsvgp_build_d_split_f32", E, _ld(E), P, _ld(P), E.shape[0] if n is None else n, scale, hi, lo, _ld(hi))
+
+
 def kdir_fwd_half(x1, u1, p1, x2, w2, p2, hyp, K, Kh, Kl, hscale, canon=None, use_os=True):
     """K_zx assembly that writes only the two-half split of K * hscale; returns True if it did (else K was written)."""
     n1, d = x1.shape

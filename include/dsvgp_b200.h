@@ -135,8 +135,8 @@ int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* 
  * dsvgp_absmax_*: *out_bits = max(*out_bits, max|x_ij|) as the bit pattern of a non-negative float (zero it first; NaN
  *   gives +inf); mode 0: all entries, 2: the entries of tril(x) - I.
  * dsvgp_tc_scales_f32: power-of-two scales (device float[16]) of every operand of a step from rigorous a-priori bounds
- *   (list in csrc/tc_prep.cu): [0] W [1] K_zx [2] E [3] A [4] B [5] dA [6] A_g, [8..12] the reciprocal products
- *   1/(sW sK), 1/(sE sA), 1/(sE sB), 1/(sW sdA), 1/(sAg sA).  maxbits (device uint[4]) = absmax bits of E, m, g_mu, g_var.
+ *   (list in csrc/tc_prep.cu): [0] W [1] K_zx [2] E [3] A [4] B [5] dA [6] A_g [7] D = S - I, [8..13] the reciprocal products
+ *   1/(sW sK), 1/(sE sA), 1/(sE sB), 1/(sW sdA), 1/(sAg sA), 1/(sD sA).  maxbits (device uint[4]) = absmax bits of E, m, g_mu, g_var.
  *   stage 0 fills what the forward pass needs (hyp, jitter, maxbits[0]), stage 1 the rest.
  * dsvgp_split_half_*: (hi, lo) = two-half split of op(src) * *scale, optionally also of its transpose (hiT, loT);
  *   mode 0: src, 1: tril(src), 2: tril(src) - I.
@@ -148,6 +148,9 @@ int dsvgp_absmax_f64(const double* x, int64_t ld, int rows, int cols, int mode, 
 int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* maxbits, int Mq, float* scales, int stage, dsvgp_stream_t s);
 int dsvgp_split_half_f32(const float* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s);
 int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s);
+/* (hi, lo) = two-half split of D * *scale with D = S - I = E + E^T + E E^T (symmetric), from the lower triangles of
+ * E = tril(L_s) - I and P = E E^T: the operand of the single dense product C = (S - I) A of the training step. */
+int dsvgp_build_d_split_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo, int64_t ldh, dsvgp_stream_t s);
 int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s);
 int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s);
 /* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles

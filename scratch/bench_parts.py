@@ -37,6 +37,11 @@ def timed(fn, k=10, warm=2):
 res = {}
 for _ in range(3): step()
 res["step_ms"] = timed(step, 10)
+if dtype == torch.float32:                # A/B in one process: one dense (S - I) A product vs the two triangular ones
+    for flag in (False, True, False, True):
+        engine.DENSE_D = flag
+        res[f"step_ms_dense_d_{int(flag)}" + ("" if f"step_ms_dense_d_{int(flag)}" not in res else "_again")] = timed(step, 10)
+    engine.DENSE_D = True
 ws = ENGINE.workspace(dev, dtype, n, d, M, p, p2)
 f = ENGINE.factor(dev, dtype, d, M, p)
 vs = model.variational_strategy

@@ -1,0 +1,35 @@
+"""Kernel durations of real (back-to-back) training steps via torch.profiler (CUPTI), no replay/serialisation."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gp-derivatives-variational-inference_b200"))
+import torch, bench, collections
+from torch.profiler import profile, ProfilerActivity
+from dsvgp_b200 import gp
+name = sys.argv[1] if len(sys.argv) > 1 else "C3"
+wl = dict(bench.WORKLOADS[name]); dtype = torch.float64 if wl["dtype"] == "f64" else torch.float32
+dev = torch.device("cuda", 0)
+model, lik = bench.build_model(wl, dtype, dev)
+mll = gp.VariationalELBO(lik, model, num_data=(wl["d"] + 1) * wl["N"])
+x, V, y = (t.to(dev) for t in bench.synth_batch(wl["n"], wl["d"], wl["p"], wl["variant"], dtype, "cpu", 1000))
+params = list(model.parameters()) + list(lik.parameters())
+def step():
+    for q in params: q.grad = None
+    loss = -mll(lik(model(x, derivative_directions=V)), y); loss.backward(); return loss
+for _ in range(5): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+agg = collections.OrderedDict()
+for e in evs:
+    k = e.name.split("(")[0].split("<")[0][-48:]
+    a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v[1] for v in agg.values())
+t0 = min(e.time_range.start for e in evs); t1 = max(e.time_range.end for e in evs)
+print(f"wall span per step {(t1 - t0) / 5 / 1000:.3f} ms; sum of kernel times per step {tot / 5 / 1000:.3f} ms")
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"{k:50s} {c // 5:5d}/step {t / 5 / 1000:9.3f} ms/step")
+# individual tch gemm launches of the last step
+g = [e for e in evs if "gemm_tch" in e.name][-4:]
+print("tch launches (us):", [round(e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in g])
