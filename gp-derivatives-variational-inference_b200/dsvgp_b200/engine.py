@@ -60,6 +60,9 @@ class Factor:
         e = lambda *s, dt=F64: torch.empty(*s, dtype=dt, device=device)
         self.hyp = e(8)
         self.info = torch.zeros(1, dtype=torch.int32, device=device)
+        # the status travels to pinned host memory right after the factorisation; the host waits for THAT event only
+        self.info_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.info_event = torch.cuda.Event()
         self.Kzz, self.L, self.W = e(self.Mp, self.Mp), e(self.Mp, self.Mp), e(self.Mp, self.Mp)
         self.ldm = _round_up(self.Mq, 8)
         self.Wt = e(self.Mq, self.ldm, dt=dtype)[:, : self.Mq] if dtype == F32 else self.W   # W in the model dtype
@@ -76,6 +79,7 @@ class Factor:
             self.scales = torch.ones(16, dtype=F32, device=device)
             self.maxbits = torch.zeros(4, dtype=torch.int32, device=device)
         self.jitter = KZZ_JITTER
+        self.Wt_fresh = False
         self.uzT = self.invzT = self.uz64 = self.invz64 = None
         self.valid = False
         self.owner = None          # (strategy id, parameter versions) the memoised factor belongs to
@@ -143,8 +147,15 @@ class Workspace:
 
 class Engine:
     def __init__(self):
-        self._ws, self._fac, self._streams = {}, {}, {}
+        self._ws, self._fac, self._streams, self._events = {}, {}, {}, {}
         self.reduce_hook = None     # callable(big_or_None, small) summing the buffers over ranks, or None
+
+    def _fork_event(self, device):
+        key = str(device)
+        ev = self._events.get(key)
+        if ev is None:
+            ev = self._events[key] = torch.cuda.Event()
+        return ev
 
     def _side_stream(self, device):
         key = str(device)
@@ -201,21 +212,38 @@ class Engine:
             ops.pad_identity(f.Kzz, f.Mq)
         ops.kdir_fwd(P.Z, f.uz64, f.p, P.Z, f.uz64, f.p, f.hyp, f.Kzz, diag_add=KZZ_JITTER + extra_jitter)
         ops.cholesky_inverse(f.Kzz, f.L, f.W, f.nb0, f.nlev, f.info)
+        f.info_host.copy_(f.info, non_blocking=True)
+        f.info_event.record()
         f.jitter = KZZ_JITTER + extra_jitter
         if f.tch:
             if prep:
                 Engine._scales0(f, P)
             ops.split_half(f.W, f.scales[0:1], f.Wh, f.Wl, mode=1, hiT=f.WTh, loT=f.WTl, rows=f.Mq, cols=f.Mq)
-        if T == F32:
+        f.Wt_fresh = T != F32
+        if T == F32 and not f.tch:                  # (the 3xFP16 path reads W only through its two-half split: see _wt)
             ops.cast2d(f.W, f.Wt, f.Mq, f.Mq, tril=True)
-            if f.tc and not f.tch:
+            f.Wt_fresh = True
+            if f.tc:
                 ops.split_lo(f.Wt, f.Wt_lo)
                 ops.transpose(f.Wt, f.WtT)
                 ops.split_lo(f.WtT, f.WtT_lo)
 
     @staticmethod
+    def _wt(f):
+        """W in the model dtype, made on demand for the consumers outside the 3xFP16 path (small minibatches that take
+        the mma.sync kernels, the legacy re-whitening)."""
+        if not f.Wt_fresh:
+            ops.cast2d(f.W, f.Wt, f.Mq, f.Mq, tril=True)
+            f.Wt_fresh = True
+        return f.Wt
+
+    @staticmethod
     def _check(f, P):
-        info = int(f.info.item())          # the one host sync of a step
+        # The one host synchronisation of a step -- on the event recorded right after the factorisation, not on the
+        # whole step: by the time the host has enqueued the rest of the step the status is usually there already, and
+        # the host goes on to prepare the next step while the GPU is still working on this one.
+        f.info_event.synchronize()
+        info = int(f.info_host[0])
         if info == 0:
             return True
         for name in ("Z", "Vz", "raw_ell", "raw_os"):
@@ -315,7 +343,7 @@ class Engine:
                 ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, Bp=ws.Bp)
             ops.predict_finish(ws.pm, ws.pv, nq, ws.p2, f.hyp, ws.mu, ws.var, add_noise, PRED_JITTER)
             return
-        ops.gemm(f.Wt, Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)                        # A = L^-1 K_zx
+        ops.gemm(Engine._wt(f), Kzx, A, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)               # A = L^-1 K_zx
         ops.gemm(ws.E, A, ws.Bp, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq, C2=B if need_C else None,
                  D2=A if need_C else None)
         if need_C:
@@ -354,7 +382,7 @@ class Engine:
             if tc:
                 ops.gemm_tc(f.WtT, f.WtT_lo, C, ws.lo1, dKzx, Mq, nq, Mq, a_tri=TRI_UPPER, chunk=TC_CHUNK)   # dK_zx = L^-T dA
             else:
-                ops.gemm(f.Wt, C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
+                ops.gemm(self._wt(f), C, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             if tc:                                                                       # G = A diag(gvar) A^T
                 # (A_lo is still in ws.lo2 from the forward pass)
@@ -425,16 +453,20 @@ class Engine:
         if f.tch:
             self._scales0(f, P, KZZ_JITTER)
         # K_zx assembly and the L_s operands do not depend on the factor: they run on a side stream underneath the
-        # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle)
+        # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle).  The host has just come out of the
+        # previous step's status read, so the GPU is waiting for launches: the factorisation (the critical path) is
+        # enqueued first, the side-stream work -- forked at an event recorded BEFORE it -- second.
         cur, side = torch.cuda.current_stream(dev), self._side_stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._assemble(ws, f, P, x, wx)
+        fork = self._fork_event(dev)
+        fork.record(cur)
         for extra in (0.0,) + CHOL_RETRY:
             if f.tch and extra != 0.0:
                 self._scales0(f, P, KZZ_JITTER + extra)
             self._factorise(f, P, T, extra, prep=False)
             if extra == 0.0:
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    self._assemble(ws, f, P, x, wx)
                 cur.wait_stream(side)
             self._forward(ws, f, P, x, wx, through_likelihood, need_C=True, assembled=(extra == 0.0))
             ws.small.zero_()
@@ -448,13 +480,16 @@ class Engine:
                 self._backward(ws, f, P, x, wx, ws.gmu, ws.gvar, through_likelihood, 1.0 / num_data)
             elif self.reduce_hook is not None:
                 self.reduce_hook(None, ws.small)
+            # everything the caller gets is enqueued BEFORE the one host synchronisation of the step (the Cholesky status
+            # read), so the GPU never waits for the host at the end of a step
+            elbo = ws.sc[0] - ws.kl[0] / num_data
+            grads = self._collect(ws, f, P, T, ws.sc[1] + ws.sc[6]) if want_grads else None
+            mean, var = ws.mu.clone(), ws.var.clone()
             if self._check(f, P):
                 break
         else:
             raise NotPSDError("K_zz is not positive definite after adding jitter up to 1e-4 (psd_safe_cholesky ladder)")
-        elbo = ws.sc[0] - ws.kl[0] / num_data
-        grads = self._collect(ws, f, P, T, ws.sc[1] + ws.sc[6]) if want_grads else None
-        return elbo, grads, ws.mu.clone(), ws.var.clone()
+        return elbo, grads, mean, var
 
     # --------------------------------------------------------------------------- public: differentiable q(f)
     def predictive_forward(self, P, x, Vx, p, p2, add_noise):

@@ -412,10 +412,13 @@ class _ElboStep(torch.autograd.Function):
         grads = ctx.grads
         if grads is None:
             raise RuntimeError("the ELBO was evaluated without gradients (torch.no_grad / no parameter requires grad)")
-        out = []
-        for name, need in zip(_PARAM_ORDER, ctx.needs_input_grad[4:]):
-            g = grads.get(name)
-            out.append(g * g_elbo.to(g.dtype) if (need and g is not None) else None)
+        wanted = [(k, grads[name]) for k, (name, need) in enumerate(zip(_PARAM_ORDER, ctx.needs_input_grad[4:]))
+                  if need and grads.get(name) is not None]
+        out = [None] * len(_PARAM_ORDER)
+        if wanted:          # one fused multi-tensor launch per dtype instead of one multiply per parameter
+            scaled = torch._foreach_mul([g for _, g in wanted], g_elbo.to(wanted[0][1].dtype))
+            for (k, _), g in zip(wanted, scaled):
+                out[k] = g
         return (None, None, None, None, *out)
 
 
@@ -673,7 +676,7 @@ class _DirectionalStrategyBase(Module):
             rhs[:, :Mq] = vd.chol_variational_covar.tril()
             rhs[:, Mq] = vd.variational_mean - self.model.mean_module.constant
             out = torch.empty_like(rhs)
-            ops.gemm(f.Wt, rhs, out, a_tri=ops.TRI_LOWER, M=Mq, N=Mq + 1, K=Mq)
+            ops.gemm(ENGINE._wt(f), rhs, out, a_tri=ops.TRI_LOWER, M=Mq, N=Mq + 1, K=Mq)
             root = out[:, :Mq].tril()
             sign = torch.where(root.diagonal() < 0, -1.0, 1.0).to(T)
             vd.chol_variational_covar.copy_(root * sign)

@@ -33,3 +33,18 @@ for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
 # individual tch gemm launches of the last step
 g = [e for e in evs if "gemm_tch" in e.name][-4:]
 print("tch launches (us):", [round(e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in g])
+# timeline of the last step: Cholesky phase and gaps on the critical path
+last = [e for e in evs if e.time_range.start >= sorted(e2.time_range.start for e2 in evs if "hyp_from_raw" in e2.name)[-1]]
+last.sort(key=lambda e: e.time_range.start)
+po = [e for e in last if "potrf" in e.name]
+print(f"potrf: n={len(po)} first start -> last end {(po[-1].time_range.end - po[0].time_range.start)/1000:.3f} ms, sum of potrf {sum(e.time_range.end - e.time_range.start for e in po)/1000:.3f} ms")
+gaps = [(po[i+1].time_range.start - po[i].time_range.end) for i in range(len(po)-1)]
+print("gaps between consecutive potrf (us):", [round(g) for g in gaps])
+t_first = last[0].time_range.start
+def when(sub, which=0):
+    xs = [e for e in last if sub in e.name]
+    return None if not xs else (xs[which].time_range.start - t_first, xs[which].time_range.end - t_first)
+for nm in ("hyp_from_raw", "kdir_fwd_v4", "kdir_fwd_blocked", "potrf", "split_half", "gemm_tch", "col_dots", "dA_half", "kdir_bwd_v4", "splitk_reduce", "gemm_tc2", "kdir_bwd_blocked", "var_grads"):
+    w = when(nm); wl_ = when(nm, -1)
+    if w: print(f"{nm:20s} first {w[0]/1000:8.3f} .. last end {wl_[1]/1000:8.3f} ms")
+print("step span", (last[-1].time_range.end - t_first)/1000)
