@@ -48,3 +48,13 @@ for nm in ("hyp_from_raw", "kdir_fwd_v4", "kdir_fwd_blocked", "potrf", "split_ha
     w = when(nm); wl_ = when(nm, -1)
     if w: print(f"{nm:20s} first {w[0]/1000:8.3f} .. last end {wl_[1]/1000:8.3f} ms")
 print("step span", (last[-1].time_range.end - t_first)/1000)
+# idle gaps (> 8 us with NO kernel running) in the last step and what follows them
+iv = sorted((e.time_range.start, e.time_range.end, e.name.split("(")[0].split("<")[0][-40:]) for e in last)
+cur_end = iv[0][1]; idle = 0.0
+print("idle gaps > 8us:")
+for s0, e0, nm in iv[1:]:
+    if s0 - cur_end > 8:
+        print(f"   at {(s0 - t_first)/1000:7.3f} ms: {s0 - cur_end:6.1f} us before {nm}")
+    if s0 > cur_end: idle += s0 - cur_end
+    cur_end = max(cur_end, e0)
+print(f"total idle inside the step: {idle/1000:.3f} ms")
