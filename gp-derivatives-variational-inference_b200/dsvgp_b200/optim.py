@@ -57,7 +57,9 @@ class FusedAdam(torch.optim.Optimizer):
                 st["step"] += 1
                 step_t = float(st["step"])
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                tri = p.shape[0] if (id(p) in self._tri and p.dim() == 2 and p.shape[0] == p.shape[1]) else 0
+                # (with weight decay the strictly-upper entries are not fixed points of the update: visit everything)
+                tri = p.shape[0] if (id(p) in self._tri and p.dim() == 2 and p.shape[0] == p.shape[1]
+                                     and group["weight_decay"] == 0) else 0
                 per_dtype.setdefault(p.dtype, []).append((p, g, st["exp_avg"], st["exp_avg_sq"], gi, tri, step_t))
             b1, b2 = group["betas"]
             ghost[8 * gi: 8 * gi + 5] = [float(group["lr"]), float(b1), float(b2), float(group["eps"]),
