@@ -136,6 +136,7 @@ class Workspace:
         self.gVz = self.small[8 + M * d:].view(M * p, d) if p else None
         self.kl = torch.zeros(1, dtype=F64, device=device)
         self.scratch = e(8192, dt=F64)
+        self.scratch_kl = e(512, dt=F64)           # (its own partial-sum buffer: the KL runs on the side stream)
         self.H = e(Mq, self.ldg)[:, :Mq] if T == F32 else sq()
         self.X = sq()
         self.Xd = e(Mq, Mq, dt=F64) if T == F32 else self.X
@@ -467,15 +468,15 @@ class Engine:
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
                     self._assemble(ws, f, P, x, wx)
+                    ws.kl.zero_()                      # KL(q(u) || p(u)) needs the parameters only: also under the Cholesky
+                    ops.kl_divergence(P.m, P.Ls_raw, ws.kl, ws.scratch_kl)
                 cur.wait_stream(side)
             self._forward(ws, f, P, x, wx, through_likelihood, need_C=True, assembled=(extra == 0.0))
             ws.small.zero_()
-            ws.kl.zero_()
             if objective == "pll":
                 ops.pll_terms(ws.mu, ws.var, y, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
             else:
                 ops.elbo_terms(ws.mu, ws.var, y, f.hyp, 1.0 / nq_global, ws.gmu, ws.gvar, ws.sc, ws.scratch)
-            ops.kl_divergence(P.m, P.Ls_raw, ws.kl, ws.scratch)
             if want_grads:
                 self._backward(ws, f, P, x, wx, ws.gmu, ws.gvar, through_likelihood, 1.0 / num_data)
             elif self.reduce_hook is not None:
