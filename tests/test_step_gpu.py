@@ -500,9 +500,9 @@ def test_training_trajectory_agrees_across_tensor_core_paths():
     from dsvgp_b200 import engine, gp
     from dsvgp_b200.optim import FusedAdam
 
-    def run(use_tc, use_fp16):
-        old = (engine.USE_TC, engine.USE_FP16)
-        engine.USE_TC, engine.USE_FP16 = use_tc, use_fp16
+    def run(use_tc, use_fp16, dense_d=True):
+        old = (engine.USE_TC, engine.USE_FP16, engine.DENSE_D)
+        engine.USE_TC, engine.USE_FP16, engine.DENSE_D = use_tc, use_fp16, dense_d
         engine.ENGINE._ws.clear(), engine.ENGINE._fac.clear()
         try:
             wl = dict(bench.WORKLOADS["C3"], M=64, n=512, N=5000)
@@ -525,12 +525,13 @@ def test_training_trajectory_agrees_across_tensor_core_paths():
             assert ws.tc == use_tc and ws.tch == (use_tc and use_fp16)
             return losses, float(model.covar_module.base_kernel.lengthscale), float(vd.chol_variational_covar.abs().max())
         finally:
-            engine.USE_TC, engine.USE_FP16 = old
+            engine.USE_TC, engine.USE_FP16, engine.DENSE_D = old
             engine.ENGINE._ws.clear(), engine.ENGINE._fac.clear()
 
     ref, ell_ref, _ = run(False, False)            # mma.sync 3xTF32 with fp64 master sums
     assert all(math.isfinite(v) for v in ref) and ref[-1] < ref[0] - 1.0
-    for mode in ((True, True), (True, False)):
+    # 3xFP16 with one dense (S - I) A product (default), 3xFP16 with the two triangular products, 3xTF32
+    for mode in ((True, True, True), (True, True, False), (True, False, True)):
         got, ell, lmax = run(*mode)
         assert all(math.isfinite(v) for v in got), mode
         dev_rel = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(got, ref))
