@@ -17,6 +17,7 @@
 namespace dsvgp {
 
 constexpr int POTRF_THREADS = 512;
+static_assert(POTRF_THREADS == 512, "potrf_inv_block: warp 0 + a named barrier of 480 threads (warps 1-15), 16 x 32 mappings");
 
 void chol_plan(int Mq, int* Mp, int* nb0, int* nlev) {
   int k = 0;

@@ -99,7 +99,10 @@ int dsvgp_kdir_bwd_f32f64(const float* x1, const double* u1, const double* inv1,
  * (DirectionalGradVariationalStrategy.py:72-75) and TriangularLazyTensor.inv_matmul (:181,:183).
  * dsvgp_chol_plan: padded size Mp = nb0 << nlev for an Mq x Mq matrix.  dsvgp_pad_identity_f64 writes the identity
  * padding.  dsvgp_chol_f64: Awork (destroyed) -> L (lower), W = L^-1 (lower); *info (device int) = 0 or
- * 1 + index of the first non-positive pivot. */
+ * 1 + index of the first non-positive pivot.  The panel / trailing-update GEMMs of the factorisation run on a
+ * library-owned side stream (one per device) that is forked from and joined back into `s` with events: from the
+ * caller's point of view everything is ordered on `s`, there is still no host synchronisation, and the call stays
+ * CUDA-graph capturable.  Not re-entrant from two host threads on the same device at the same time. */
 void dsvgp_chol_plan(int Mq, int* Mp_host, int* nb0_host, int* nlev_host);
 int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t s);
 int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0, int nlev, int* info, dsvgp_stream_t s);
