@@ -142,6 +142,9 @@ CASES = [  # variant, n, d, M, p, dtype
     ("grad", 40, 5, 12, 5, F64),            # p = d > 3: runtime-p kernels
     ("dsvgp", 1, 2, 3, 1, F64),             # single point
     ("dsvgp", 65, 4, 29, 1, F32),           # M' = 58: padded Cholesky block
+    ("dsvgp", 95, 5, 43, 2, F32),           # tcgen05 path at ragged sizes: M' = 129, n' = 285
+    ("dsvgp", 300, 3, 65, 1, F32),          # M' = 130, n' = 600
+    ("dfree", 270, 7, 50, 2, F32),          # M' = 150, n' = 270 (values only)
 ]
 
 
