@@ -540,3 +540,28 @@ def test_training_trajectory_agrees_across_tensor_core_paths():
         dev_rel = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(got, ref))
         assert dev_rel < 2e-3, (mode, dev_rel)
         assert abs(ell - ell_ref) < 2e-3 * ell_ref
+
+
+def test_step_is_bitwise_deterministic():
+    """The step has no float atomics and a fixed reduction order, so identical inputs give bit-identical losses and
+    gradients -- which also makes this a race detector for the engine's and the Cholesky's side streams
+    (scratch/soak_determinism.py runs the long version at the bench sizes)."""
+    import bench
+    from dsvgp_b200 import gp
+    wl = dict(bench.WORKLOADS["C3"], M=128, n=1024, N=20000)            # M' = 384, n' = 3072: tcgen05 path, 4 Cholesky blocks
+    dev = torch.device("cuda", 0)
+    model, lik = bench.build_model(wl, F32, dev)
+    mll = gp.VariationalELBO(lik, model, num_data=(wl["d"] + 1) * wl["N"])
+    x, V, y = (t.to(dev) for t in bench.synth_batch(wl["n"], wl["d"], wl["p"], "dsvgp", F32, "cpu", 3))
+    params = list(model.parameters()) + list(lik.parameters())
+
+    def step():
+        for q in params:
+            q.grad = None
+        loss = -mll(lik(model(x, derivative_directions=V)), y)
+        loss.backward()
+        return torch.cat([loss.detach().reshape(1).double()] + [q.grad.reshape(-1).double() for q in params])
+    ref = step()
+    assert bool(torch.isfinite(ref).all())
+    for _ in range(12):
+        assert torch.equal(step(), ref)
