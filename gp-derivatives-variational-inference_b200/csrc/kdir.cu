@@ -1164,7 +1164,7 @@ int kdir_fwd(const T* x1, const TK* u1, int n1, int p1, const T* x2, const TK* w
   if (p1 == A && p2 == B)                                                                                      \
     return launch_fwd_v4<A, B>(x1, u1, n1, x2, w2, cidx2, canon_flag, n2, d, hyp, use_os, diag_add, K, ldk, Klo, st,          \
                                static_cast<__half*>(Kh), static_cast<__half*>(Kl), ldkh, hscale);
-      V4_CASE(1, 1) V4_CASE(2, 2) V4_CASE(1, 0) V4_CASE(2, 0) V4_CASE(3, 0)
+      V4_CASE(1, 1) V4_CASE(2, 2) V4_CASE(3, 3) V4_CASE(1, 0) V4_CASE(2, 0) V4_CASE(3, 0)
 #undef V4_CASE
     }
   }
