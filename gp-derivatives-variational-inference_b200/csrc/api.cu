@@ -91,6 +91,7 @@ int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* ma
 int dsvgp_split_half_f32(const float* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<float>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
 int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int mode, const float* scale, void* hi, void* lo, int64_t ldh, void* hiT, void* loT, int64_t ldhT, dsvgp_stream_t s) { return split_half<double>(src, lds, rows, cols, mode, scale, hi, lo, ldh, hiT, loT, ldhT, ST(s)); }
 int dsvgp_build_d_split_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo, int64_t ldh, dsvgp_stream_t s) { return build_d_split(E, lde, P, ldp, n, scale, hi, lo, ldh, ST(s)); }
+int dsvgp_build_d_absmax_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, unsigned int* out_bits, dsvgp_stream_t s) { return build_d_absmax(E, lde, P, ldp, n, out_bits, ST(s)); }
 int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s) {
   if (!x1 || !x2 || !hyp || !K || !Kh || !Kl || !hscale || (p1 > 0 && !u1) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;
   return kdir_fwd<float, float>(x1, u1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, diag_add, K, ldk, ST(s), cidx2, canon_flag, nullptr, Kh, Kl, ldkh, hscale);
@@ -130,9 +131,9 @@ int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
 
 #define PER_T(SUF, T)                                                                                              \
   int dsvgp_col_dots_##SUF(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm,    \
-                           T* pv, int nslab, dsvgp_stream_t s) {                                                   \
+                           T* pv, int nslab, unsigned int* cmax_bits, dsvgp_stream_t s) {                          \
     if (!A || !m || !pm || !pv) return DSVGP_ERR_ARG;                                                              \
-    return col_dots<T>(A, C, B, ld, rows, nq, m, pm, pv, nslab, ST(s));                                            \
+    return col_dots<T>(A, C, B, ld, rows, nq, m, pm, pv, nslab, cmax_bits, ST(s));                                 \
   }                                                                                                                \
   int dsvgp_predict_finish_##SUF(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp,           \
                                  double pred_jitter, int add_noise, double min_var, T* mu, T* var,                 \
@@ -171,6 +172,8 @@ int dsvgp_reduce_slabs(int rows, int cols) { return reduce_slabs(rows, cols); }
   }
 PER_T(f32, float)
 PER_T(f64, double)
+
+int dsvgp_dmma_peak_f64(int iters, int ctas, double* out, double* flops_host, dsvgp_stream_t s) { return dmma_peak(iters, ctas, out, flops_host, ST(s)); }
 
 int dsvgp_adam_step_f32(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s) { return adam_step<float>(ntensors, desc_host, ngroups, group_host, ST(s)); }
 int dsvgp_adam_step_f64(int ntensors, const int64_t* desc_host, int ngroups, const double* group_host, dsvgp_stream_t s) { return adam_step<double>(ntensors, desc_host, ngroups, group_host, ST(s)); }

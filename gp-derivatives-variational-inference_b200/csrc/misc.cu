@@ -121,12 +121,14 @@ __global__ void symmetrize_kernel(double* A, int64_t ld, int n) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 col_dots_kernel(const T* __restrict__ A, const T* __restrict__ C, int64_t ld, int rows, int nq,
-                const T* __restrict__ m, int rows_per_slab, T* __restrict__ pm, T* __restrict__ pv) {
+                const T* __restrict__ m, int rows_per_slab, T* __restrict__ pm, T* __restrict__ pv,
+                unsigned* __restrict__ cmax_bits) {
   __shared__ T sm[4][64], sv[4][64];
   const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + cl;
   const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
   T am = 0, av = 0;
+  float cm = 0.f;                       // max|C| seen by this thread (scale of the dA operand, csrc/tc_prep.cu)
   if (j < nq) {
     int i = r0 + rl;
     for (; i + 12 < r1; i += 16) {
@@ -140,13 +142,23 @@ col_dots_kernel(const T* __restrict__ A, const T* __restrict__ C, int64_t ld, in
       for (int q = 0; q < 4; ++q) {
         am += a[q] * m[i + 4 * q];
         av += a[q] * c[q];
+        cm = fmaxf(cm, fabsf((float)c[q]));
       }
     }
     for (; i < r1; i += 4) {
       const T a = A[(int64_t)i * ld + j];
       am += a * m[i];
-      if (C) av += a * C[(int64_t)i * ld + j];
+      if (C) {
+        const T c = C[(int64_t)i * ld + j];
+        av += a * c;
+        cm = fmaxf(cm, fabsf((float)c));
+      }
     }
+  }
+  if (cmax_bits != nullptr) {           // order-independent maximum on the bit pattern: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if ((threadIdx.x & 31) == 0 && cm > 0.f) atomicMax(cmax_bits, __float_as_uint(cm));
   }
   sm[rl][cl] = am;
   sv[rl][cl] = av;
@@ -569,13 +581,13 @@ int reduce_slabs(int rows, int cols) {
 
 template <typename T>
 int col_dots(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm, T* pv, int nslab,
-             cudaStream_t st) {
+             unsigned* cmax_bits, cudaStream_t st) {
   if (rows <= 0 || nq <= 0) return DSVGP_OK;
   if (nslab < 1) return DSVGP_ERR_ARG;
   const int rps = ceil_div(rows, nslab);
   dim3 grid(ceil_div(nq, 64), nslab);
   if (B) col_sqdiff_kernel<T><<<grid, 256, 0, st>>>(A, B, ld, rows, nq, m, rps, pm, pv);
-  else col_dots_kernel<T><<<grid, 256, 0, st>>>(A, C, ld, rows, nq, m, rps, pm, pv);
+  else col_dots_kernel<T><<<grid, 256, 0, st>>>(A, C, ld, rows, nq, m, rps, pm, pv, cmax_bits);
   CHECK_LAUNCH();
   return DSVGP_OK;
 }
@@ -682,12 +694,42 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
   return DSVGP_OK;
 }
 
+// ------------------------------------------------------------------------------------ fp64 tensor peak (measurement)
+// Register-resident DMMA m8n8k4 chains, 8 independent accumulators per warp, no memory traffic: what the fp64 tensor pipe
+// sustains on this device.  bench.py times it with CUDA events and uses the result as the roofline denominator of every
+// fp64 product (MEASURED_PEAKS.json has no fp64 figure).
+__global__ void __launch_bounds__(256)
+dmma_peak_kernel(double* __restrict__ out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == -1.0) out[0] = s;        // never true: keeps the chains alive
+}
+
+int dmma_peak(int iters, int ctas, double* out, double* flops_host, cudaStream_t st) {
+  if (iters <= 0 || ctas <= 0 || !out) return DSVGP_ERR_ARG;
+  dmma_peak_kernel<<<ctas, 256, 0, st>>>(out, iters);
+  CHECK_LAUNCH();
+  if (flops_host) *flops_host = (double)ctas * 8.0 /*warps*/ * (double)iters * 8.0 /*chains*/ * 512.0 /*2*8*8*4*/;
+  return DSVGP_OK;
+}
+
 #define INST(T)                                                                                                    \
   template int hyp_from_raw<T>(const T*, const T*, const T*, const T*, double*, cudaStream_t);                     \
   template int mirror_lower<T>(T*, int64_t, int, cudaStream_t);                                                    \
   template int tril_minus_eye<T>(const T*, int64_t, T*, int64_t, int, cudaStream_t);                                                    \
   template int add_outer<T>(T*, int64_t, int, const T*, const T*, double, cudaStream_t);                           \
-  template int col_dots<T>(const T*, const T*, const T*, int64_t, int, int, const T*, T*, T*, int, cudaStream_t);  \
+  template int col_dots<T>(const T*, const T*, const T*, int64_t, int, int, const T*, T*, T*, int, unsigned*, cudaStream_t);  \
   template int predict_finish<T>(const T*, const T*, int, int, int, const double*, double, int, double, T*, T*,    \
                                  cudaStream_t);                                                                    \
   template int elbo_terms<T>(const T*, const T*, const T*, int, const double*, double, double, T*, T*, double*,    \

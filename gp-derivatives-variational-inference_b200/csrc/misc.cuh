@@ -18,7 +18,7 @@ int symmetrize(double* A, int64_t ld, int n, cudaStream_t st);
 int reduce_slabs(int rows, int cols);
 template <typename T>
 int col_dots(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, const T* m, T* pm, T* pv, int nslab,
-             cudaStream_t st);
+             unsigned* cmax_bits, cudaStream_t st);
 template <typename T>
 int predict_finish(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter,
                    int add_noise, double min_var, T* mu, T* var, cudaStream_t st);
@@ -42,5 +42,7 @@ int kl_divergence(const T* m, const T* Ls, int64_t ld, int Mq, double* out, doub
 template <typename T>
 int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, const T* m, int Mq, double inv_nd, T* gm,
               T* gLs, int64_t ldg, cudaStream_t st);
+
+int dmma_peak(int iters, int ctas, double* out, double* flops_host, cudaStream_t st);
 
 }  // namespace dsvgp

@@ -20,4 +20,7 @@ int split_half(const S* src, int64_t lds, int rows, int cols, int mode, const fl
 int build_d_split(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo,
                   int64_t ldh, cudaStream_t st);
 
+// *out_bits = max(*out_bits, max |E + E^T + E E^T|) (bit pattern of a non-negative float): the measured bound of D
+int build_d_absmax(const float* E, int64_t lde, const float* P, int64_t ldp, int n, unsigned* out_bits, cudaStream_t st);
+
 }  // namespace dsvgp

@@ -684,12 +684,14 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
   if (b_kmajor) ok = ok && tc::map_kmajor(&mBh, Bh, ldb, N, K, bnl) && tc::map_kmajor(&mBl, Bl, ldb, N, K, bnl);
   else ok = ok && tc::map_mnmajor(&mBh, Bh, ldb, K, N, bnl) && tc::map_mnmajor(&mBl, Bl, ldb, K, N, bnl);
   if (!ok) return DSVGP_ERR_ARG;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                    // the attribute is PER DEVICE
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     if (cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<1>::SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(tc::gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess)
       return DSVGP_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   const int mtiles = cg == 2 ? ((ceil_div(M, tc::BM) + 1) & ~1) : ceil_div(M, tc::BM);   // whole CTA pairs
   auto launch = [&](const tc::Params& pp, int nz) {
@@ -747,12 +749,14 @@ int gemm_tch(const void* Ah_, const void* Al_, int64_t lda, const void* Bh_, con
   if (b_kmajor) ok = ok && tc::map_kmajor_h(&mBh, Bh, ldb, N, K, bnl) && tc::map_kmajor_h(&mBl, Bl, ldb, N, K, bnl);
   else ok = ok && tc::map_mnmajor_h(&mBh, Bh, ldb, K, N, bnl) && tc::map_mnmajor_h(&mBl, Bl, ldb, K, N, bnl);
   if (!ok) return DSVGP_ERR_ARG;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                    // the attribute is PER DEVICE
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     if (cudaFuncSetAttribute(tc::gemm_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<1>::SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(tc::gemm_tch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess)
       return DSVGP_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   const int mtiles = cg == 2 ? ((ceil_div(M, tc::BM) + 1) & ~1) : ceil_div(M, tc::BM);
   auto launch = [&](const tc::Params& pp, int nz) {

@@ -127,8 +127,9 @@ def _optimizers(model, likelihood, lr, lr_sched, n_samples, minibatch_size, num_
 def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1, minibatch_dim=1, num_epochs=1,
              learning_rate_hypers=0.01, learning_rate_ngd=0.1, inducing_data_initialization=True, use_ngd=False,
              use_ciq=False, lr_sched=None, mll_type="ELBO", num_contour_quadrature=15, watch_model=False, gamma=0.1,
-             verbose=True, fixed_inducing_locations=None, **args):
-    """Train a DSVGP (reference :93-268).  Returns (model, likelihood)."""
+             verbose=True, fixed_inducing_locations=None, _model_factory=None, **args):
+    """Train a DSVGP (reference :93-268).  Returns (model, likelihood).
+    (_model_factory: the sibling drivers that differ only in the model they build -- shared_directional_vi -- plug in here.)"""
     assert num_directions == minibatch_dim
     if use_ciq:
         raise NotImplementedError("use_ciq (contour-integral-quadrature whitening) is outside the B200 hot path")
@@ -143,9 +144,12 @@ def train_gp(train_dataset, num_inducing=128, num_directions=1, minibatch_size=1
     if fixed_inducing_locations is not None:
         inducing_points, learn_inducing_locations = fixed_inducing_locations, False
     dtype = train_dataset[0][0].dtype
-    model = GPModel(inducing_points.to(dtype), inducing_directions.to(dtype), dim,
-                    learn_inducing_locations=learn_inducing_locations,
-                    **({"variational_distribution": "NGD"} if use_ngd else {})).to(device=device, dtype=dtype)
+    mkw = dict(learn_inducing_locations=learn_inducing_locations, **({"variational_distribution": "NGD"} if use_ngd else {}))
+    if _model_factory is not None:
+        model = _model_factory(inducing_points.to(dtype), inducing_directions.to(dtype), dim, num_inducing, num_directions, **mkw)
+    else:
+        model = GPModel(inducing_points.to(dtype), inducing_directions.to(dtype), dim, **mkw)
+    model = model.to(device=device, dtype=dtype)
     likelihood = gp.GaussianLikelihood().to(device=device, dtype=dtype)
     model.train()
     likelihood.train()

@@ -16,7 +16,6 @@ The data term is normalised by the GLOBAL n' (the reference divides by the batch
 import torch
 import torch.distributed as dist
 
-from .engine import ENGINE
 
 
 def shard_bounds(n, rank, world_size):
@@ -27,23 +26,51 @@ def shard_bounds(n, rank, world_size):
 
 
 def all_reduce_payload(big, small, group=None):
-    """Sum the two engine buffers over `group`.  `big` may be None (forward-only evaluation of the ELBO)."""
+    """Sum the two engine buffers over `group` (blocking form).  `big` may be None (forward-only evaluation)."""
     if big is not None:
         dist.all_reduce(big, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
+
+
+class Reducer:
+    """The one exchange of a sharded step, split in two so that it hides under compute:
+
+        begin(big)   right after the Gram product: the all-reduce of [G | t] (37.8 MB at C3) is issued asynchronously --
+                     NCCL runs it on its own stream -- while the main stream goes on with dK_zx = L^-T dA and the K_zx
+                     assembly backward, neither of which needs G;
+        end(small)   after those: the small fp64 buffer they accumulated into follows, and the main stream then waits for
+                     both collectives before the replicated tail.
+
+    One Reducer per model (model.variational_strategy._reducer), so that other models of the process stay unsharded."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self._pending = None
+
+    def begin(self, big):
+        self._pending = dist.all_reduce(big, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def end(self, small):
+        w = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if self._pending is not None:
+            self._pending.wait()
+            self._pending = None
+        w.wait()
 
 
 def enable(model, n_global, group=None):
     """Make every subsequent ELBO step of `model` a shard of a global minibatch of `n_global` points."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    model.variational_strategy._n_global = int(n_global)
-    ENGINE.reduce_hook = lambda big, small: all_reduce_payload(big, small, group)
+    vs = model.variational_strategy
+    vs._n_global = int(n_global)
+    vs._reducer = Reducer(group)
 
 
 def disable(model):
-    model.variational_strategy._n_global = None
-    ENGINE.reduce_hook = None
+    vs = model.variational_strategy
+    vs._n_global = None
+    vs._reducer = None
 
 
 def broadcast_parameters(model, likelihood, src=0, group=None):

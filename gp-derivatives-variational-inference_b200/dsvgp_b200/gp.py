@@ -92,6 +92,24 @@ class MultivariateNormal:
         return self.loc.shape[-1:]
 
 
+class _LazyNormal(MultivariateNormal):
+    """MultivariateNormal whose dense covariance is only built when somebody looks at it (prior / variational q(u))."""
+
+    def __init__(self, mean, make_cov):
+        self.loc = mean
+        self._make_cov, self._cov = make_cov, None
+
+    @property
+    def covariance_matrix(self):
+        if self._cov is None:
+            self._cov = self._make_cov()
+        return self._cov
+
+    @property
+    def lazy_covariance_matrix(self):
+        return self.covariance_matrix
+
+
 # --------------------------------------------------------------------------------------------- kernel modules
 class _KDir(torch.autograd.Function):
     """K = RBFKernelDirectionalGrad(x1, x2; v1, v2, lengthscale) with the fused backward."""
@@ -402,7 +420,8 @@ class _ElboStep(torch.autograd.Function):
         want = any(ctx.needs_input_grad[4:])      # (grad mode is off inside forward; this is the reliable signal)
         elbo, grads, mean, var = ENGINE.elbo_step(P, x, Vx, y, cfg["num_data"], cfg["p"], cfg["p2"],
                                                   cfg["through_likelihood"], cfg.get("n_global"), want_grads=want,
-                                                  objective=cfg.get("objective", "elbo"))
+                                                  objective=cfg.get("objective", "elbo"), include_kl=cfg.get("include_kl", True),
+                                                  reducer=cfg.get("reducer"))
         ctx.grads = grads
         ctx.mark_non_differentiable(mean, var)
         return elbo.to(x.dtype), mean, var
@@ -431,13 +450,12 @@ class _Predictive(torch.autograd.Function):
         P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
         ectx, mean, var = ENGINE.predictive_forward(P, x, Vx, cfg["p"], cfg["p2"], cfg["add_noise"])
         ctx.ectx, ctx.P, ctx.x, ctx.cfg = ectx, P, x, cfg
-        ectx[0].generation = getattr(ectx[0], "generation", 0) + 1
-        ctx.generation = ectx[0].generation
+        ctx.generation = (ectx[0].generation, ectx[1].generation)     # bumped by EVERY later user of the workspace / factor
         return mean, var
 
     @staticmethod
     def backward(ctx, gmu, gvar):
-        if ctx.ectx[0].generation != ctx.generation:
+        if (ctx.ectx[0].generation, ctx.ectx[1].generation) != ctx.generation:
             raise RuntimeError("dsvgp_b200: the predictive workspace was overwritten by a later forward pass before "
                                "backward ran; call backward before evaluating the model again on the same shape")
         grads = ENGINE.predictive_backward(ctx.ectx, ctx.P, ctx.x, gmu, gvar, ctx.cfg["add_noise"])
@@ -528,6 +546,14 @@ class PredictiveDistribution:
 
 
 # ------------------------------------------------------------------------------------------------ objectives
+def _target_like(target, x):
+    """The labels in the model's dtype (torch would promote `y - mean` silently in the reference; the kernels read raw
+    memory, so the cast is explicit).  A device mismatch is an error, as it is in the reference."""
+    if target.device != x.device:
+        raise RuntimeError(f"the target is on {target.device}, the model output on {x.device}")
+    return target.to(x.dtype).contiguous()
+
+
 class VariationalELBO(Module):
     """gpytorch.mlls.VariationalELBO(likelihood, model, num_data): (dist, target) -> scalar
     (1/n') sum_j E_q[log p(y_j | f_j)] - KL(q(u) || p(u)) / num_data."""
@@ -543,10 +569,13 @@ class VariationalELBO(Module):
             raise TypeError("VariationalELBO expects the distribution returned by model(x, ...) or likelihood(model(x, ...))")
         st = dist._strategy
         cfg = dict(p=st._p(), p2=st._p2(), num_data=float(self.num_data) / float(self.beta),
-                   through_likelihood=dist._noise_mult, n_global=st._n_global)
+                   through_likelihood=dist._noise_mult, n_global=st._n_global, include_kl=not st._external_kl,
+                   reducer=st._reducer)
         params = st._param_list(self.likelihood)
-        elbo, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, target.contiguous(), *params)
+        elbo, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, _target_like(target, dist._x), *params)
         dist._cache = (mean, var)      # train loops print output.mean / output.variance (directional_vi.py:256-257)
+        if st._external_kl:            # q(u) is not over the M(p+1) inducing values the step saw: KL by autograd, M'^2 work
+            elbo = elbo - st.kl_divergence().to(elbo.dtype) / cfg["num_data"]
         return elbo
 
 
@@ -565,9 +594,12 @@ class PredictiveLogLikelihood(Module):
             raise TypeError("PredictiveLogLikelihood expects the distribution returned by model(x, ...) or likelihood(model(x, ...))")
         st = dist._strategy
         cfg = dict(p=st._p(), p2=st._p2(), num_data=float(self.num_data) / float(self.beta), objective="pll",
-                   through_likelihood=dist._noise_mult + 1, n_global=st._n_global)
+                   through_likelihood=dist._noise_mult + 1, n_global=st._n_global, include_kl=not st._external_kl,
+                   reducer=st._reducer)
         params = st._param_list(self.likelihood)
-        val, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, target.contiguous(), *params)
+        val, mean, var = _ElboStep.apply(cfg, dist._x, dist._Vx, _target_like(target, dist._x), *params)
+        if st._external_kl:
+            val = val - st.kl_divergence().to(val.dtype) / cfg["num_data"]
         # the step's variance carries log_marginal's extra noise; `dist` itself (what the loop prints, :256-257) does not
         dist._cache = (mean, (var - self.likelihood.noise.detach().to(var.dtype)).clamp_min(
             1e-10 if var.dtype == torch.float64 else 1e-6))
@@ -619,8 +651,24 @@ class _DirectionalStrategyBase(Module):
         self.register_buffer("variational_params_initialized", torch.tensor(0))
         self.register_buffer("updated_strategy", torch.tensor(True))
         self._register_load_state_dict_pre_hook(_ensure_updated_strategy_flag_set, with_module=True)
-        self._n_global = None          # set by distributed.shard(): global minibatch size of a sharded step
+        self._n_global = None          # set by distributed.enable(): global minibatch size of a sharded step ...
+        self._reducer = None           # ... and the object that sums its payload over ranks (per model, not per process)
         self._flags_checked = False    # host-side memo of the two flag buffers (reset by load_state_dict)
+        self._external_kl = False      # True: the fused step leaves the KL term to autograd (shared-direction strategy)
+
+    @property
+    def variational_distribution(self):
+        """q(u) = N(m, L_s L_s^T) (gpytorch _VariationalStrategy.variational_distribution, used by DGVS.py:222)."""
+        m, Ls = self._variational_distribution.mean_and_chol()
+        return _LazyNormal(m, lambda: Ls.tril() @ Ls.tril().transpose(-1, -2))
+
+    @property
+    def prior_distribution(self):
+        """p(u) = N(0, I) of the whitened parameterisation (DGVS.py:77-87)."""
+        vd = self._variational_distribution
+        ref = next(vd.parameters())
+        zeros = torch.zeros(vd.shape(), dtype=ref.dtype, device=ref.device)
+        return _LazyNormal(zeros, lambda: torch.eye(zeros.numel(), dtype=ref.dtype, device=ref.device))
 
     # ---- shape helpers
     def _p(self):
@@ -654,9 +702,15 @@ class _DirectionalStrategyBase(Module):
         raise NotImplementedError
 
     def forward(self, x, inducing_points, inducing_values, variational_inducing_covar=None, **kwargs):
-        """Same signature as the reference forward (DGVS.py:89); the inducing arguments are the module's own
-        parameters and are read from the module."""
+        """Same signature as the reference forward (DGVS.py:89).  The fused step reads the inducing points / values from
+        the module's own parameters, so anything else in those arguments is refused rather than silently ignored."""
         Vx = self._data_directions(x, kwargs)
+        own_m = getattr(self._variational_distribution, "variational_mean", None)
+        if (inducing_points is not None and inducing_points is not self.inducing_points) or \
+                variational_inducing_covar is not None or (inducing_values is not None and inducing_values is not own_m):
+            raise NotImplementedError("dsvgp_b200 strategies evaluate q(f) with the module's own inducing points and variational "
+                                      "parameters; foreign inducing_points / inducing_values / variational_inducing_covar "
+                                      "arguments are not supported -- load them into the module instead")
         return PredictiveDistribution(self, x.contiguous(), Vx)
 
     def _rewhiten_legacy_parameters(self):
@@ -722,6 +776,47 @@ class DirectionalGradVariationalStrategy(_DirectionalStrategyBase):
         assert num_derivative_directions == self._p(), "Need minibatch dim to be same as number of directions for kernel"
         self.model.covar_module.base_kernel.set_num_directions(self._p())
         return derivative_directions.to(device=x.device, dtype=x.dtype).contiguous()
+
+
+class SharedDirectionalGradVariationalStrategy(DirectionalGradVariationalStrategy):
+    """Drop-in for directionalvi/SharedDirectionalGradVariationalStrategy.py:32-259 (exported there under the name
+    DirectionalGradVariationalStrategy, shared_directional_vi.py:13): ONE set of p inducing directions shared by all
+    inducing points (`inducing_directions` is (p, d), repeated per point :95-98), a variational distribution over
+    M + p values -- M function values and p shared directional-derivative values, expanded to the M(p+1) inducing values
+    [m_i, g_1..g_p] (:99-105) -- and, as shipped, a middle term overwritten with zeros (:209-211): the predictive
+    covariance is the prior's K_xx + 1e-4 I, so L_s only enters the objective through the KL term.
+
+    Runs on the same fused step: the expansion of (V, m) is differentiable torch glue (M' numbers), the step is given
+    L_s = I (so (S - I) A vanishes identically, which IS the zeroed middle term) and leaves the KL of the (M + p)-variate
+    q(u) to autograd."""
+
+    def __init__(self, model, inducing_points, inducing_directions, variational_distribution,
+                 learn_inducing_locations=True):
+        super().__init__(model, inducing_points, inducing_directions, variational_distribution, learn_inducing_locations)
+        self._external_kl = True
+        self._eye = None
+
+    def _p(self):
+        return int(self.inducing_directions.size(-2))
+
+    def _param_list(self, likelihood):
+        vd, model = self._variational_distribution, self.model
+        raw_noise = likelihood.noise_covar.raw_noise if likelihood is not None else None
+        m, _ = vd.mean_and_chol()
+        Z, V = self.inducing_points, self.inducing_directions
+        M, p = Z.shape[0], V.shape[0]
+        if m.numel() != M + p:
+            raise ValueError(f"the shared-direction strategy needs a variational distribution over M + p = {M + p} values, "
+                             f"got {m.numel()}")
+        m_full = torch.cat([m[:M, None], m[M:].expand(M, p)], 1).reshape(-1)                  # :99-105
+        Mq = M * (p + 1)
+        if self._eye is None or self._eye.shape[0] != Mq or self._eye.device != Z.device or self._eye.dtype != Z.dtype:
+            self._eye = torch.eye(Mq, dtype=Z.dtype, device=Z.device)
+        return (Z, V.repeat(M, 1), m_full, self._eye, model.mean_module.constant, model.covar_module.raw_outputscale,
+                model.covar_module.base_kernel.raw_lengthscale, raw_noise)
+
+    def _rewhiten_legacy_parameters(self):
+        raise NotImplementedError("un-whitened legacy checkpoints are not supported by the shared-direction strategy")
 
 
 class DFreeDirectionalGradVariationalStrategy(DirectionalGradVariationalStrategy):

@@ -168,6 +168,11 @@ def build_d_split(E, P, scale, hi, lo, n=None):
     call("dsvgp_build_d_split_f32", E, _ld(E), P, _ld(P), E.shape[0] if n is None else n, scale, hi, lo, _ld(hi))
 
 
+def build_d_absmax(E, P, out_bits, n=None):
+    """out_bits = max(out_bits, bits of max|E + E^T + E E^T|) from the lower triangles of E and P = E E^T."""
+    call("dsvgp_build_d_absmax_f32", E, _ld(E), P, _ld(P), E.shape[0] if n is None else n, out_bits)
+
+
 def kdir_fwd_half(x1, u1, p1, x2, w2, p2, hyp, K, Kh, Kl, hscale, canon=None, use_os=True):
     """K_zx assembly that writes only the two-half split of K * hscale; returns True if it did (else K was written)."""
     n1, d = x1.shape
@@ -255,11 +260,12 @@ def reduce_slabs(rows, cols):
     return call_raw("dsvgp_reduce_slabs", rows, cols)
 
 
-def col_dots(A, m, pm, pv, rows, nq, C=None, Bp=None):
-    """pm = A^T m partials; pv = sum A*C (C given) or sum Bp*(2A + Bp) (Bp = B - A given)."""
+def col_dots(A, m, pm, pv, rows, nq, C=None, Bp=None, cmax=None):
+    """pm = A^T m partials; pv = sum A*C (C given) or sum Bp*(2A + Bp) (Bp = B - A given).
+    cmax (1-element int32 device tensor, zeroed by the caller): receives the bits of max|C|."""
     B = Bp
     nslab = pm.shape[0]
-    call("dsvgp_col_dots_" + suffix(A.dtype), A, C, B, _ld(A), rows, nq, m, pm, pv, nslab)
+    call("dsvgp_col_dots_" + suffix(A.dtype), A, C, B, _ld(A), rows, nq, m, pm, pv, nslab, cmax if C is not None else None)
 
 
 def predict_finish(pm, pv, nq, p2, hyp, mu, var, add_noise, pred_jitter=1e-4):

@@ -139,8 +139,10 @@ int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* 
  *   gives +inf); mode 0: all entries, 2: the entries of tril(x) - I.
  * dsvgp_tc_scales_f32: power-of-two scales (device float[16]) of every operand of a step from rigorous a-priori bounds
  *   (list in csrc/tc_prep.cu): [0] W [1] K_zx [2] E [3] A [4] B [5] dA [6] A_g [7] D = S - I, [8..13] the reciprocal products
- *   1/(sW sK), 1/(sE sA), 1/(sE sB), 1/(sW sdA), 1/(sAg sA), 1/(sD sA).  maxbits (device uint[4]) = absmax bits of E, m, g_mu, g_var.
- *   stage 0 fills what the forward pass needs (hyp, jitter, maxbits[0]), stage 1 the rest.
+ *   1/(sW sK), 1/(sE sA), 1/(sE sB), 1/(sW sdA), 1/(sAg sA), 1/(sD sA).  maxbits (device uint[8]) = absmax bits of E, m, g_mu,
+ *   g_var, and the MEASURED maxima of D = S - I ([4]) and C = (S - I) A ([5]; 0 = fall back to the a-priori bound).
+ *   stage 0 fills what the forward pass needs (hyp, jitter, maxbits[0]), stage 2 re-makes the scale of D from maxbits[4],
+ *   stage 1 the backward scales (dA from max|m| max|g_mu| + 2 max|g_var| max|C|).
  * dsvgp_split_half_*: (hi, lo) = two-half split of op(src) * *scale, optionally also of its transpose (hiT, loT);
  *   mode 0: src, 1: tril(src), 2: tril(src) - I.
  * dsvgp_kdir_fwd_half_f32: dsvgp_kdir_fwd_canon_f32 that writes ONLY the split (Kh, Kl) of K * *hscale; returns 2 when
@@ -154,6 +156,9 @@ int dsvgp_split_half_f64(const double* src, int64_t lds, int rows, int cols, int
 /* (hi, lo) = two-half split of D * *scale with D = S - I = E + E^T + E E^T (symmetric), from the lower triangles of
  * E = tril(L_s) - I and P = E E^T: the operand of the single dense product C = (S - I) A of the training step. */
 int dsvgp_build_d_split_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, const float* scale, void* hi, void* lo, int64_t ldh, dsvgp_stream_t s);
+/* *out_bits = max(*out_bits, max|D_ij|) for the same D (measured, so that the scale of D stays tight when q(u) is far from
+ * N(0, I)); feed it to dsvgp_tc_scales_f32 as maxbits[4] with stage 2 before dsvgp_build_d_split_f32. */
+int dsvgp_build_d_absmax_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, unsigned int* out_bits, dsvgp_stream_t s);
 int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s);
 int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s);
 /* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles
@@ -183,10 +188,12 @@ int dsvgp_symmetrize_f64(double* A, int64_t ld, int n, dsvgp_stream_t s);
 /* predictive mean / diagonal variance (DirectionalGradVariationalStrategy.py:188,:192-205):
  *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or, with B' = B - A given in
  *   the `B` slot, sum B'_ij (2 A_ij + B'_ij) = sum (B_ij^2 - A_ij^2)
- *   mu_j = sum_s pm + c ; var_j = kdiag_j + pred_jitter + sum_s pv [+ noise], clamped at min_var. */
+ *   mu_j = sum_s pm + c ; var_j = kdiag_j + pred_jitter + sum_s pv [+ noise], clamped at min_var.
+ *   cmax_bits (optional, C given): *cmax_bits = max(*cmax_bits, max|C_ij|) as float bits -- the measured bound the
+ *   3xFP16 scale of dA is made from (dsvgp_tc_scales_f32 maxbits[5]). */
 int dsvgp_reduce_slabs(int rows, int cols);
-int dsvgp_col_dots_f32(const float* A, const float* C, const float* B, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, dsvgp_stream_t s);
-int dsvgp_col_dots_f64(const double* A, const double* C, const double* B, int64_t ld, int rows, int nq, const double* m, double* pm, double* pv, int nslab, dsvgp_stream_t s);
+int dsvgp_col_dots_f32(const float* A, const float* C, const float* B, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, unsigned int* cmax_bits, dsvgp_stream_t s);
+int dsvgp_col_dots_f64(const double* A, const double* C, const double* B, int64_t ld, int rows, int nq, const double* m, double* pm, double* pv, int nslab, unsigned int* cmax_bits, dsvgp_stream_t s);
 int dsvgp_predict_finish_f32(const float* pm, const float* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter, int add_noise, double min_var, float* mu, float* var, dsvgp_stream_t s);
 int dsvgp_predict_finish_f64(const double* pm, const double* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter, int add_noise, double min_var, double* mu, double* var, dsvgp_stream_t s);
 
@@ -221,6 +228,12 @@ int dsvgp_kl_f64(const double* m, const double* Ls_raw, int64_t ld, int Mq, doub
 /* gm = t - m/num_data ; gLs = tril(2 H^T) - (tril(Ls) - diag(1/Ls_ii))/num_data  (H = Ls^T G) */
 int dsvgp_var_grads_f32(const float* H, int64_t ldh, const float* Ls_raw, int64_t ldl, const float* t, const float* m, int Mq, double inv_num_data, float* gm, float* gLs, int64_t ldg, dsvgp_stream_t s);
 int dsvgp_var_grads_f64(const double* H, int64_t ldh, const double* Ls_raw, int64_t ldl, const double* t, const double* m, int Mq, double inv_num_data, double* gm, double* gLs, int64_t ldg, dsvgp_stream_t s);
+
+/* Measurement aid (bench.py): `ctas` CTAs of 8 warps each run `iters` rounds of 8 independent register-resident DMMA
+ * m8n8k4 chains -- no memory traffic -- so that flops / elapsed time is the fp64 tensor-pipe peak of THIS device, the
+ * roofline denominator of the fp64 products (Cholesky updates, Cholesky backward, every product of an fp64 model).
+ * *flops_host (HOST double, optional) receives the flop count of the launch; out: device double[1] (never written). */
+int dsvgp_dmma_peak_f64(int iters, int ctas, double* out, double* flops_host, dsvgp_stream_t s);
 
 /* ---- optimiser step ------------------------------------------------------------
  * One launch of a fused multi-tensor Adam over every tensor of an optimiser: replaces torch.optim.Adam.step() of the

@@ -39,6 +39,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     import directional_vi as ref_dsvgp  # noqa: E402  (reference file)
     import dfree_directional_vi as ref_dfree  # noqa: E402  (reference file)
     import grad_svgp as ref_grad  # noqa: E402  (reference file)
+    import shared_directional_vi as ref_shared  # noqa: E402  (reference file; SharedDirectionalGradVariationalStrategy.py)
 
 
 def kernel_case(n1, n2, d, p, dtype, seed, same=False):
@@ -131,6 +132,37 @@ def strategy_case(variant, n, d, M, p, dtype, seed, perturb_dirs=True):
         torch.set_default_dtype(torch.float32)
 
 
+def shared_case(n, d, M, p, dtype, seed):
+    """shared_directional_vi.GPModel (one direction set for all inducing points, M + p variational values, middle term
+    zeroed -- SharedDirectionalGradVariationalStrategy.py:95-108, :209-212): one training step and one eval prediction."""
+    P, x, Vx, y, num_data = O.make_shared_problem(n, d, M, p, dtype, seed)
+    torch.set_default_dtype(dtype)        # the reference builds `iv = torch.zeros(...)` in the default dtype (:100)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref_shared.GPModel(P.Z, P.Vz, d)
+        likelihood = gpytorch.likelihoods.GaussianLikelihood()
+        model, likelihood = model.to(dtype), likelihood.to(dtype)
+        _load(model, likelihood, P, "shared")
+        model.train(), likelihood.train()
+        kwargs = {"derivative_directions": Vx}
+        mll = gpytorch.mlls.VariationalELBO(likelihood, model, num_data=num_data)
+        output = likelihood(model(x, **kwargs))
+        loss = -mll(output, y)
+        loss.backward()
+        grads = {k: -v for k, v in _grads(model, likelihood, "shared").items()}
+        res = dict(variant="shared", n=n, d=d, M=M, p=p, seed=seed, num_data=num_data, x=x, Vx=Vx, y=y, params=P.tensors(),
+                   elbo=(-loss).detach().clone(), grads=grads, train_mean=output.mean.detach().clone(),
+                   train_variance=output.variance.detach().clone())
+        model.eval(), likelihood.eval()
+        with torch.no_grad():
+            preds = likelihood(model(x, **kwargs))
+            res["pred_mean"], res["pred_variance"] = preds.mean.clone(), preds.variance.clone()
+            res["pred_covariance"] = preds.covariance_matrix.clone()
+        return res
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 def ngd_case(n, d, M, p, dtype, seed):
     """The reference model with variational_distribution="NGD" (directional_vi.py:38-40): one training step through
     NaturalVariationalDistribution; the gradients of natural_vec / natural_mat are the natural gradients that
@@ -180,6 +212,12 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     f64, f32 = torch.float64, torch.float32
+    shared = {"shared_d3_p2_f64": shared_case(30, 3, 8, 2, f64, 31), "shared_d3_p2_f32": shared_case(30, 3, 8, 2, f32, 31),
+              "shared_d5_p1_f64": shared_case(25, 5, 12, 1, f64, 32), "shared_d6_p3_f32": shared_case(40, 6, 10, 3, f32, 33)}
+    torch.save(shared, os.path.join(out_dir, "shared_cases.pt"))
+    print("shared_cases.pt", {k: float(v["elbo"]) for k, v in shared.items()})
+    if "--shared-only" in sys.argv:
+        return
     kernels = {
         "k_d2_p2_f64": kernel_case(7, 9, 2, 2, f64, 1),
         "k_d3_p1_f64": kernel_case(8, 5, 3, 1, f64, 2),

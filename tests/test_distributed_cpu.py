@@ -43,8 +43,14 @@ def _worker(rank, world, port, n, d, M, p, out):
         small = torch.cat([val.detach().reshape(1)] + [g.reshape(-1) for g in grads])
         big = torch.zeros(4, dtype=torch.float64)          # stands for [G | t]; only its summation is checked here
         big[rank] = 1.0
-        distributed.all_reduce_payload(big, small)
+        reducer = distributed.Reducer()                    # the two-phase form the engine drives: begin([G|t]) ... end(small)
+        reducer.begin(big)
+        reducer.end(small)
         assert torch.equal(big[:world], torch.ones(world, dtype=torch.float64))
+        chk_b, chk_s = torch.ones(3, dtype=torch.float64), torch.full((2,), float(rank), dtype=torch.float64)
+        distributed.all_reduce_payload(chk_b, chk_s)       # blocking form
+        assert torch.equal(chk_b, torch.full((3,), float(world), dtype=torch.float64))
+        assert torch.equal(chk_s, torch.full((2,), float(sum(range(world))), dtype=torch.float64))
         # replicated tail: the KL term is added once on every rank, never reduced
         Q2 = P.clone().requires_grad_(True)
         kl = O.kl_divergence(Q2) / nd

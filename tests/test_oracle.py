@@ -203,3 +203,48 @@ def test_ngd_natural_gradients_match_reference_model(name):
     # gpytorch.optim.NGD.step with lr = 0.1 (loss = -ELBO, so the step adds lr*num_data*dELBO)
     after = c["natural_vec"] + 0.1 * c["num_data"] * c["grad_natural_vec"]
     assert rel(after, c["natural_vec_after"]) < (1e-12 if f64 else 1e-5)
+
+
+SHARED = torch.load(os.path.join(GOLD, "shared_cases.pt"))
+
+
+@pytest.mark.parametrize("structure", ["lean", "reference"])
+@pytest.mark.parametrize("name", sorted(SHARED))
+def test_shared_strategy_matches_reference_file(name, structure):
+    """variant="shared" of the oracle against the unmodified SharedDirectionalGradVariationalStrategy.py /
+    shared_directional_vi.GPModel (one direction set, M + p variational values, zeroed middle term)."""
+    c = SHARED[name]
+    P = O.Params(**{k: v.clone() for k, v in c["params"].items()})
+    f64 = c["x"].dtype == torch.float64
+    tol_v, tol_g = (1e-9, 1e-7) if f64 else (1e-4, 1e-4)
+    val, grads = O.elbo_and_grads(P, c["x"], c["Vx"], c["y"], c["num_data"], "shared", structure)
+    assert abs(float(val - c["elbo"])) / abs(float(c["elbo"])) < tol_v
+    for k, g in c["grads"].items():
+        assert rel(grads[k].reshape(g.shape), g) < tol_g, (k, rel(grads[k].reshape(g.shape), g))
+    mean, var = O.predict(P, c["x"], c["Vx"], "shared", structure)
+    assert rel(mean, c["pred_mean"]) < (1e-9 if f64 else 1e-4)
+    assert rel(var, c["pred_variance"]) < (1e-9 if f64 else 1e-4)
+    _, cov = O.predictive_full(P, c["x"], c["Vx"], "shared", add_noise=True)
+    assert rel(cov, c["pred_covariance"]) < (1e-9 if f64 else 1e-4)
+    # the quirk itself: the predictive variance is the prior's (S never enters it)
+    assert rel(var - O.noise(P), O.outputscale(P) * O.kernel_diag(c["n"], c["p"], O.lengthscale(P)) + 1e-4) < 1e-6
+
+
+def test_trained_state_generator_is_far_from_prior():
+    for kind in ("optimal", "rough"):
+        P, x, Vx, y, nd = O.make_trained_problem(64, 3, 24, 2, torch.float64, seed=1, ell=0.7, kind=kind)
+        Ls = O.chol_factor_of_q(P)
+        assert float((Ls - torch.eye(Ls.shape[0], dtype=Ls.dtype)).abs().max()) > 0.3
+        assert float(P.m.abs().max()) > 0.5 and float(Ls.diagonal().min()) > 0
+        v, g = O.elbo_and_grads(P, x, Vx, y, nd)
+        assert torch.isfinite(v) and all(torch.isfinite(t).all() for t in g.values())
+
+
+def test_chunked_oracle_equals_unchunked():
+    P, x, Vx, y, nd = O.make_problem(150, 4, 20, 2, torch.float64, 3, N=3000)
+    v, g = O.elbo_and_grads(P, x, Vx, y, nd)
+    v2, g2, mean, var = O.elbo_and_grads_chunked(P, x, Vx, y, nd, chunk=47)
+    assert abs(float(v) - float(v2)) < 1e-12 * abs(float(v))
+    assert max(rel(g2[k], g[k]) for k in g) < 1e-11
+    m0, v0 = O.predict(P, x, Vx)
+    assert rel(mean, m0) < 1e-13 and rel(var, v0) < 1e-13

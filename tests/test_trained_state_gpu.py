@@ -1,0 +1,143 @@
+"""Parity where round 1 had none:
+
+  * q(u) FAR from N(0, I) -- a converged-looking state (oracle.make_trained_problem) and an unstructured rough one --
+    at BASELINE.json's full inducing sizes, on the default 3xFP16 tensor-core path, 1e-4 against the fp64 oracle on the
+    ELBO, every gradient, the predictive mean and variance;
+  * the benchmark's own minibatch (n = 16384 per GPU: split-K Gram product, evict-first stores, slab reductions take other
+    branches than at n = 512) against the chunked fp64 oracle;
+  * two forwards before one backward (the gradients an fp64 step hands to autograd must not alias the workspace);
+  * dtype / shape mismatches raise instead of reinterpreting memory.
+"""
+import pytest
+import torch
+
+from oracle import dsvgp_oracle as O
+from test_step_gpu import F32, F64, build, check_against, grads_of, rel, run_step
+
+pytestmark = pytest.mark.gpu
+
+TRAINED = [  # variant, n, d, M, p, dtype, lengthscale, kind
+    ("dsvgp", 512, 10, 1024, 2, F32, 0.7, "optimal"),      # C3, full M' = 3072
+    ("dsvgp", 512, 10, 1024, 2, F32, 0.15, "optimal"),
+    ("dsvgp", 512, 10, 1024, 2, F32, 2.0, "optimal"),
+    ("dsvgp", 512, 10, 1024, 2, F32, 0.7, "rough"),
+    ("dsvgp", 512, 60, 800, 3, F32, 2.0, "optimal"),       # C4, full M' = 3200
+    ("dsvgp", 512, 60, 800, 3, F32, 0.7, "rough"),
+    ("dfree", 512, 18, 1024, 2, F32, 0.7, "optimal"),      # C5, full M' = 3072
+    ("dfree", 512, 18, 1024, 2, F32, 2.0, "rough"),
+    ("dsvgp", 500, 3, 512, 1, F64, 0.15, "optimal"),       # C2 (fp64 throughout), full M' = 1024
+    ("dsvgp", 500, 3, 512, 1, F64, 0.7, "rough"),
+    ("dsvgp", 300, 10, 96, 2, F32, 0.7, "optimal"),        # small shapes of every variant (fast)
+    ("dsvgp", 300, 10, 96, 2, F64, 2.0, "rough"),
+    ("grad", 60, 3, 33, 3, F32, 0.7, "optimal"),
+    ("grad", 60, 3, 33, 3, F64, 0.15, "rough"),
+]
+
+
+@pytest.mark.parametrize("variant,n,d,M,p,dtype,ell,kind", TRAINED)
+def test_trained_state_matches_oracle(variant, n, d, M, p, dtype, ell, kind):
+    P, x, Vx, y, num_data = O.make_trained_problem(n, d, M, p, dtype, seed=2, variant=variant, ell=ell, kind=kind, N=100 * n)
+    Ls = O.chol_factor_of_q(P)
+    far = float((Ls - torch.eye(Ls.shape[0], dtype=Ls.dtype)).abs().max())
+    assert far > 0.3 and float(P.m.abs().max()) > 0.5, (far, float(P.m.abs().max()))      # really far from N(0, I)
+    up = lambda t: None if t is None else t.double()
+    P64 = P.clone(F64)
+    ref_val, ref_grads = O.elbo_and_grads(P64, up(x), up(Vx), up(y), num_data, variant)
+    model, lik, val, grads, out = run_step(variant, P, x, Vx, y, num_data, d, dtype)
+    f64 = dtype == F64
+    check_against(val, grads, ref_val, ref_grads, 1e-10 if f64 else 1e-4, 1e-9 if f64 else 1e-4)
+    mean, var = O.predict(P64, up(x), up(Vx), variant)
+    assert rel(out.mean, mean) < (1e-10 if f64 else 1e-4)
+    assert rel(out.variance, var) < (1e-10 if f64 else 1e-4)
+    model.eval(), lik.eval()
+    with torch.no_grad():
+        kw = {} if variant == "grad" else {"derivative_directions": Vx}
+        preds = lik(model(x.cuda(), **kw))
+    assert rel(preds.mean, mean) < (1e-10 if f64 else 1e-4)
+    assert rel(preds.variance, var) < (1e-10 if f64 else 1e-4)
+
+
+@pytest.mark.parametrize("kind", ["near_identity", "optimal"])
+def test_bench_size_matches_chunked_oracle(kind):
+    """C3 at the benchmark's per-GPU minibatch (n = 16384, n' = 49152, M' = 3072) against the fp64 oracle evaluated
+    chunk by chunk on the host (about a minute of host time)."""
+    variant, n, d, M, p = "dsvgp", 16384, 10, 1024, 2
+    if kind == "near_identity":
+        P, x, Vx, y, num_data = O.make_problem(n, d, M, p, F32, seed=4, variant=variant, N=1000000)
+    else:
+        P, x, Vx, y, num_data = O.make_trained_problem(n, d, M, p, F32, seed=4, variant=variant, ell=0.7, kind=kind,
+                                                       N=1000000, weight=3.0)
+    up = lambda t: None if t is None else t.double()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref_val, ref_grads, mean, var = O.elbo_and_grads_chunked(P.clone(F64), up(x), up(Vx), up(y), num_data, variant, chunk=2048)
+    model, lik, val, grads, out = run_step(variant, P, x, Vx, y, num_data, d, F32)
+    check_against(val, grads, ref_val, ref_grads, 1e-4, 1e-4)
+    assert rel(out.mean, mean) < 1e-4 and rel(out.variance, var) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+def test_two_forwards_then_one_backward(dtype):
+    """(l1 + l2).backward() with both forwards done first: the second step must not clobber the gradients the first one
+    saved (for an fp64 model they used to be views of the workspace the next step zeroes)."""
+    from dsvgp_b200 import gp
+    n, d, M, p = 96, 3, 24, 2
+    P, x, Vx, y, nd = O.make_problem(2 * n, d, M, p, dtype, seed=9, N=5000)
+    model, lik = build("dsvgp", P, d, dtype)
+    model.train(), lik.train()
+    mll = gp.VariationalELBO(lik, model, num_data=nd)
+    q = p + 1
+    xs, Vs, ys = (x[:n], x[n:]), (Vx[: n * p], Vx[n * p:]), (y[: n * q], y[n * q:])
+    l1 = mll(lik(model(xs[0].cuda(), derivative_directions=Vs[0])), ys[0].cuda())
+    l2 = mll(lik(model(xs[1].cuda(), derivative_directions=Vs[1])), ys[1].cuda())
+    (l1 + l2).backward()
+    got = grads_of(model, lik)
+    up = lambda t: t.double()
+    tot = None
+    for k in range(2):
+        _, g = O.elbo_and_grads(P.clone(F64), up(xs[k]), up(Vs[k]), up(ys[k]), nd)
+        tot = g if tot is None else {a: tot[a] + g[a] for a in g}
+    for k, g in tot.items():
+        assert rel(got[k], g) < (1e-9 if dtype == F64 else 1e-4), k
+
+
+def test_stale_predictive_workspace_raises():
+    """A differentiable .mean followed by ANY other use of the same workspace (an ELBO step, a no-grad prediction) and
+    then backward must raise, not silently differentiate overwritten buffers."""
+    from dsvgp_b200 import gp
+    P, x, Vx, y, nd = O.make_problem(64, 3, 16, 2, F64, 3)
+    model, lik = build("dsvgp", P, 3, F64)
+    model.train(), lik.train()
+    mll = gp.VariationalELBO(lik, model, num_data=nd)
+    mean = model(x.cuda(), derivative_directions=Vx).mean
+    mll(lik(model(x.cuda(), derivative_directions=Vx)), y.cuda())
+    with pytest.raises(RuntimeError, match="overwritten"):
+        mean.sum().backward()
+    mean = model(x.cuda(), derivative_directions=Vx).mean
+    with torch.no_grad():
+        lik(model(x.cuda(), derivative_directions=Vx)).variance
+    with pytest.raises(RuntimeError, match="overwritten"):
+        mean.sum().backward()
+    mean = model(x.cuda(), derivative_directions=Vx).mean        # and the undisturbed sequence still works
+    mean.sum().backward()
+    assert torch.isfinite(model.variational_strategy.inducing_points.grad).all()
+
+
+def test_dtype_and_shape_mismatches_raise():
+    from dsvgp_b200 import gp
+    P, x, Vx, y, nd = O.make_problem(40, 3, 12, 2, F32, 3)
+    model, lik = build("dsvgp", P, 3, F32)
+    model.train(), lik.train()
+    mll = gp.VariationalELBO(lik, model, num_data=nd)
+    # float64 labels with a float32 model: cast explicitly (torch would promote silently in the reference)
+    a = mll(lik(model(x.cuda(), derivative_directions=Vx)), y.double().cuda())
+    b = mll(lik(model(x.cuda(), derivative_directions=Vx)), y.cuda())
+    assert float(a) == float(b)
+    with pytest.raises(ValueError, match="target has"):
+        mll(lik(model(x.cuda(), derivative_directions=Vx)), y[:-1].cuda())
+    with pytest.raises(TypeError, match="float64"):                       # fp64 inputs into an fp32 model
+        mll(lik(model(x.double().cuda(), derivative_directions=Vx.double())), y.double().cuda())
+    lik64 = gp.GaussianLikelihood().to("cuda", F64)                       # likelihood left in another dtype
+    with pytest.raises(TypeError, match="raw_noise"):
+        gp.VariationalELBO(lik64, model, num_data=nd)(lik64(model(x.cuda(), derivative_directions=Vx)), y.cuda())
+    with pytest.raises(RuntimeError, match="target is on"):
+        mll(lik(model(x.cuda(), derivative_directions=Vx)), y)
