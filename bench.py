@@ -456,7 +456,7 @@ def main():
     chol_flops = 2.0 * float(fac.Mp) ** 3 / 3.0
 
     # ---- dominant kernel alone: A = W K_zx (lower-triangular W), algorithmic flops M'^2 n'
-    wx = ops.normalize_dirs(V, dtype)[0] if p2 else None
+    wx = ENGINE._data_dirs(ws, V, dtype)          # normalised data directions + on-device canonical detection (sets ws.canon)
     ops.kdir_fwd(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx)
     use_tc = bool(getattr(ws, "tc", False) and getattr(fac, "tc", False))
     use_tch = bool(getattr(ws, "tch", False) and getattr(fac, "tch", False))

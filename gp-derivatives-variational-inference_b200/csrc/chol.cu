@@ -354,6 +354,297 @@ potrf_inv_block(const double* __restrict__ A, int64_t lda, double* __restrict__ 
     }
 }
 
+
+// =====================================================================================================================
+// Variant 2 of the diagonal-block chain (round 2).  ncu of variant 1 (profiles/r01_ncu_prof_potrf.txt): 142k cycles per
+// block, issue slots 32 % busy, top stall = barrier -- ~39k cycles of DMMA prologue on ONE SM (two 96^3 products at that
+// SM's own DMMA rate) and ~8.6k cycles per 8-column step whose long pole is scalar fp64 code fed from shared memory two
+// loads per FMA (the inverse's T = L[I,0:I] W[0:I,0:I] and the rank-8 trailing update).  Here:
+//   * diag_prepare (ncta CTAs, main stream, before the block kernel): CTA r forms the COLUMN slice Z[:, cols_r] of
+//     Z = A[k,k-1] W11(k-1)^T and from it its share D_r = Z[:, cols_r] Z[:, cols_r]^T of the update of the diagonal block
+//     (splitting the SYRK along its contraction index needs no exchange between CTAs); partials go to dead upper blocks of
+//     the work matrix and the block kernel starts from A[k,k] - sum_r D_r;
+//   * potrf_inv_block2: every bulk operation of the factorisation and of the inversion is an 8x8 DMMA tile product on
+//     fragments with a row stride of nbp + 4 doubles (conflict-free): panel = A_panel D^T with D = inv(L11) (8x8, from
+//     warp 0 right after the pivot chain) instead of a per-row substitution, thin and trailing rank-8 updates, the
+//     inverse's block row T and -D T.  Warp 0 runs the sequential 8x8 pivot chain of block column j+1 while warps 1-15 do
+//     the trailing update of step j and the inverse block row j.
+constexpr int PREP_MAXC = 4;        // CTAs of diag_prepare = partial sums the block kernel adds up
+
+struct PrepParts { double* p[PREP_MAXC]; };
+
+__global__ void __launch_bounds__(POTRF_THREADS)
+diag_prepare(const double* __restrict__ Aleft, int64_t lda, const double* __restrict__ Wprev, int64_t ldw, int nb,
+             PrepParts parts, int64_t ldd, int ncta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbp = (nb + 7) & ~7, ldp = nbp + 4, T = nbp >> 3;
+  const int tcs = (T + ncta - 1) / ncta;                       // tile columns per CTA
+  const int c0 = blockIdx.x * tcs, c1 = min(T, c0 + tcs), nc = max(c1 - c0, 0);
+  const int ldz = 8 * tcs + 4;
+  double* X = reinterpret_cast<double*>(smem_raw);             // [nbp][ldp]   A[k,k-1]
+  double* Y = X + nbp * ldp;                                   // [8 tcs][ldp] rows 8 c0 .. 8 c1 of W11(k-1)
+  double* Zs = Y + 8 * tcs * ldp;                              // [nbp][ldz]   Z[:, 8 c0 .. 8 c1)
+  double* Dp = parts.p[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int kmax_all = 8 * c1;                                 // W11 lower: column j of Z needs k <= j only
+  for (int e = tid; e < nbp * (kmax_all >> 1); e += POTRF_THREADS) {        // 16-byte chunks
+    const int i = e / (kmax_all >> 1), c = 2 * (e - i * (kmax_all >> 1));
+    const bool in = i < nb && c + 1 < nb;
+    if (in) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(X + i * ldp + c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(Aleft + (int64_t)i * lda + c) : "memory");
+    } else {
+      X[i * ldp + c] = (i < nb && c < nb) ? Aleft[(int64_t)i * lda + c] : 0.0;
+      X[i * ldp + c + 1] = 0.0;
+    }
+  }
+  for (int e = tid; e < 8 * nc * kmax_all; e += POTRF_THREADS) {
+    const int r = e / kmax_all, c = e - r * kmax_all, j = 8 * c0 + r;
+    const bool in = j < nb && c <= j;
+    cp_async8(Y + r * ldp + c, in ? Wprev + (int64_t)j * ldw + c : Wprev, in);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // Z slice: 8 x (8 nc) output strips, one per (tile row, warp), up to PREP tile columns wide (nc <= 4 accumulators)
+  for (int ti = warp; ti < T; ti += POTRF_THREADS / 32) {
+    double acc[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+    const double* xa = X + (8 * ti + g) * ldp + t;
+    for (int k0 = 0; k0 < kmax_all; k0 += 4) {
+      const double a = xa[k0];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nc && k0 < 8 * (c0 + q + 1)) dmma884(acc[q], a, Y[(8 * q + g) * ldp + k0 + t]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < nc) {
+        double* z = Zs + (8 * ti + g) * ldz + 8 * q + 2 * t;
+        z[0] = acc[q][0];
+        z[1] = acc[q][1];
+      }
+  }
+  __syncthreads();
+  // D_r = Zs Zs^T on the lower tiles (contraction over this CTA's 8 nc columns only)
+  const int groups = (T + 2) / 3, nblocks = T * groups;
+  for (int blk = warp; blk < nblocks; blk += POTRF_THREADS / 32) {
+    const int ri = blk / groups, cg = blk % groups;
+    if (3 * cg > ri) continue;
+    double acc[3][2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
+    const double* za = Zs + (8 * ri + g) * ldz + t;
+    for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
+      const double a = za[k0];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (3 * cg + q <= ri) dmma884(acc[q], a, Zs[(8 * (3 * cg + q) + g) * ldz + k0 + t]);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (3 * cg + q <= ri) {
+        const int r = 8 * ri + g, c = 8 * (3 * cg + q) + 2 * t;
+        if (r < nb) {
+          if (c < nb) Dp[(int64_t)r * ldd + c] = acc[q][0];
+          if (c + 1 < nb) Dp[(int64_t)r * ldd + c + 1] = acc[q][1];
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(POTRF_THREADS)
+potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl,
+                 double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset,
+                 PrepParts parts, int64_t ldd, int nparts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbp = (nb + 7) & ~7, ld = nbp + 4, T = nbp >> 3;
+  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
+  double* Ws = Ls + nbp * ld;                         // [nbp][ld]
+  double* rdg = Ws + nbp * ld;                        // [nbp] reciprocals of the diagonal of L
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  // ---- start: Ls = A[k,k] - sum_r D_r (lower), identity on the padding; Ws = 0
+  for (int e = tid; e < nbp * nbp; e += POTRF_THREADS) {
+    const int i = e / nbp, c = e - i * nbp;
+    double v = 0.0;
+    if (c <= i) {
+      if (i < nb) {
+        v = A[(int64_t)i * lda + c];
+        for (int r = 0; r < nparts; ++r) v -= parts.p[r][(int64_t)i * ldd + c];
+      } else {
+        v = (i == c) ? 1.0 : 0.0;
+      }
+    }
+    Ls[i * ld + c] = v;
+    Ws[i * ld + c] = 0.0;
+  }
+  auto factor_diag = [&](int k0) {                     // warp 0: lanes r = lane & 7 hold row r of the 8x8 diagonal block
+    const int r = lane & 7;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = Ls[(k0 + r) * ld + k0 + c];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {                   // two pivots per link (see variant 1)
+      const double a11 = __shfl_sync(0xffffffffu, a[k], k);
+      const double a21 = __shfl_sync(0xffffffffu, a[k], k + 1);
+      const double a22 = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+      const double det = fma(a11, a22, -(a21 * a21));
+      const bool ok1 = a11 > 0.0, ok2 = ok1 && det > 0.0;
+      double l11, r1, sdet, rdet;
+      if (ok2 && a11 > 1e-30 && a11 < 1e30 && det > 1e-30 && det < 1e30) {
+        rsqrt_sqrt_f64(a11, r1, l11);
+        rsqrt_sqrt_f64(det, rdet, sdet);
+      } else if (ok2) {
+        l11 = sqrt(a11);
+        r1 = 1.0 / l11;
+        sdet = sqrt(det);
+        rdet = 1.0 / sdet;
+      } else {
+        if (lane == 0) atomicCAS(info, 0, row_offset + k0 + k + (ok1 ? 2 : 1));
+        l11 = r1 = sdet = rdet = nan("");
+      }
+      const double l21 = a21 * r1;
+      const double r2 = rdet * l11;
+      const double l22 = sdet * r1;
+      if (r == k) {
+        a[k] = l11;
+      } else if (r == k + 1) {
+        a[k] = l21;
+        a[k + 1] = l22;
+      } else if (r > k + 1) {
+        a[k] = a[k] * r1;
+        a[k + 1] = (a[k + 1] - a[k] * l21) * r2;
+      }
+      if (lane == k) rdg[k0 + k] = r1;
+      if (lane == k + 1) rdg[k0 + k + 1] = r2;
+#pragma unroll
+      for (int c = k + 2; c < 8; ++c) {
+        const double lck = __shfl_sync(0xffffffffu, a[k], c);
+        const double lck1 = __shfl_sync(0xffffffffu, a[k + 1], c);
+        if (r >= c) a[c] = fma(-a[k + 1], lck1, fma(-a[k], lck, a[c]));
+      }
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Ls[(k0 + r) * ld + k0 + c] = (c <= r) ? a[c] : 0.0;
+    }
+    __syncwarp();
+    // D = inv(L11): lane j < 8 = column j of the inverse, right-looking substitution; D goes to the diagonal block of Ws
+    if (lane < 8) {
+      const int j = lane;
+      double x[8], acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        x[k] = (k >= j) ? acc[k] * rdg[k0 + k] : 0.0;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) acc[i] = fma(-Ls[(k0 + i) * ld + k0 + k], x[k], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Ws[(k0 + i) * ld + k0 + j] = (i >= j) ? x[i] : 0.0;
+    }
+  };
+  __syncthreads();
+  for (int j = 0; j < T; ++j) {
+    const int k0 = 8 * j;
+    // ---- S1: pivot chain + 8x8 inverse of block column j (warp 0)  ||  leftovers of step j-1 (warps 1-15)
+    if (warp == 0) {
+      factor_diag(k0);
+    } else if (j > 0) {
+      const int jp = j - 1, kp = 8 * jp;               // previous step: panel jp is final, D_jp sits in Ws[jp,jp]
+      // items: [0, jp)  inverse block row jp, tile column tc;   [jp, jp + ntr)  trailing tiles (ti >= tj >= j + 1)
+      const int nt = T - (j + 1), ntr = nt * (nt + 1) / 2, nitems = jp + ntr;
+      for (int it = warp - 1; it < nitems; it += POTRF_THREADS / 32 - 1) {
+        if (it < jp) {
+          const int tc = it;
+          // Tt = L[jp, tc..jp) W[tc..jp, tc]  (8x8), then W[jp, tc] = -D_jp Tt
+          double acc[2] = {0.0, 0.0};
+          const double* la = Ls + (kp + g) * ld + t;
+          for (int kk = 8 * tc; kk < kp; kk += 4) dmma884(acc, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
+          double* wt = Ws + (kp + g) * ld + 8 * tc + 2 * t;
+          wt[0] = acc[0];
+          wt[1] = acc[1];
+          __syncwarp();
+          double out[2] = {0.0, 0.0};
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            dmma884(out, -Ws[(kp + g) * ld + kp + 4 * s + t], Ws[(kp + 4 * s + t) * ld + 8 * tc + g]);
+          __syncwarp();
+          wt[0] = out[0];
+          wt[1] = out[1];
+        } else {
+          int q = it - jp, ti = 0;                       // q-th lower tile of the trailing nt x nt tile triangle
+          while (q > ti) { q -= ti + 1; ++ti; }
+          const int tj = q;
+          const int ri = 8 * (j + 1 + ti), rj = 8 * (j + 1 + tj);
+          double acc[2] = {0.0, 0.0};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) dmma884(acc, Ls[(ri + g) * ld + kp + 4 * s + t], Ls[(rj + g) * ld + kp + 4 * s + t]);
+          double* c = Ls + (ri + g) * ld + rj + 2 * t;
+          c[0] -= acc[0];
+          c[1] -= acc[1];
+        }
+      }
+    }
+    __syncthreads();
+    if (j + 1 < T) {
+      // ---- S2: panel j = (rows below the diagonal block, columns of block j) * D_j^T, one 8x8 tile per warp
+      for (int ti = j + 1 + warp; ti < T; ti += POTRF_THREADS / 32) {
+        double* pa = Ls + (8 * ti + g) * ld + k0;
+        const double a0 = pa[t], a1 = pa[4 + t];
+        double acc[2] = {0.0, 0.0};
+        dmma884(acc, a0, Ws[(k0 + g) * ld + k0 + t]);
+        dmma884(acc, a1, Ws[(k0 + g) * ld + k0 + 4 + t]);
+        pa[2 * t] = acc[0];
+        pa[2 * t + 1] = acc[1];
+      }
+      __syncthreads();
+      // ---- S3: thin update of block column j+1 (all that the next pivot chain and the next panel read)
+      const int t0 = k0 + 8;
+      for (int ti = j + 1 + warp; ti < T; ti += POTRF_THREADS / 32) {
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) dmma884(acc, Ls[(8 * ti + g) * ld + k0 + 4 * s + t], Ls[(t0 + g) * ld + k0 + 4 * s + t]);
+        double* c = Ls + (8 * ti + g) * ld + t0 + 2 * t;
+        c[0] -= acc[0];
+        c[1] -= acc[1];
+      }
+      __syncthreads();
+    }
+  }
+  // inverse block row T-1 (all warps; the trailing triangle of the last step is empty)
+  {
+    const int jp = T - 1, kp = 8 * jp;
+    for (int tc = warp; tc < jp; tc += POTRF_THREADS / 32) {
+      double acc[2] = {0.0, 0.0};
+      const double* la = Ls + (kp + g) * ld + t;
+      for (int kk = 8 * tc; kk < kp; kk += 4) dmma884(acc, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
+      double* wt = Ws + (kp + g) * ld + 8 * tc + 2 * t;
+      wt[0] = acc[0];
+      wt[1] = acc[1];
+      __syncwarp();
+      double out[2] = {0.0, 0.0};
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        dmma884(out, -Ws[(kp + g) * ld + kp + 4 * s + t], Ws[(kp + 4 * s + t) * ld + 8 * tc + g]);
+      __syncwarp();
+      wt[0] = out[0];
+      wt[1] = out[1];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int i = e / nb, c = e - i * nb;
+    L[(int64_t)i * ldl + c] = (c <= i) ? Ls[i * ld + c] : 0.0;
+    W[(int64_t)i * ldw + c] = (c <= i) ? Ws[i * ld + c] : 0.0;
+  }
+}
+
+static int g_chol_variant = 2;
+void set_chol_variant(int v) { g_chol_variant = (v == 1) ? 1 : 2; }
+int get_chol_variant() { return g_chol_variant; }
+
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st) {
   if (Mp <= 0) return DSVGP_OK;
@@ -362,8 +653,28 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   const int nbp = (nb0 + 7) & ~7;
   if ((nbp >> 3) * (((nbp >> 3) + 2) / 3) > 16 * POTRF_MAXBLK) return DSVGP_ERR_ARG;
   const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 4) + nbp);
-  if (smem > 48 * 1024)
+  const bool v2 = g_chol_variant == 2 && nblk >= 4;    // (one or two blocks: nothing to gain, and only one dead block to hold partials)
+  // variant 2: partial sums of the diagonal-block update live in dead blocks of the work matrix above its diagonal
+  // (the factorisation only touches the lower triangle; the inverse's scratch is below it too)
+  PrepParts parts{};
+  int nparts = 0;
+  if (v2) {
+    if (nblk >= 5) {
+      for (int r = 0; r < 4; ++r) parts.p[nparts++] = Awork + (int64_t)(r + 1) * nb0;             // blocks (0,1) .. (0,4)
+    } else {
+      for (int r = 0; r < 3; ++r) parts.p[nparts++] = Awork + (int64_t)(r + 1) * nb0;             // (0,1) (0,2) (0,3)
+      parts.p[nparts++] = Awork + (int64_t)nb0 * lda + 2 * nb0;                                    // (1,2)
+    }
+    const int T = nbp >> 3;
+    if (nparts > T) nparts = T;
+  }
+  const int tcs = nparts ? ((nbp >> 3) + nparts - 1) / nparts : 0;
+  const size_t smem_prep = sizeof(double) * (size_t)(nbp * (nbp + 4) + 8 * tcs * (nbp + 4) + nbp * (8 * tcs + 4));
+  if (smem > 48 * 1024) {
     cudaFuncSetAttribute(potrf_inv_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(potrf_inv_block2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if (smem_prep > 48 * 1024) cudaFuncSetAttribute(diag_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
   cudaMemsetAsync(info, 0, sizeof(int), st);
   // Two chains.  Main stream: the diagonal blocks only -- potrf(k) applies the step-(k-1) update to its own block in
   // its prologue, so it needs W11(k-1) (stream order) and block row k updated through step k-2 (event from the side
@@ -393,8 +704,17 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     if (two_chains && k >= 2 && last_side >= k - 2) cudaStreamWaitEvent(st, sc.ev_side[k - 2], 0);
     const double* Aleft = k > 0 ? Awork + o * lda + (o - nb0) : nullptr;
     const double* Wprev = k > 0 ? W + (o - nb0) * ldw + (o - nb0) : nullptr;
-    potrf_inv_block<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o, ldw,
-                                                    nb0, info, (int)o, Aleft, Wprev);
+    if (v2) {
+      if (k > 0) {
+        diag_prepare<<<nparts, POTRF_THREADS, smem_prep, st>>>(Aleft, lda, Wprev, ldw, nb0, parts, lda, nparts);
+        CHECK_LAUNCH();
+      }
+      potrf_inv_block2<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o, ldw,
+                                                       nb0, info, (int)o, parts, lda, k > 0 ? nparts : 0);
+    } else {
+      potrf_inv_block<<<1, POTRF_THREADS, smem, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o, ldw,
+                                                      nb0, info, (int)o, Aleft, Wprev);
+    }
     CHECK_LAUNCH();
     const int m = Mp - (int)o - nb0;
     if (m > 0) {

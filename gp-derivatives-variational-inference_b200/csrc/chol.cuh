@@ -13,4 +13,8 @@ void chol_plan(int Mq, int* Mp, int* nb0, int* nlev);
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st);
 
+// 1: round-1 diagonal-block kernel (in-kernel DMMA prologue, scalar updates); 2 (default): diag_prepare + all-DMMA block kernel
+void set_chol_variant(int v);
+int get_chol_variant();
+
 }  // namespace dsvgp

@@ -105,6 +105,10 @@ int dsvgp_kdir_bwd_f32f64(const float* x1, const double* u1, const double* inv1,
  * CUDA-graph capturable.  Not re-entrant from two host threads on the same device at the same time. */
 void dsvgp_chol_plan(int Mq, int* Mp_host, int* nb0_host, int* nlev_host);
 int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t s);
+/* A/B knob of the diagonal-block chain: 1 = the round-1 kernel (DMMA prologue inside the single-CTA block kernel, scalar
+ * rank-8 updates and inverse), 2 (default) = a small multi-CTA kernel forms the update of the next diagonal block and the
+ * block kernel does every bulk operation as 8x8 DMMA tiles.  Returns the value in force.  Results agree to rounding. */
+int dsvgp_set_chol_variant(int v);
 int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0, int nlev, int* info, dsvgp_stream_t s);
 
 /* C = alpha*op(A)*op(B) + beta*C, triangle-aware, batched -- every dense product of the strategy
