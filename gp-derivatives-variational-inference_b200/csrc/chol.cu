@@ -10,6 +10,8 @@
 // applied bottom-up; each level is two batched GEMMs.  Diagonal nb0 x nb0 blocks are factorised AND inverted
 // inside one CTA in shared memory.  Status goes to a device int (0 ok, i+1 = first non-positive pivot), never to
 // the host: the caller decides when to look (no hidden synchronisation).
+#include <algorithm>
+
 #include "chol.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -453,43 +455,33 @@ diag_prepare(const double* __restrict__ Aleft, int64_t lda, const double* __rest
   }
 }
 
-__global__ void __launch_bounds__(POTRF_THREADS)
-potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl,
-                 double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset,
-                 PrepParts parts, int64_t ldd, int nparts) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nbp = (nb + 7) & ~7, ld = nbp + 4, T = nbp >> 3;
-  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
-  double* Ws = Ls + nbp * ld;                         // [nbp][ld]
-  double* rdg = Ws + nbp * ld;                        // [nbp] reciprocals of the diagonal of L
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  // ---- start: Ls = A[k,k] - sum_r D_r (lower), identity on the padding; Ws = 0
-  for (int e = tid; e < nbp * nbp; e += POTRF_THREADS) {
-    const int i = e / nbp, c = e - i * nbp;
-    double v = 0.0;
-    if (c <= i) {
-      if (i < nb) {
-        v = A[(int64_t)i * lda + c];
-        for (int r = 0; r < nparts; ++r) v -= parts.p[r][(int64_t)i * ldd + c];
-      } else {
-        v = (i == c) ? 1.0 : 0.0;
-      }
-    }
-    Ls[i * ld + c] = v;
-    Ws[i * ld + c] = 0.0;
-  }
-  auto factor_diag = [&](int k0) {                     // warp 0: lanes r = lane & 7 hold row r of the 8x8 diagonal block
-    const int r = lane & 7;
-    double a[8];
+__device__ long long* g_potrf_dbg = nullptr;     // profiling aid: clock64() at the phase boundaries of one block kernel
+#define DBG_T(slot) do { if (dbg != nullptr && tid == 0) dbg[slot] = clock64(); } while (0)
+
+// Factorise the nbp x nbp block held in shared memory (Ls, row stride ld) and invert the factor (Ws): the body shared by
+// the single-CTA block kernel (variant 2) and the cluster kernel (variant 3).  Ends with L and W written to global memory.
+__device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, double* __restrict__ Ws, const int ld, const int nbp,
+                                                   const int nb, int* __restrict__ info, const int row_offset,
+                                                   double* __restrict__ L, const int64_t ldl, double* __restrict__ W,
+                                                   const int64_t ldw, long long* dbg) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, T = nbp >> 3;
+  // The 8x8 diagonal block, entirely in registers and redundantly in every lane of warp 0: no shuffles, no shared-memory
+  // round trips inside the sequential pivot chain (measured: the shuffle-based version + the 8x8 inverse through shared memory
+  // took 4.0k cycles per 8 columns = 49k of the 65k cycles between the first and the last barrier of this kernel).
+  // Two pivots per link (det = a11 a22 - a21^2: rsqrt(a11) and rsqrt(det) are independent chains), then D = inv(L11) by a
+  // right-looking substitution on the registers, lane j < 8 doing column j.  L11 -> Ls, D -> diagonal block of Ws.
+  auto factor_diag = [&](int k0) {
+    double a[8][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = Ls[(k0 + r) * ld + k0 + c];
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) {                   // two pivots per link (see variant 1)
-      const double a11 = __shfl_sync(0xffffffffu, a[k], k);
-      const double a21 = __shfl_sync(0xffffffffu, a[k], k + 1);
-      const double a22 = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+      for (int c = 0; c <= i; ++c) a[i][c] = Ls[(k0 + i) * ld + k0 + c];
+    double rd[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const double a11 = a[k][k], a21 = a[k + 1][k], a22 = a[k + 1][k + 1];
       const double det = fma(a11, a22, -(a21 * a21));
-      const bool ok1 = a11 > 0.0, ok2 = ok1 && det > 0.0;
+      const bool ok1 = a11 > 0.0, ok2 = ok1 && det > 0.0;          // also false for NaN
       double l11, r1, sdet, rdet;
       if (ok2 && a11 > 1e-30 && a11 < 1e30 && det > 1e-30 && det < 1e30) {
         rsqrt_sqrt_f64(a11, r1, l11);
@@ -504,75 +496,84 @@ potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__
         l11 = r1 = sdet = rdet = nan("");
       }
       const double l21 = a21 * r1;
-      const double r2 = rdet * l11;
-      const double l22 = sdet * r1;
-      if (r == k) {
-        a[k] = l11;
-      } else if (r == k + 1) {
-        a[k] = l21;
-        a[k + 1] = l22;
-      } else if (r > k + 1) {
-        a[k] = a[k] * r1;
-        a[k + 1] = (a[k + 1] - a[k] * l21) * r2;
-      }
-      if (lane == k) rdg[k0 + k] = r1;
-      if (lane == k + 1) rdg[k0 + k + 1] = r2;
+      const double r2 = rdet * l11;                                // 1 / l22
+      a[k][k] = l11;
+      a[k + 1][k] = l21;
+      a[k + 1][k + 1] = sdet * r1;                                 // sqrt(det / a11)
+      rd[k] = r1;
+      rd[k + 1] = r2;
 #pragma unroll
-      for (int c = k + 2; c < 8; ++c) {
-        const double lck = __shfl_sync(0xffffffffu, a[k], c);
-        const double lck1 = __shfl_sync(0xffffffffu, a[k + 1], c);
-        if (r >= c) a[c] = fma(-a[k + 1], lck1, fma(-a[k], lck, a[c]));
+      for (int i = k + 2; i < 8; ++i) {
+        a[i][k] *= r1;
+        a[i][k + 1] = (a[i][k + 1] - a[i][k] * l21) * r2;
       }
+#pragma unroll
+      for (int i = k + 2; i < 8; ++i)
+#pragma unroll
+        for (int c = k + 2; c <= i; ++c) a[i][c] = fma(-a[i][k + 1], a[c][k + 1], fma(-a[i][k], a[c][k], a[i][c]));
+    }
+    // D = inv(L11), column j on lane j (lanes >= 8 compute a copy of column lane & 7 and do not store)
+    const int j = lane & 7;
+    double x[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x[k] = (k >= j) ? acc[k] * rd[k] : 0.0;
+#pragma unroll
+      for (int i = k + 1; i < 8; ++i) acc[i] = fma(-a[i][k], x[k], acc[i]);
     }
     if (lane < 8) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) Ls[(k0 + r) * ld + k0 + c] = (c <= r) ? a[c] : 0.0;
-    }
-    __syncwarp();
-    // D = inv(L11): lane j < 8 = column j of the inverse, right-looking substitution; D goes to the diagonal block of Ws
-    if (lane < 8) {
-      const int j = lane;
-      double x[8], acc[8];
+      for (int i = 0; i < 8; ++i) Ws[(k0 + i) * ld + k0 + j] = x[i];       // (x[i] = 0 above the diagonal)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = (i == j) ? 1.0 : 0.0;
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        x[k] = (k >= j) ? acc[k] * rdg[k0 + k] : 0.0;
-#pragma unroll
-        for (int i = k + 1; i < 8; ++i) acc[i] = fma(-Ls[(k0 + i) * ld + k0 + k], x[k], acc[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) Ws[(k0 + i) * ld + k0 + j] = (i >= j) ? x[i] : 0.0;
+        for (int c = 0; c < 8; ++c)
+          if (lane == c) Ls[(k0 + i) * ld + k0 + c] = (c <= i) ? a[i][c] : 0.0;   // lane c writes column c of L11
     }
   };
+  // one tile of the inverse's block row jp: Tt = L[jp, tc..jp) W[tc..jp, tc] on two independent accumulators (half the
+  // dependent-DMMA chain), then W[jp, tc] = -D_jp Tt through the warp's own 8x8 patch of Ws
+  auto inverse_tile = [&](int jp, int tc) {
+    const int kp = 8 * jp;
+    double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+    const double* la = Ls + (kp + g) * ld + t;
+    int kk = 8 * tc;
+    for (; kk + 4 < kp; kk += 8) {
+      dmma884(acc0, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
+      dmma884(acc1, la[kk + 4], Ws[(kk + 4 + t) * ld + 8 * tc + g]);
+    }
+    if (kk < kp) dmma884(acc0, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
+    double* wt = Ws + (kp + g) * ld + 8 * tc + 2 * t;
+    wt[0] = acc0[0] + acc1[0];
+    wt[1] = acc0[1] + acc1[1];
+    __syncwarp();
+    double out[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      dmma884(out, -Ws[(kp + g) * ld + kp + 4 * s + t], Ws[(kp + 4 * s + t) * ld + 8 * tc + g]);
+    __syncwarp();
+    wt[0] = out[0];
+    wt[1] = out[1];
+  };
+  DBG_T(0);
   __syncthreads();
+  DBG_T(1);
   for (int j = 0; j < T; ++j) {
     const int k0 = 8 * j;
     // ---- S1: pivot chain + 8x8 inverse of block column j (warp 0)  ||  leftovers of step j-1 (warps 1-15)
     if (warp == 0) {
       factor_diag(k0);
+      DBG_T(2 + 4 * j);
     } else if (j > 0) {
       const int jp = j - 1, kp = 8 * jp;               // previous step: panel jp is final, D_jp sits in Ws[jp,jp]
-      // items: [0, jp)  inverse block row jp, tile column tc;   [jp, jp + ntr)  trailing tiles (ti >= tj >= j + 1)
+      // items: [0, jp)  inverse block row jp, tile column tc (longest chains first);
+      //        [jp, jp + ntr)  trailing tiles (ti >= tj >= j + 1)
       const int nt = T - (j + 1), ntr = nt * (nt + 1) / 2, nitems = jp + ntr;
       for (int it = warp - 1; it < nitems; it += POTRF_THREADS / 32 - 1) {
         if (it < jp) {
-          const int tc = it;
-          // Tt = L[jp, tc..jp) W[tc..jp, tc]  (8x8), then W[jp, tc] = -D_jp Tt
-          double acc[2] = {0.0, 0.0};
-          const double* la = Ls + (kp + g) * ld + t;
-          for (int kk = 8 * tc; kk < kp; kk += 4) dmma884(acc, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
-          double* wt = Ws + (kp + g) * ld + 8 * tc + 2 * t;
-          wt[0] = acc[0];
-          wt[1] = acc[1];
-          __syncwarp();
-          double out[2] = {0.0, 0.0};
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            dmma884(out, -Ws[(kp + g) * ld + kp + 4 * s + t], Ws[(kp + 4 * s + t) * ld + 8 * tc + g]);
-          __syncwarp();
-          wt[0] = out[0];
-          wt[1] = out[1];
+          inverse_tile(jp, it);
         } else {
           int q = it - jp, ti = 0;                       // q-th lower tile of the trailing nt x nt tile triangle
           while (q > ti) { q -= ti + 1; ++ti; }
@@ -588,6 +589,7 @@ potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__
       }
     }
     __syncthreads();
+    DBG_T(3 + 4 * j);
     if (j + 1 < T) {
       // ---- S2: panel j = (rows below the diagonal block, columns of block j) * D_j^T, one 8x8 tile per warp
       for (int ti = j + 1 + warp; ti < T; ti += POTRF_THREADS / 32) {
@@ -600,6 +602,7 @@ potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__
         pa[2 * t + 1] = acc[1];
       }
       __syncthreads();
+      DBG_T(4 + 4 * j);
       // ---- S3: thin update of block column j+1 (all that the next pivot chain and the next panel read)
       const int t0 = k0 + 8;
       for (int ti = j + 1 + warp; ti < T; ti += POTRF_THREADS / 32) {
@@ -611,38 +614,237 @@ potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__
         c[1] -= acc[1];
       }
       __syncthreads();
+      DBG_T(5 + 4 * j);
     }
   }
   // inverse block row T-1 (all warps; the trailing triangle of the last step is empty)
-  {
-    const int jp = T - 1, kp = 8 * jp;
-    for (int tc = warp; tc < jp; tc += POTRF_THREADS / 32) {
-      double acc[2] = {0.0, 0.0};
-      const double* la = Ls + (kp + g) * ld + t;
-      for (int kk = 8 * tc; kk < kp; kk += 4) dmma884(acc, la[kk], Ws[(kk + t) * ld + 8 * tc + g]);
-      double* wt = Ws + (kp + g) * ld + 8 * tc + 2 * t;
-      wt[0] = acc[0];
-      wt[1] = acc[1];
-      __syncwarp();
-      double out[2] = {0.0, 0.0};
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-        dmma884(out, -Ws[(kp + g) * ld + kp + 4 * s + t], Ws[(kp + 4 * s + t) * ld + 8 * tc + g]);
-      __syncwarp();
-      wt[0] = out[0];
-      wt[1] = out[1];
-    }
-  }
+  for (int tc = warp; tc < T - 1; tc += POTRF_THREADS / 32) inverse_tile(T - 1, tc);
   __syncthreads();
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int i = e / nb, c = e - i * nb;
-    L[(int64_t)i * ldl + c] = (c <= i) ? Ls[i * ld + c] : 0.0;
-    W[(int64_t)i * ldw + c] = (c <= i) ? Ws[i * ld + c] : 0.0;
-  }
+  DBG_T(62);
+  for (int i = warp; i < nb; i += POTRF_THREADS / 32)
+    for (int c = lane; c < nb; c += 32) {
+      const bool low = c <= i;
+      L[(int64_t)i * ldl + c] = low ? Ls[i * ld + c] : 0.0;
+      W[(int64_t)i * ldw + c] = low ? Ws[i * ld + c] : 0.0;
+    }
+  DBG_T(63);
 }
 
-static int g_chol_variant = 2;
-void set_chol_variant(int v) { g_chol_variant = (v == 1) ? 1 : 2; }
+__global__ void __launch_bounds__(POTRF_THREADS)
+potrf_inv_block2(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl,
+                 double* __restrict__ W, int64_t ldw, int nb, int* __restrict__ info, int row_offset,
+                 PrepParts parts, int64_t ldd, int nparts) {
+  long long* dbg = (row_offset == 0) ? nullptr : g_potrf_dbg;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbp = (nb + 7) & ~7, ld = nbp + 4, T = nbp >> 3;
+  double* Ls = reinterpret_cast<double*>(smem_raw);   // [nbp][ld]
+  double* Ws = Ls + nbp * ld;                         // [nbp][ld]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  DBG_T(61);
+  // ---- start: Ls = A[k,k] - sum_r D_r (lower), identity on the padding; Ws = 0.
+  // (measured, round 2: one element at a time with its five dependent-latency loads cost 27k of this kernel's 93k cycles.
+  // A warp owns rows warp, warp+16, ..; lanes own columns lane, lane+32, lane+64, lane+96; all loads of two rows -- up to
+  // 2 x 4 x 5 -- are in flight together.)
+  for (int e = tid; e < nbp * ld; e += POTRF_THREADS) Ws[e] = 0.0;
+  for (int i0 = warp; i0 < nbp; i0 += 2 * (POTRF_THREADS / 32)) {
+    double v[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * (POTRF_THREADS / 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = lane + 32 * q;
+        v[u][q] = (i < nb && c <= i) ? A[(int64_t)i * lda + c] : ((i < nbp && i == c) ? 1.0 : 0.0);
+      }
+    }
+    for (int r = 0; r < nparts; r += 2) {             // two partial sums per round: 16 more loads in flight
+      const double* pr0 = parts.p[r];
+      const double* pr1 = parts.p[r + 1 < nparts ? r + 1 : r];
+      const bool two = r + 1 < nparts;
+      double w0[2][4], w1[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * (POTRF_THREADS / 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = lane + 32 * q;
+          const bool in = i < nb && c <= i;
+          w0[u][q] = in ? pr0[(int64_t)i * ldd + c] : 0.0;
+          w1[u][q] = (in && two) ? pr1[(int64_t)i * ldd + c] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[u][q] = (v[u][q] - w0[u][q]) - w1[u][q];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * (POTRF_THREADS / 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = lane + 32 * q;
+        if (i < nbp && c < nbp) Ls[i * ld + c] = v[u][q];
+      }
+    }
+  }
+  factor_invert_smem(Ls, Ws, ld, nbp, nb, info, row_offset, L, ldl, W, ldw, dbg);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 3: diag_prepare and the block kernel as ONE launch of a 4-CTA thread-block cluster.  CTA r forms its column slice
+// of Z = A[k,k-1] W11(k-1)^T and its partial update D_r = Z_r Z_r^T in its OWN shared memory; after a cluster barrier CTA 0
+// gathers  A[k,k] - D_0 - D_1 - D_2 - D_3  straight from the four shared memories (distributed shared memory,
+// ld.shared::cluster) and factorises; CTAs 1-3 leave after a second barrier.  Against variant 2 this drops a launch gap
+// and the round trip of the partial sums through global memory (9 dependent L2 round trips, ~10k cycles per block).
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_ptr, uint32_t rank) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr);
+  uint32_t ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int CL = 4;               // cluster size = column slices of Z
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(POTRF_THREADS)
+potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L, int64_t ldl, double* __restrict__ W,
+              int64_t ldw, int nb, int* __restrict__ info, int row_offset, const double* __restrict__ Aleft,
+              const double* __restrict__ Wprev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbp = (nb + 7) & ~7, ld = nbp + 4, T = nbp >> 3;
+  const int tcs = (T + CL - 1) / CL, ldz = 8 * tcs + 4;
+  // two regions of nbp x ld doubles:  R0 = X = A[k,k-1]  ->  D_r (lower tiles; X is dead once Z is formed)  ->  Ls (in place)
+  //                                    R1 = Y (rows of W11(k-1)) + Zs (column slice of Z)  ->  Ws
+  double* R0 = reinterpret_cast<double*>(smem_raw);
+  double* R1 = R0 + nbp * ld;
+  double* R2 = R0;                                     // D_r
+  double* Y = R1;                                      // [8 tcs][ld]
+  double* Zs = Y + 8 * tcs * ld;                       // [nbp][ldz]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t rank = cluster_rank();
+  long long* dbg = (row_offset == 0 || rank != 0) ? nullptr : g_potrf_dbg;
+  DBG_T(61);
+  if (Aleft != nullptr) {
+    const int c0 = (int)rank * tcs, c1 = min(T, c0 + tcs), nc = max(c1 - c0, 0);
+    const int kmax_all = 8 * c1;                               // W11 lower: column j of Z needs k <= j only
+    if (nc > 0) {
+      for (int e = tid; e < nbp * (kmax_all >> 1); e += POTRF_THREADS) {        // 16-byte chunks
+        const int i = e / (kmax_all >> 1), c = 2 * (e - i * (kmax_all >> 1));
+        if (i < nb && c + 1 < nb) {
+          const uint32_t d = (uint32_t)__cvta_generic_to_shared(R0 + i * ld + c);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(Aleft + (int64_t)i * lda + c) : "memory");
+        } else {
+          R0[i * ld + c] = (i < nb && c < nb) ? Aleft[(int64_t)i * lda + c] : 0.0;
+          R0[i * ld + c + 1] = 0.0;
+        }
+      }
+      for (int e = tid; e < 8 * nc * kmax_all; e += POTRF_THREADS) {
+        const int r = e / kmax_all, c = e - r * kmax_all, j = 8 * c0 + r;
+        const bool in = j < nb && c <= j;
+        cp_async8(Y + r * ld + c, in ? Wprev + (int64_t)j * ldw + c : Wprev, in);
+      }
+    }
+    if (nc == 0)                                          // (more CTAs than tile columns: this one contributes zero)
+      for (int e = tid; e < nbp * ld; e += POTRF_THREADS) R2[e] = 0.0;
+    cp_async_wait_all();
+    __syncthreads();
+    for (int ti = warp; ti < T && nc > 0; ti += POTRF_THREADS / 32) {          // Z slice: 8 x (8 nc) strips
+      double acc[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+      const double* xa = R0 + (8 * ti + g) * ld + t;
+      for (int k0 = 0; k0 < kmax_all; k0 += 4) {
+        const double a = xa[k0];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nc && k0 < 8 * (c0 + q + 1)) dmma884(acc[q], a, Y[(8 * q + g) * ld + k0 + t]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nc) {
+          double* z = Zs + (8 * ti + g) * ldz + 8 * q + 2 * t;
+          z[0] = acc[q][0];
+          z[1] = acc[q][1];
+        }
+    }
+    __syncthreads();
+    const int groups = (T + 2) / 3, nblocks = nc > 0 ? T * groups : 0;          // D_r = Zs Zs^T, lower tiles, into R2
+    for (int blk = warp; blk < nblocks; blk += POTRF_THREADS / 32) {
+      const int ri = blk / groups, cg = blk % groups;
+      if (3 * cg > ri) continue;
+      double acc[3][2];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
+      const double* za = Zs + (8 * ri + g) * ldz + t;
+      for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
+        const double a = za[k0];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (3 * cg + q <= ri) dmma884(acc[q], a, Zs[(8 * (3 * cg + q) + g) * ldz + k0 + t]);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (3 * cg + q <= ri) {
+          double* dd = R2 + (8 * ri + g) * ld + 8 * (3 * cg + q) + 2 * t;
+          dd[0] = acc[q][0];
+          dd[1] = acc[q][1];
+        }
+    }
+  }
+  cluster_barrier();                                   // every partial is in place (release / acquire at cluster scope)
+  if (rank == 0) {
+    // Ls = A[k,k] - sum_r D_r on the lower triangle, identity on the padding; X is dead, its region becomes Ls
+    const bool upd = Aleft != nullptr;
+    for (int i0 = warp; i0 < nbp; i0 += 2 * (POTRF_THREADS / 32)) {
+      double v[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * (POTRF_THREADS / 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = lane + 32 * q;
+          const bool in = i < nb && c <= i;
+          double a = in ? A[(int64_t)i * lda + c] : ((i < nbp && i == c) ? 1.0 : 0.0);
+          if (in && upd) {
+            const double* dp = R2 + i * ld + c;
+            const double d0 = *dp, d1 = ld_dsmem_f64(dp, 1), d2 = ld_dsmem_f64(dp, 2), d3 = ld_dsmem_f64(dp, 3);
+            a = (((a - d0) - d1) - d2) - d3;
+          }
+          v[u][q] = a;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * (POTRF_THREADS / 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = lane + 32 * q;
+          if (i < nbp && c < nbp) R0[i * ld + c] = v[u][q];
+        }
+      }
+    }
+  }
+  cluster_barrier();                                   // CTA 0 has read the remote partials: the others may go
+  if (rank != 0) return;
+  for (int e = tid; e < nbp * ld; e += POTRF_THREADS) R1[e] = 0.0;              // Y / Zs are dead: their region becomes Ws
+  factor_invert_smem(R0, R1, ld, nbp, nb, info, row_offset, L, ldl, W, ldw, dbg);
+}
+
+void set_potrf_debug(long long* p) { cudaMemcpyToSymbol(g_potrf_dbg, &p, sizeof(p)); }
+
+static int g_chol_variant = 3;
+void set_chol_variant(int v) { g_chol_variant = (v >= 1 && v <= 3) ? v : 3; }
 int get_chol_variant() { return g_chol_variant; }
 
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
@@ -653,6 +855,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   const int nbp = (nb0 + 7) & ~7;
   if ((nbp >> 3) * (((nbp >> 3) + 2) / 3) > 16 * POTRF_MAXBLK) return DSVGP_ERR_ARG;
   const size_t smem = sizeof(double) * (size_t)(2 * nbp * (nbp + 4) + nbp);
+  const bool v3 = g_chol_variant == 3 && nblk >= 2;     // cluster kernel: no scratch in global memory at all
   const bool v2 = g_chol_variant == 2 && nblk >= 4;    // (one or two blocks: nothing to gain, and only one dead block to hold partials)
   // variant 2: partial sums of the diagonal-block update live in dead blocks of the work matrix above its diagonal
   // (the factorisation only touches the lower triangle; the inverse's scratch is below it too)
@@ -675,6 +878,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     cudaFuncSetAttribute(potrf_inv_block2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (smem_prep > 48 * 1024) cudaFuncSetAttribute(diag_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
+  const int tcs_cl = ((nbp >> 3) + CL - 1) / CL;
+  const size_t smem_cl = sizeof(double) * (size_t)(nbp * (nbp + 4)) +
+                         sizeof(double) * (size_t)std::max(nbp * (nbp + 4), 8 * tcs_cl * (nbp + 4) + nbp * (8 * tcs_cl + 4));
+  if (v3 && smem_cl > 48 * 1024) cudaFuncSetAttribute(potrf_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
   cudaMemsetAsync(info, 0, sizeof(int), st);
   // Two chains.  Main stream: the diagonal blocks only -- potrf(k) applies the step-(k-1) update to its own block in
   // its prologue, so it needs W11(k-1) (stream order) and block row k updated through step k-2 (event from the side
@@ -682,21 +889,31 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // update of everything below block row k+1 (a lower trapezoid: block column k+1 included, the diagonal block (k+1,k+1)
   // excluded -- potrf(k+1) owns it).  The 32 latency-bound single-CTA kernels overlap the throughput-bound GEMMs.
   // Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
-  struct SideCtx { cudaStream_t side = nullptr; cudaEvent_t ev_main[64], ev_side[64]; bool ready = false; };
+  struct SideCtx { cudaStream_t side = nullptr, inv = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_inv; bool ready = false; };
   static SideCtx ctxs[16];                              // one side stream + event pool per device
   int dev = 0;
   cudaGetDevice(&dev);
   SideCtx& sc = ctxs[dev & 15];
   if (!sc.ready) {
     if (cudaStreamCreateWithFlags(&sc.side, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    if (cudaStreamCreateWithFlags(&sc.inv, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     for (int i = 0; i < 64; ++i) {
       cudaEventCreateWithFlags(&sc.ev_main[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&sc.ev_side[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&sc.ev_panel[i], cudaEventDisableTiming);
     }
+    cudaEventCreateWithFlags(&sc.ev_inv, cudaEventDisableTiming);
     sc.ready = true;
   }
-  cudaStream_t side = sc.side;
+  cudaStream_t side = sc.side, inv = sc.inv;
   const bool two_chains = nblk <= 64;
+  // Eager inverse (round 2): the recursive-doubling inverse W = [[W11, 0], [-W22 (L21 W11), W22]] does not wait for the end
+  // of the factorisation.  For every pair of every level, T = L21 W11 is issued (third stream) as soon as the pair's top half
+  // is factorised and inverted, and W21 = -W22 T as soon as its bottom half is: after the last diagonal block only ONE product
+  // per level is left (96, 192, .. 1536 wide) instead of the ten batched level products of round 1 (0.72 ms at M' = 3072).
+  // T lives in the dead upper-right quadrant of the pair inside W (the work matrix' lower-left quadrant is still read by the
+  // next diag_prepare).
+  const bool eager_inv = two_chains && nlev >= 1 && g_chol_variant >= 2;
   int last_side = -1;
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
@@ -704,7 +921,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     if (two_chains && k >= 2 && last_side >= k - 2) cudaStreamWaitEvent(st, sc.ev_side[k - 2], 0);
     const double* Aleft = k > 0 ? Awork + o * lda + (o - nb0) : nullptr;
     const double* Wprev = k > 0 ? W + (o - nb0) * ldw + (o - nb0) : nullptr;
-    if (v2) {
+    if (v3) {
+      potrf_cluster<<<CL, POTRF_THREADS, smem_cl, st>>>(Awork + o * lda + o, lda, L + o * ldl + o, ldl, W + o * ldw + o, ldw, nb0,
+                                                        info, (int)o, Aleft, Wprev);
+    } else if (v2) {
       if (k > 0) {
         diag_prepare<<<nparts, POTRF_THREADS, smem_prep, st>>>(Aleft, lda, Wprev, ldw, nb0, parts, lda, nparts);
         CHECK_LAUNCH();
@@ -717,17 +937,16 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     }
     CHECK_LAUNCH();
     const int m = Mp - (int)o - nb0;
+    if (two_chains) cudaEventRecord(sc.ev_main[k], st);
     if (m > 0) {
       cudaStream_t gs = two_chains ? side : st;
-      if (two_chains) {
-        cudaEventRecord(sc.ev_main[k], st);
-        cudaStreamWaitEvent(side, sc.ev_main[k], 0);
-      }
+      if (two_chains) cudaStreamWaitEvent(side, sc.ev_main[k], 0);
       double* L21 = L + (o + nb0) * ldl + o;
       // panel  L21 = A21 * W11^T   (op(B) = W11^T is upper triangular)
       int rc = gemm1<double>(false, true, m, nb0, nb0, 1.0, Awork + (o + nb0) * lda + o, lda, W + o * ldw + o, ldw, 0.0,
                              L21, ldl, TRI_NONE, TRI_UPPER, 0, gs);
       if (rc) return rc;
+      if (eager_inv) cudaEventRecord(sc.ev_panel[k], side);
       const int m2 = m - nb0;
       if (m2 > 0) {
         // trailing update below block row k+1:  A22[nb0:, :] -= L21[nb0:, :] * L21^T  on the tiles with col <= row + nb0
@@ -742,8 +961,36 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
         last_side = k;
       }
     }
+    if (eager_inv) {
+      bool waited = false;
+      for (int lev = 0; lev < nlev && ((k + 1) & ((1 << lev) - 1)) == 0; ++lev) {
+        const int idx = (k + 1) >> lev;                  // groups of 2^lev blocks finished so far
+        const int b = nb0 << lev;
+        if (!waited) {
+          cudaStreamWaitEvent(inv, sc.ev_main[k], 0);    // block k is factorised and inverted
+          waited = true;
+        }
+        if (idx & 1) {                                   // a TOP half just ended: T = L21 W11 (needs the panel of column k)
+          const int64_t s0 = (int64_t)(idx - 1) * b;
+          cudaStreamWaitEvent(inv, sc.ev_panel[k], 0);
+          int rc = gemm<double>(false, false, b, b, b, 1.0, L + (s0 + b) * ldl + s0, ldl, W + s0 * ldw + s0, ldw, 0.0,
+                                W + s0 * ldw + (s0 + b), ldw, TRI_NONE, TRI_LOWER, 0, 1, 0, 0, 0, inv);
+          if (rc) return rc;
+          break;
+        }
+        const int64_t s0 = (int64_t)(idx - 2) * b;       // a BOTTOM half just ended: W21 = -W22 T, the pair is complete
+        int rc = gemm<double>(false, false, b, b, b, -1.0, W + (s0 + b) * ldw + (s0 + b), ldw, W + s0 * ldw + (s0 + b), ldw, 0.0,
+                              W + (s0 + b) * ldw + s0, ldw, TRI_LOWER, TRI_NONE, 0, 1, 0, 0, 0, inv);
+        if (rc) return rc;
+      }
+    }
   }
   if (two_chains && last_side >= 0) cudaStreamWaitEvent(st, sc.ev_side[last_side], 0);
+  if (eager_inv) {
+    cudaEventRecord(sc.ev_inv, inv);
+    cudaStreamWaitEvent(st, sc.ev_inv, 0);
+    return DSVGP_OK;
+  }
   // recursive inverse; Awork (no longer needed) is the scratch for T = L21 * W11
   for (int lev = 0; lev < nlev; ++lev) {
     const int b = nb0 << lev, npairs = nblk >> (lev + 1);

@@ -16,5 +16,6 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
 // 1: round-1 diagonal-block kernel (in-kernel DMMA prologue, scalar updates); 2 (default): diag_prepare + all-DMMA block kernel
 void set_chol_variant(int v);
 int get_chol_variant();
+void set_potrf_debug(long long* p);   // profiling aid: device buffer of 64 clock64() stamps (nullptr = off)
 
 }  // namespace dsvgp

@@ -31,6 +31,14 @@ CHOL_RETRY = (1e-6, 1e-5, 1e-4)   # psd_safe_cholesky(jitter=1e-6): 1e-6 * 10**i
 USE_TC = True      # fp32 model: run the big whitening products on tcgen05 (set False to force the mma.sync kernels)
 USE_FP16 = True    # ... as 3xFP16 (kind::f16, scaled two-half operands) instead of 3xTF32: same 22 significand bits, 1.6x faster
 DENSE_D = True     # 3xFP16 training path: (S - I) A as ONE dense product with D = E + E^T + E E^T (False: B' = E^T A, C = E B + B')
+WHITEN_FP64 = "auto"  # fp32 model: run the two products that multiply by W = L^-1 (A = W K_zx, dK_zx = W^T dA) in fp64 on DMMA, the
+                      # way the reference does its triangular solves (DGVS.py:181,183), instead of as 3xFP16.  |W||K_zx| / |A| is the
+                      # conditioning of K_zz + 1e-3 I (~4e2 at the BASELINE inputs, 1e3-1e4 for long lengthscales / converged q(u)):
+                      # a 22-bit operand split and fp32 accumulation carry that factor into A, fp64 does not.  Costs 2 M'^2 n' DMMA
+                      # flops per step (+1.2 ms at C3 with n = 512; 31 ms at n = 16384).  True / False / "auto" = whenever the
+                      # minibatch is small enough for that to be cheap (n' <= WHITEN_FP64_MAX_NQ: every minibatch size the
+                      # reference's drivers ship).  DESIGN.md section 4.2 has the measured error table of both forms.
+WHITEN_FP64_MAX_NQ = 2048
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
 F16 = torch.float16
@@ -115,6 +123,7 @@ class Workspace:
             self.Eh, self.El, self.ETh, self.ETl = sh(), sh(), sh(), sh()
             self.Dh, self.Dl = sh(), sh()               # split of D = S - I = E + E^T + E E^T (training: C = D A)
             self.P = e(Mq, self.ldg)[:, :Mq]            # E E^T (lower tiles)
+        self.A64 = self.B64 = None                      # fp64 operands of the W products (Engine._w64 allocates them)
         if self.tc:
             if not self.tch:
                 self.lo1, self.lo2, self.lo3 = (e(Mq, self.ldn) for _ in range(3))   # "lo" parts of the current big operands
@@ -314,6 +323,14 @@ class Engine:
         ws.canon = None
         return ops.normalize_dirs(Vx, T)[0]
 
+    @staticmethod
+    def _w64(ws):
+        """fp64 whitening for this workspace?  (allocates its two fp64 M' x n' operands on first use)"""
+        on = WHITEN_FP64 is True or (WHITEN_FP64 == "auto" and ws.nq <= WHITEN_FP64_MAX_NQ)
+        if on and getattr(ws, "A64", None) is None:
+            ws.A64, ws.B64 = (torch.empty(ws.Mq, ws.ldn, dtype=F64, device=ws.A.device) for _ in range(2))
+        return on
+
     # ------------------------------------------------------------------------------------------------ forward
     @staticmethod
     def _assemble(ws, f, P, x, wx, need_C=True):
@@ -322,8 +339,11 @@ class Engine:
         Mq, nq = ws.Mq, ws.nq
         tc = ws.tc and f.tc
         if ws.tch and f.tch:
+            if Engine._w64(ws):
+                # fp64 whitening: K_zx in the model's fp32 arithmetic (what the reference's kernel returns), widened below
+                ops.kdir_fwd(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, canon=ws.canon)
             # 3xFP16 path: K_zx leaves the assembly kernel only as the two-half split of K * sK (no fp32 matrix at all)
-            if not ops.kdir_fwd_half(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, ws.Kh, ws.Kl, f.scales[1:2], canon=ws.canon):
+            elif not ops.kdir_fwd_half(P.Z, f.uzT, ws.p, x, wx, ws.p2, f.hyp, ws.Kzx, ws.Kh, ws.Kl, f.scales[1:2], canon=ws.canon):
                 ops.split_half(ws.Kzx, f.scales[1:2], ws.Kh, ws.Kl, rows=Mq, cols=nq)
             if need_C and DENSE_D:
                 # training: D = S - I = E + E^T + E E^T explicitly (every term is small when S ~ I: no cancellation), so
@@ -367,8 +387,15 @@ class Engine:
             Engine._assemble(ws, f, P, x, wx, need_C)
         if ws.tch and f.tch:
             sc, H = f.scales, TCH_CHUNK
-            ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
-                         Ch=(ws.Ah, ws.Al), c_scale=sc[3:4])                                  # A = L^-1 K_zx (+ its split)
+            if Engine._w64(ws):
+                # K_zx -> fp64, A = W K_zx on DMMA (W = L^-1 in fp64), back to fp32 + the two-half split the next products read
+                ops.cast2d(ws.Kzx, ws.B64, Mq, nq)
+                ops.gemm(f.W, ws.B64, ws.A64, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)
+                ops.cast2d(ws.A64, A, Mq, nq)
+                ops.split_half(ws.A64, sc[3:4], ws.Ah, ws.Al, rows=Mq, cols=nq)
+            else:
+                ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
+                             Ch=(ws.Ah, ws.Al), c_scale=sc[3:4])                              # A = L^-1 K_zx (+ its split)
             if need_C and DENSE_D:
                 ops.gemm_tch((ws.Dh, ws.Dl), (ws.Ah, ws.Al), C, Mq, nq, Mq, sc[13:14], chunk=H)   # C = (S - I) A, dense
                 ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C, cmax=f.maxbits[5:6])
@@ -433,7 +460,14 @@ class Engine:
             ops.mirror_lower(ws.G, Mq)
             if reducer is not None:
                 reducer.begin(ws.big)
-            ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
+            if self._w64(ws):
+                # dA = m g_mu^T + 2 C diag(g_var) in fp64 (torch glue on M' x n' numbers), dK_zx = W^T dA on DMMA
+                torch.mul(C[:, :nq], gvar, out=ws.B64[:, :nq])
+                ws.B64[:, :nq].mul_(2.0).addmm_(P.m.double().unsqueeze(1), gmu.double().unsqueeze(0))
+                ops.gemm(f.W, ws.B64, ws.A64, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
+                ops.cast2d(ws.A64, dKzx, Mq, nq)
+            else:
+                ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             # (E, E^T as fp32 + lo for the two M'^3 products of the tail were made by _assemble)
         else:

@@ -109,6 +109,9 @@ int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t
  * rank-8 updates and inverse), 2 (default) = a small multi-CTA kernel forms the update of the next diagonal block and the
  * block kernel does every bulk operation as 8x8 DMMA tiles.  Returns the value in force.  Results agree to rounding. */
 int dsvgp_set_chol_variant(int v);
+/* profiling aid: a device buffer of 64 int64 that one diagonal-block kernel fills with clock64() stamps at its phase
+ * boundaries (NULL switches it off); see scratch/potrf_phases.py */
+int dsvgp_set_potrf_debug(void* buf);
 int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0, int nlev, int* info, dsvgp_stream_t s);
 
 /* C = alpha*op(A)*op(B) + beta*C, triangle-aware, batched -- every dense product of the strategy

@@ -15,7 +15,7 @@ for Mq in (250, 448, 1024, 1500, 3072, 3200):
     Lr = torch.linalg.cholesky(A)
     Wr = torch.linalg.inv(Lr)
     Mp, nb0, nlev = ops.chol_plan(Mq)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         _lib.call_raw("dsvgp_set_chol_variant", variant)
         Aw = torch.empty(Mp, Mp, dtype=F64, device="cuda")
         L = torch.full((Mp, Mp), float("nan"), dtype=F64, device="cuda")
@@ -48,4 +48,4 @@ for Mq in (250, 448, 1024, 1500, 3072, 3200):
         torch.cuda.synchronize()
         print(f"Mq={Mq} Mp={Mp} nb0={nb0} nlev={nlev} variant {variant}: info {int(info.item())} errL {eL:.1e} errW {eW:.1e} "
               f"chol+inv {tot - e0.elapsed_time(e1) / 10:.3f} ms", flush=True)
-_lib.call_raw("dsvgp_set_chol_variant", 2)
+_lib.call_raw("dsvgp_set_chol_variant", 3)

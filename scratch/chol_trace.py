@@ -9,7 +9,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from dsvgp_b200 import ops, _lib
 Mq = int(sys.argv[1]) if len(sys.argv) > 1 else 3072
-variant = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+variant = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 _lib.call_raw("dsvgp_set_chol_variant", variant)
 F64 = torch.float64
 g = torch.Generator().manual_seed(Mq)

@@ -29,12 +29,12 @@ for (variant, n, d, M, p, ell, kind) in CASES:
     cv, cg = O.elbo_and_grads(P, x, Vx, y, nd, variant, structure="reference")
     cm, cvv = O.predict(P, x, Vx, variant, "reference")
     rows["cpu_ref_fp32"] = (abs(float(cv) - float(rv)) / abs(float(rv)), {k: T.rel(cg[k], rg[k]) for k in rg}, T.rel(cm, mean), T.rel(cvv, var))
-    for name, (tc, h) in {"3xFP16": (True, True), "3xTF32": (True, False), "mma.sync": (False, False)}.items():
-        engine.USE_TC, engine.USE_FP16 = tc, h
+    for name, (tc, h, w64) in {"3xFP16": (True, True, False), "3xFP16+W64": (True, True, True), "mma.sync": (False, False, False)}.items():
+        engine.USE_TC, engine.USE_FP16, engine.WHITEN_FP64 = tc, h, w64
         engine.ENGINE._ws.clear(), engine.ENGINE._fac.clear()
         model, lik, val, grads, out = T.run_step(variant, P, x, Vx, y, nd, d, F32)
         rows[name] = (abs(float(val) - float(rv)) / abs(float(rv)), {k: T.rel(grads[k], rg[k]) for k in rg}, T.rel(out.mean, mean), T.rel(out.variance, var))
-    engine.USE_TC, engine.USE_FP16 = True, True
+    engine.USE_TC, engine.USE_FP16, engine.WHITEN_FP64 = True, True, False
     print(f"== {variant} n={n} d={d} M={M} p={p} ell={ell} {kind}: elbo {float(rv):.4f} max|m| {float(P.m.abs().max()):.2f}")
     for name, (ev, eg, em, evar) in rows.items():
         print(f"  {name:13s} elbo {ev:.1e} mean {em:.1e} var {evar:.1e} | " + " ".join(f"{k}:{v:.1e}" for k, v in eg.items()))
