@@ -43,8 +43,10 @@ class Reducer:
 
     One Reducer per model (model.variational_strategy._reducer), so that other models of the process stay unsharded."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, shard_tail=True):
         self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.shard_tail = shard_tail      # also split the replicated O(M'^3) Cholesky-backward tail over the ranks (engine._tail_panel)
         self._pending = None
 
     def begin(self, big):
@@ -58,13 +60,18 @@ class Reducer:
         w.wait()
 
 
-def enable(model, n_global, group=None):
+    def reduce_tail(self, small2):
+        """second, tiny exchange of a step with a sharded tail: every rank's share of dK_zz contracted with dK_zz/dtheta"""
+        dist.all_reduce(small2, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def enable(model, n_global, group=None, shard_tail=True):
     """Make every subsequent ELBO step of `model` a shard of a global minibatch of `n_global` points."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     vs = model.variational_strategy
     vs._n_global = int(n_global)
-    vs._reducer = Reducer(group)
+    vs._reducer = Reducer(group, shard_tail)
 
 
 def disable(model):

@@ -146,6 +146,9 @@ class Workspace:
         self.sc = self.small[:8]
         self.gZ = self.small[8: 8 + M * d].view(M, d)
         self.gVz = self.small[8 + M * d:].view(M * p, d) if p else None
+        self.small2 = torch.zeros_like(self.small)        # sharded tail (N > 1): this rank's panels, summed over ranks separately
+        self.gZ2 = self.small2[8: 8 + M * d].view(M, d)
+        self.gVz2 = self.small2[8 + M * d:].view(M * p, d) if p else None
         self.kl = torch.zeros(1, dtype=F64, device=device)
         self.scratch = e(max(8192, 2 * ((nq + 255) // 256) + 64), dt=F64)   # elbo_terms / pll_terms: 2 * ceil(nq / 256) partial sums
         self.scratch_kl = e(512, dt=F64)           # (its own partial-sum buffer: the KL runs on the side stream)
@@ -508,12 +511,65 @@ class Engine:
         # is strictly upper, so  tril(L^T dL) = -tril(X)  EXACTLY and  dK_zz = sym(L^-T Phi(L^T dL) L^-1) = -sym(W^T Phi(X) W):
         # the two M'^3 fp64 products dL = -tril(W^T X) and Y = L^T dL of round 1 are not needed at all (0.78 ms of 2.1 at C3).
         ops.phi_lower(ws.Xd, ws.Psi, Mq)                                                              # Phi(X): tril, halved diagonal
-        ops.gemm(ws.Psi, W, ws.Y, a_tri=TRI_LOWER, b_tri=TRI_LOWER, c_tri=1, alpha=-1.0, M=Mq, N=Mq, K=Mq)   # Y = -Phi(X) W (lower)
-        ops.gemm(W, ws.Y, ws.S, ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, M=Mq, N=Mq, K=Mq)          # W^T (-Phi(X) W)
-        ops.symmetrize(ws.S, Mq)
-        ops.kdir_bwd(P.Z, f.uz64, f.invz64, ws.p, P.Z, f.uz64, ws.p, f.hyp, ws.S, ws.gZ, ws.gVz, ws.sc[4:6],
-                     scale=2.0)
+        shards = self._tail_shards(reducer)
+        if shards is None:
+            ops.gemm(ws.Psi, W, ws.Y, a_tri=TRI_LOWER, b_tri=TRI_LOWER, c_tri=1, alpha=-1.0, M=Mq, N=Mq, K=Mq)   # Y = -Phi(X) W (lower)
+            ops.gemm(W, ws.Y, ws.S, ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, M=Mq, N=Mq, K=Mq)          # W^T (-Phi(X) W)
+            ops.symmetrize(ws.S, Mq)
+            ops.kdir_bwd(P.Z, f.uz64, f.invz64, ws.p, P.Z, f.uz64, ws.p, f.hyp, ws.S, ws.gZ, ws.gVz, ws.sc[4:6],
+                         scale=2.0)
+        else:
+            # N > 1: the two fp64 products and the K_zz assembly backward are SHARDED over the ranks by column panels of
+            # dK_zz (every rank holds X, W; panel J of Y = -Phi(X) W and of S = W^T Y needs nothing from the other panels),
+            # and what is summed over ranks is the contraction of S[:, J] with dK_zz/d(Z, V_z, ell, os) -- 250 KB -- instead
+            # of the replicated 1.3 ms of DMMA work.  sum_ij S_ij dK_ij needs no symmetrisation (dK/dtheta is symmetric):
+            # row side + column side of the unsymmetrised panel.
+            ws.small2.zero_()
+            for rank, world in shards:
+                for c0, c1 in self.tail_panels(Mq, ws.p + 1, rank, world):
+                    self._tail_panel(ws, f, P, c0, c1)
+            if reducer is not None:
+                reducer.reduce_tail(ws.small2)
+            ws.small.add_(ws.small2)
         ops.var_grads(ws.H, P.Ls_raw, ws.t, P.m, inv_num_data, ws.gm, ws.gLs)
+
+    tail_shards_debug = None      # tests: a world size whose panels THIS process loops over (single-GPU check of the sharded tail)
+
+    def _tail_shards(self, reducer):
+        """[(rank, world), ...] whose column panels of the tail this process computes, or None for the unsharded tail"""
+        if self.tail_shards_debug:
+            return [(r, self.tail_shards_debug) for r in range(self.tail_shards_debug)]
+        if reducer is not None and getattr(reducer, "world", 1) > 1 and getattr(reducer, "shard_tail", True):
+            return [(reducer.rank, reducer.world)]
+        return None
+
+    @staticmethod
+    def tail_panels(Mq, q, rank, world):
+        """Column panels [c0, c1) of dK_zz owned by `rank`: 2 * world blocks of whole inducing points (q = p + 1 columns
+        each); block b and block 2 * world - 1 - b go to the same rank, because the cost of a panel falls with c0 (only
+        rows >= c0 of the lower-triangular factors take part)."""
+        M, nb = Mq // q, 2 * world
+        bounds = [(M * b) // nb * q for b in range(nb + 1)]
+        return [(bounds[b], bounds[b + 1]) for b in (rank, nb - 1 - rank) if bounds[b + 1] > bounds[b]]
+
+    @staticmethod
+    def _tail_panel(ws, f, P, c0, c1):
+        """contribution of the column panel J = [c0, c1) of dK_zz = -W^T Phi(X) W to d(Z, V_z, ell, os), into ws.small2"""
+        Mq, p, q = ws.Mq, ws.p, ws.p + 1
+        W, nJ, Kk = f.W, c1 - c0, ws.Mq - c0
+        Yp = ws.Y[c0:, c0:c1]                              # only rows >= c0 of Y[:, J] are non-zero (lower x lower)
+        ops.gemm(ws.Psi[c0:, c0:], W[c0:Mq, c0:c1], Yp, a_tri=TRI_LOWER, b_tri=TRI_LOWER, c_tri=1, alpha=-1.0, M=Kk, N=nJ, K=Kk)
+        if c0 > 0:                                         # S[:c0, J] = W[c0:, :c0]^T Y[c0:, J]   (dense block of W)
+            ops.gemm(W[c0:Mq, :c0], Yp, ws.S[:c0, c0:c1], ta=True, b_tri=TRI_LOWER, M=c0, N=nJ, K=Kk)
+        ops.gemm(W[c0:Mq, c0:Mq], Yp, ws.S[c0:, c0:c1], ta=True, a_tri=TRI_UPPER, b_tri=TRI_LOWER, M=Kk, N=nJ, K=Kk)
+        j0, j1 = c0 // q, c1 // q                          # the inducing points of the panel
+        Sp = ws.S[:, c0:c1]
+        uz, iz = f.uz64, f.invz64
+        sl = slice(j0 * p, j1 * p)
+        gZ2, gV2, sc2 = ws.gZ2, ws.gVz2, ws.small2[4:6]
+        ops.kdir_bwd(P.Z, uz, iz, p, P.Z[j0:j1], uz[sl] if p else None, p, f.hyp, Sp, gZ2, gV2, sc2)                 # row side
+        ops.kdir_bwd(P.Z[j0:j1], uz[sl] if p else None, iz[sl] if p else None, p, P.Z, uz, p, f.hyp, Sp, gZ2[j0:j1],
+                     gV2[sl] if p else None, None, dk_trans=True)                                                    # column side
 
     @staticmethod
     def _collect(ws, f, P, T, noise_terms):

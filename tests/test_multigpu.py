@@ -61,3 +61,39 @@ def test_sharded_step_two_gpus():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert dict(out) == {0: "ok", 1: "ok"}
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("dtype,M,n", [(torch.float64, 96, 300), (torch.float32, 256, 1024), (torch.float32, 1024, 512)])
+def test_sharded_tail_equals_replicated_tail_on_one_gpu(world, dtype, M, n):
+    """The N > 1 form of the Cholesky-backward tail (column panels of dK_zz per rank, contraction summed over ranks) run for
+    every rank of a `world` in ONE process: the summed contributions must equal the replicated tail's gradients."""
+    import bench
+    from dsvgp_b200 import engine, gp
+    wl = dict(bench.WORKLOADS["C3"], M=M, n=n, N=50000)
+    dev = torch.device("cuda", 0)
+    model, lik = bench.build_model(wl, dtype, dev)
+    mll = gp.VariationalELBO(lik, model, num_data=(wl["d"] + 1) * wl["N"])
+    x, V, y = (t.to(dev) for t in bench.synth_batch(n, wl["d"], wl["p"], "dsvgp", dtype, "cpu", 11))
+    params = list(model.parameters()) + list(lik.parameters())
+
+    def grads():
+        for q in params:
+            q.grad = None
+        loss = -mll(lik(model(x, derivative_directions=V)), y)
+        loss.backward()
+        return float(loss), torch.cat([q.grad.reshape(-1).double() for q in params])
+
+    l0, g0 = grads()
+    engine.ENGINE.tail_shards_debug = world
+    try:
+        l1, g1 = grads()
+    finally:
+        engine.ENGINE.tail_shards_debug = None
+    assert l0 == l1
+    err = float((g1 - g0).abs().max() / g0.abs().max())
+    assert err < (1e-11 if dtype == torch.float64 else 2e-6), err
+    # the panels partition the columns
+    Mq, q = M * 3, 3
+    cover = sorted(c for r in range(world) for c in engine.Engine.tail_panels(Mq, q, r, world))
+    assert cover[0][0] == 0 and cover[-1][1] == Mq and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
