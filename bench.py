@@ -393,9 +393,19 @@ def main():
                 arm.shard(ns * world)
             ms = ms_step if ns == n else arm.time_steps(ns, 2000 + rank, 3, 5)
             row = {"n_per_gpu": ns, "global_batch": ns * world, "ms_per_step": ms, "points_per_s": ns * world / (ms * 1e-3)}
+            p2s = 0 if wl["variant"] == "dfree" else wl["p"]
+            row["whitening"] = ("fp64 DMMA (engine.WHITEN_FP64 = 'auto': the two products with W = L^-1 as the reference's fp64 "
+                                "triangular solves)") if (_eng.WHITEN_FP64 == "auto" and ns * (p2s + 1) <= _eng.WHITEN_FP64_MAX_NQ) \
+                else "3xFP16 tcgen05"
             if ns <= graphs.MAX_GRAPH_N and world == 1:
                 row["ms_per_step_cuda_graph"] = graphs.time_graphed_step(arm, ns, 2000 + rank, 3, 10)
                 row["points_per_s_cuda_graph"] = ns / (row["ms_per_step_cuda_graph"] * 1e-3)
+            if row["whitening"].startswith("fp64") and world == 1:
+                old = _eng.WHITEN_FP64                      # the same minibatch with the 3xFP16 products forced, for comparison
+                _eng.WHITEN_FP64 = False
+                arm.release()
+                row["ms_per_step_3xfp16_whitening"] = arm.time_steps(ns, 2000 + rank, 3, 5)
+                _eng.WHITEN_FP64 = old
             sweep.append(row)
             if ns != n:
                 arm.release()
@@ -569,9 +579,32 @@ def main():
             a2 = Arm(w2, device, 0, 1)
             ms = a2.time_steps(w2["n"], 77, 3, 5)
             ms_ref_n = a2.time_steps(w2["n_ref"], 78, 3, 5)
+            # kernel assembly of this workload alone (K_zx, K only), against HBM and -- where the dot products dominate
+            # (d = 60) -- against the fp32 FMA pipe: per point pair 2 d (1 + p1)(1 + p2) flops for Delta.Delta, Delta.u,
+            # Delta.w, u.w, nominal fp32 peak 148 SMs x 128 FMA x 2 x sm_max_mhz
+            dt2 = a2.dtype
+            x2, V2, _ = (t.to(device) for t in a2.batch(w2["n"], 77))
+            pp2 = 0 if w2["variant"] == "dfree" else w2["p"]
+            ws2 = ENGINE.workspace(device, dt2, w2["n"], w2["d"], w2["M"], w2["p"], pp2)
+            f2 = ENGINE.factor(device, dt2, w2["d"], w2["M"], w2["p"])
+            wx2 = ENGINE._data_dirs(ws2, V2, dt2)
+            Z2 = a2.model.variational_strategy.inducing_points.detach()
+            asm = lambda: ops.kdir_fwd(Z2, f2.uzT, w2["p"], x2, wx2, pp2, f2.hyp, ws2.Kzx, canon=ws2.canon)
+            asm()
+            ms_a = timed_local(asm, 10)
+            sz = 8 if dt2 == torch.float64 else 4
+            Mq2, nq2 = w2["M"] * (w2["p"] + 1), w2["n"] * (pp2 + 1)
+            by2 = sz * (float(Mq2) * nq2 + (w2["M"] + w2["n"]) * w2["d"] + (w2["M"] * w2["p"] + w2["n"] * pp2) * w2["d"])
+            fl2 = 2.0 * w2["d"] * (1 + w2["p"]) * (1 + pp2) * w2["M"] * w2["n"]
+            fp32_peak = 148 * 128 * 2 * 1.965e9
             extra[name] = {"workload": make_config(name, w2, 1)["workload"], "n": w2["n"], "ms_per_step": ms,
                            "points_per_s": w2["n"] / (ms * 1e-3), "n_ref": w2["n_ref"], "ms_per_step_at_n_ref": ms_ref_n,
-                           "dtype": w2["dtype"]}
+                           "dtype": w2["dtype"],
+                           "assembly": {"ms": ms_a, "bytes": by2, "gbs": by2 / (ms_a * 1e-3) / 1e9, "hbm_frac": by2 / (ms_a * 1e-3) / 1e9 / pk["hbm"],
+                                        "dot_product_flops": fl2,
+                                        "fp32_pipe_frac": (fl2 / (ms_a * 1e-3) / fp32_peak) if dt2 == torch.float32 else None,
+                                        "bound": "fp32 FMA pipe" if (dt2 == torch.float32 and fl2 / fp32_peak > by2 / (pk["hbm"] * 1e9)) else "hbm"}}
+            del ws2, f2
             ENGINE._ws.clear(), ENGINE._fac.clear()
             del a2
             torch.cuda.empty_cache()

@@ -523,6 +523,7 @@ __device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, doub
 #pragma unroll
       for (int i = k + 1; i < 8; ++i) acc[i] = fma(-a[i][k], x[k], acc[i]);
     }
+    __syncwarp();                                         // all 32 lanes have read the block before 8 of them overwrite it
     if (lane < 8) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) Ws[(k0 + i) * ld + k0 + j] = x[i];       // (x[i] = 0 above the diagonal)
@@ -598,6 +599,7 @@ __device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, doub
         double acc[2] = {0.0, 0.0};
         dmma884(acc, a0, Ws[(k0 + g) * ld + k0 + t]);
         dmma884(acc, a1, Ws[(k0 + g) * ld + k0 + 4 + t]);
+        __syncwarp();                                     // every lane's fragment loads of this tile precede the in-place stores
         pa[2 * t] = acc[0];
         pa[2 * t + 1] = acc[1];
       }
@@ -735,11 +737,19 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
   const uint32_t rank = cluster_rank();
   long long* dbg = (row_offset == 0 || rank != 0) ? nullptr : g_potrf_dbg;
   DBG_T(61);
-  if (Aleft != nullptr) {
-    const int c0 = (int)rank * tcs, c1 = min(T, c0 + tcs), nc = max(c1 - c0, 0);
-    const int kmax_all = 8 * c1;                               // W11 lower: column j of Z needs k <= j only
+  const bool upd = Aleft != nullptr;
+  if (upd) {
+    // tile columns of this CTA, dealt out boustrophedon (0 1 2 3 3 2 1 0 0 1 ..): column j of Z needs k <= j only (W11 is
+    // lower triangular), so contiguous slices would give the last CTA 5x the work of the first (measured: 6.3k cycles of
+    // the leader waiting at the cluster barrier)
+    int tcol[4] = {0, 0, 0, 0}, nc = 0;
+    for (int c = 0; c < T; ++c) {
+      const int rnd = c / CL, pos = c % CL;
+      if ((uint32_t)((rnd & 1) ? CL - 1 - pos : pos) == rank && nc < 4) tcol[nc++] = c;
+    }
+    const int kmax_all = nc > 0 ? 8 * (tcol[nc - 1] + 1) : 0;
     if (nc > 0) {
-      for (int e = tid; e < nbp * (kmax_all >> 1); e += POTRF_THREADS) {        // 16-byte chunks
+      for (int e = tid; e < nbp * (kmax_all >> 1); e += POTRF_THREADS) {        // X = A[k,k-1], 16-byte chunks
         const int i = e / (kmax_all >> 1), c = 2 * (e - i * (kmax_all >> 1));
         if (i < nb && c + 1 < nb) {
           const uint32_t d = (uint32_t)__cvta_generic_to_shared(R0 + i * ld + c);
@@ -749,16 +759,15 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
           R0[i * ld + c + 1] = 0.0;
         }
       }
-      for (int e = tid; e < 8 * nc * kmax_all; e += POTRF_THREADS) {
-        const int r = e / kmax_all, c = e - r * kmax_all, j = 8 * c0 + r;
+      for (int e = tid; e < 8 * nc * kmax_all; e += POTRF_THREADS) {            // Y = this CTA's rows of W11(k-1)
+        const int r = e / kmax_all, c = e - r * kmax_all, j = 8 * tcol[r >> 3] + (r & 7);
         const bool in = j < nb && c <= j;
         cp_async8(Y + r * ld + c, in ? Wprev + (int64_t)j * ldw + c : Wprev, in);
       }
     }
-    if (nc == 0)                                          // (more CTAs than tile columns: this one contributes zero)
-      for (int e = tid; e < nbp * ld; e += POTRF_THREADS) R2[e] = 0.0;
     cp_async_wait_all();
     __syncthreads();
+    DBG_T(52);
     for (int ti = warp; ti < T && nc > 0; ti += POTRF_THREADS / 32) {          // Z slice: 8 x (8 nc) strips
       double acc[4][2];
 #pragma unroll
@@ -768,7 +777,7 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
         const double a = xa[k0];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < nc && k0 < 8 * (c0 + q + 1)) dmma884(acc[q], a, Y[(8 * q + g) * ld + k0 + t]);
+          if (q < nc && k0 < 8 * (tcol[q] + 1)) dmma884(acc[q], a, Y[(8 * q + g) * ld + k0 + t]);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -779,46 +788,56 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
         }
     }
     __syncthreads();
-    const int groups = (T + 2) / 3, nblocks = nc > 0 ? T * groups : 0;          // D_r = Zs Zs^T, lower tiles, into R2
-    for (int blk = warp; blk < nblocks; blk += POTRF_THREADS / 32) {
-      const int ri = blk / groups, cg = blk % groups;
-      if (3 * cg > ri) continue;
-      double acc[3][2];
+    DBG_T(53);
+    // D_r = Zs Zs^T on the lower tiles (contraction over this CTA's 8 nc columns), into R2 = R0 (X is dead).  Only the
+    // blocks (tile row ri, group of 3 tile columns cg <= ri / 3) that touch the lower triangle are dealt out.
+    int idx = 0;
+    for (int ri = 0; ri < T; ++ri)
+      for (int cg = 0; 3 * cg <= ri; ++cg, ++idx) {
+        if ((idx & 15) != warp) continue;
+        double acc[3][2];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
-      const double* za = Zs + (8 * ri + g) * ldz + t;
-      for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
-        const double a = za[k0];
+        for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const double* za = Zs + (8 * ri + g) * ldz + t;
+        for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
+          const double a = za[k0];
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (3 * cg + q <= ri) dmma884(acc[q], a, Zs[(8 * (3 * cg + q) + g) * ldz + k0 + t]);
+        }
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-          if (3 * cg + q <= ri) dmma884(acc[q], a, Zs[(8 * (3 * cg + q) + g) * ldz + k0 + t]);
+          if (3 * cg + q <= ri) {
+            double* dd = R2 + (8 * ri + g) * ld + 8 * (3 * cg + q) + 2 * t;
+            dd[0] = acc[q][0];
+            dd[1] = acc[q][1];
+          }
       }
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (3 * cg + q <= ri) {
-          double* dd = R2 + (8 * ri + g) * ld + 8 * (3 * cg + q) + 2 * t;
-          dd[0] = acc[q][0];
-          dd[1] = acc[q][1];
-        }
-    }
   }
+  DBG_T(54);
   cluster_barrier();                                   // every partial is in place (release / acquire at cluster scope)
-  if (rank == 0) {
-    // Ls = A[k,k] - sum_r D_r on the lower triangle, identity on the padding; X is dead, its region becomes Ls
-    const bool upd = Aleft != nullptr;
-    for (int i0 = warp; i0 < nbp; i0 += 2 * (POTRF_THREADS / 32)) {
+  DBG_T(55);
+  // A[k,k] - D_0 - D_1 - D_2 - D_3 on the lower triangle (identity on the padding), rows dealt out round-robin over the
+  // four CTAs (each reads one local and three remote partials -- the leader alone took 9.8k cycles for it), written into
+  // the LEADER's second region (Y / Zs are dead everywhere), which becomes Ls.
+  {
+    const uint32_t r1a = (uint32_t)__cvta_generic_to_shared(R1);
+    uint32_t r1lead;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r1lead) : "r"(r1a), "r"(0u));
+    const int rows_cta = (nbp - (int)rank + CL - 1) / CL;                      // rows rank, rank + 4, ..
+    for (int m0 = warp; m0 < rows_cta; m0 += 2 * (POTRF_THREADS / 32)) {
       double v[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * (POTRF_THREADS / 32);
+        const int m = m0 + u * (POTRF_THREADS / 32), i = (int)rank + CL * m;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = lane + 32 * q;
-          const bool in = i < nb && c <= i;
-          double a = in ? A[(int64_t)i * lda + c] : ((i < nbp && i == c) ? 1.0 : 0.0);
+          const bool in = m < rows_cta && i < nb && c <= i;
+          double a = in ? A[(int64_t)i * lda + c] : ((m < rows_cta && i == c) ? 1.0 : 0.0);
           if (in && upd) {
             const double* dp = R2 + i * ld + c;
-            const double d0 = *dp, d1 = ld_dsmem_f64(dp, 1), d2 = ld_dsmem_f64(dp, 2), d3 = ld_dsmem_f64(dp, 3);
+            const double d0 = ld_dsmem_f64(dp, 0), d1 = ld_dsmem_f64(dp, 1), d2 = ld_dsmem_f64(dp, 2), d3 = ld_dsmem_f64(dp, 3);
             a = (((a - d0) - d1) - d2) - d3;
           }
           v[u][q] = a;
@@ -826,19 +845,24 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * (POTRF_THREADS / 32);
+        const int m = m0 + u * (POTRF_THREADS / 32), i = (int)rank + CL * m;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = lane + 32 * q;
-          if (i < nbp && c < nbp) R0[i * ld + c] = v[u][q];
+          if (m < rows_cta && i < nbp && c <= i) {
+            const uint32_t dst = r1lead + (uint32_t)((i * ld + c) * sizeof(double));
+            asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst), "d"(v[u][q]) : "memory");
+          }
         }
       }
     }
   }
-  cluster_barrier();                                   // CTA 0 has read the remote partials: the others may go
+  DBG_T(56);
+  cluster_barrier();                                   // the leader's Ls is complete; nobody reads a partial any more
+  DBG_T(57);
   if (rank != 0) return;
-  for (int e = tid; e < nbp * ld; e += POTRF_THREADS) R1[e] = 0.0;              // Y / Zs are dead: their region becomes Ws
-  factor_invert_smem(R0, R1, ld, nbp, nb, info, row_offset, L, ldl, W, ldw, dbg);
+  for (int e = tid; e < nbp * ld; e += POTRF_THREADS) R0[e] = 0.0;              // D_0 is dead: its region becomes Ws
+  factor_invert_smem(R1, R0, ld, nbp, nb, info, row_offset, L, ldl, W, ldw, dbg);
 }
 
 void set_potrf_debug(long long* p) { cudaMemcpyToSymbol(g_potrf_dbg, &p, sizeof(p)); }

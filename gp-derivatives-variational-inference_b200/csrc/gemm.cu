@@ -52,7 +52,12 @@ gemm_kernel(GemmParams<T> p) {
   __shared__ __align__(16) T As[2][BM * LDS_];
   __shared__ __align__(16) T Bs[2][BN * LDS_];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // Heavy tiles first: with a triangular operand the k-range of a tile grows with its row (a lower: k <= r) or column
+  // (b upper: k <= c); CUDA hands out blockIdx in increasing order, so the longest tiles would start last and run alone at
+  // the end of the launch.  Reversing that index starts them first.
+  const int by = (p.a_tri == 1) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int bx = (p.b_tri == 2) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int m0 = by * BM, n0 = bx * BN;
   if (p.c_tri == 1 && n0 >= m0 + BM + p.c_off) return;     // tile strictly above the (shifted) diagonal
   const T* A = p.A + (int64_t)blockIdx.z * p.sA;
   const T* B = p.B + (int64_t)blockIdx.z * p.sB;
@@ -225,13 +230,30 @@ gemm_kernel(GemmParams<T> p) {
     }
   };
   if constexpr (F64) {
+    // a lane holds two adjacent columns of each 8x8 tile: 16-byte loads / stores when everything is 16-byte aligned
+    const bool v2 = ((p.ldc | ldd | (p.C2 ? (p.ldc2 | p.ldd2) : 0)) & 1) == 0 && (((uintptr_t)C | (uintptr_t)D) & 15) == 0 &&
+                    (!p.C2 || ((((uintptr_t)p.C2 | (uintptr_t)p.D2) & 15) == 0));
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = m0 + wm + 8 * i + g, c = n0 + wn + 8 * j + 2 * t;
-        put(r, c, (T)acc64[i][j][0]);
-        put(r, c + 1, (T)acc64[i][j][1]);
+        if (v2 && r < p.M && c + 1 < p.N) {
+          double2 res = make_double2((double)p.alpha * acc64[i][j][0], (double)p.alpha * acc64[i][j][1]);
+          if (p.beta != T(0)) {
+            const double2 dd = *reinterpret_cast<const double2*>(D + (int64_t)r * ldd + c);
+            res.x += (double)p.beta * dd.x;
+            res.y += (double)p.beta * dd.y;
+          }
+          *reinterpret_cast<double2*>(C + (int64_t)r * p.ldc + c) = res;
+          if (p.C2) {
+            const double2 ee = *reinterpret_cast<const double2*>(p.D2 + (int64_t)r * p.ldd2 + c);
+            *reinterpret_cast<double2*>(p.C2 + (int64_t)r * p.ldc2 + c) = make_double2(res.x + ee.x, res.y + ee.y);
+          }
+        } else {
+          put(r, c, (T)acc64[i][j][0]);
+          put(r, c + 1, (T)acc64[i][j][1]);
+        }
       }
   } else {
 #pragma unroll

@@ -41,12 +41,18 @@ constexpr int EPI_WARPS = 8;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's CTA 0
 // CG = 1: one CTA per 128x256 tile.  CG = 2: a CTA PAIR (tcgen05 cta_group::2) per 256x256 tile -- each CTA stages its
 // own 128 rows of A and its own 128 columns of B, so the operand bytes per SM drop by a third and one more stage fits.
-template <int CG> struct Geo {
-  static constexpr int BN_LOCAL = BN / CG;
-  static constexpr int B_BYTES = BN_LOCAL * BK * 4;                  // 32 KB / 16 KB
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // hi + lo of both operands: 96 KB / 64 KB
-  static constexpr int STAGES = CG == 1 ? 2 : 3;
+// BNT = 256 (one CTA or CTA pair per SM / SM pair) or, for CTA pairs only, BNT = 128 with TWO pairs resident per SM pair
+// (half the tensor memory, half the ring, 4 epilogue warps each): while one pair is in its fixed phases -- barrier set-up,
+// pipeline fill, the store phase of its tile -- the other pair's main loop keeps the tensor pipe busy.
+template <int CG, int BNT = BN> struct Geo {
+  static constexpr int BN_LOCAL = BNT / CG;
+  static constexpr int B_BYTES = BN_LOCAL * BK * 4;                  // 32 KB / 16 KB / 8 KB
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // hi + lo of both operands: 96 KB / 64 KB / 48 KB
+  static constexpr int STAGES = CG == 1 ? 2 : (BNT == BN ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI = 4 * (BNT / 128);                        // epilogue warps: one per (lane quarter, 128 columns)
+  static constexpr int NTHREADS = 32 * (2 + EPI);
+  static constexpr int TMEM_COLS = 2 * BNT;                          // double-buffered accumulator
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,11 +211,12 @@ __device__ __forceinline__ void store_half4(__half* dst, const float (&x)[4], __
   *reinterpret_cast<uint2*>(dst_lo) = *reinterpret_cast<const uint2*>(l);
 }
 
-template <int CG, bool H>
+template <int CG, bool H, int BNT = BN>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUtensorMap& mapAl, const CUtensorMap& mapBh,
                                              const CUtensorMap& mapBl, const Params& p) {
-  constexpr int STAGES = Geo<CG>::STAGES, STAGE_BYTES = Geo<CG>::STAGE_BYTES, B_BYTES = Geo<CG>::B_BYTES;
-  constexpr int BNL = Geo<CG>::BN_LOCAL;
+  using G = Geo<CG, BNT>;
+  constexpr int STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, B_BYTES = G::B_BYTES;
+  constexpr int BNL = G::BN_LOCAL;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -221,7 +228,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;        // position in the CTA pair; rank 0 issues the MMAs
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BNT;
   const int m0p = CG == 2 ? (m0 - (int)rank * BM) : m0;          // first row of the pair's 256-row tile
   if (p.c_lower && n0 >= m0p + BM * CG) return;                  // tile strictly above the diagonal (pair-uniform)
 
@@ -247,7 +254,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], EPI_WARPS * CG);
+      mbar_init(&tempty[b], G::EPI * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -255,8 +262,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
     if constexpr (CG == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
+    } else if constexpr (BNT == BN) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
   }
@@ -305,7 +315,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
       // instruction descriptor: D=f32, A=B=tf32, A K-major, B per flag, N=256, M=128 (256 for a CTA pair)
       // (kind::f16: A = B = f16 is format 0)
       const uint32_t fmt = H ? 0u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((p.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BNT >> 3) << 17) |
                              ((uint32_t)((BM * CG) >> 4) << 24);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES, c = i / p.chunk, buf = c & 1;
@@ -317,7 +327,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
         mbar_wait(&full[s], (i / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * BNT;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           // A: K-major, rows of 128 B, 8-row groups 1024 B apart; a k-step advances 32 B inside the swizzled row
@@ -379,7 +389,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
       const int buf = c & 1;
       mbar_wait(&tfull[buf], (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNT + h * 128);
 #pragma unroll
       for (int part = 0; part < 4; ++part) {
         float v[32];
@@ -520,7 +530,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapAh, const CUt
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else if constexpr (BNT == BN) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -547,6 +558,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tch2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                  const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
   gemm_tc_body<2, true>(mapAh, mapAl, mapBh, mapBl, p);
+}
+
+// 3xFP16, CTA pairs, 256 x 128 tiles, two pairs resident per SM pair
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Geo<2, 128>::NTHREADS, 2)
+gemm_tch2n_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                  const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  gemm_tc_body<2, true, 128>(mapAh, mapAl, mapBh, mapBl, p);
 }
 
 __global__ void split_lo_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ lo, int64_t ldl, int rows, int cols) {
@@ -656,6 +674,9 @@ static bool map_mnmajor_h(CUtensorMap* m, const __half* base, int64_t ld, int K,
 
 }  // namespace tc
 
+static int g_tc_tile_n = 256;    // 3xFP16 CTA-pair kernel: 256 (one pair per SM pair) or 128 (two pairs per SM pair)
+void set_tc_tile_n(int n) { g_tc_tile_n = (n == 128) ? 128 : 256; }
+int get_tc_tile_n() { return g_tc_tile_n; }
 static int g_tc_cta_group = 2;   // CTA pairs by default: +9% over single-CTA tiles on the C3 whitening product
 void set_tc_cta_group(int cg) { g_tc_cta_group = (cg == 2) ? 2 : 1; }
 int get_tc_cta_group() { return g_tc_cta_group; }
@@ -743,7 +764,8 @@ int gemm_tch(const void* Ah_, const void* Al_, int64_t lda, const void* Bh_, con
   if (!gemm_tch_supported(Ah, lda, Bh, ldb, b_kmajor, N) || !gemm_tch_supported(Al, lda, Bl, ldb, b_kmajor, N))
     return DSVGP_ERR_ARG;
   const int cg = g_tc_cta_group;
-  const int bnl = tc::BN / cg;
+  const int bnt = (cg == 2 && g_tc_tile_n == 128) ? 128 : tc::BN;
+  const int bnl = bnt / cg;
   CUtensorMap mAh, mAl, mBh, mBl;
   bool ok = tc::map_kmajor_h(&mAh, Ah, lda, M, K, tc::BM) && tc::map_kmajor_h(&mAl, Al, lda, M, K, tc::BM);
   if (b_kmajor) ok = ok && tc::map_kmajor_h(&mBh, Bh, ldb, N, K, bnl) && tc::map_kmajor_h(&mBl, Bl, ldb, N, K, bnl);
@@ -754,14 +776,16 @@ int gemm_tch(const void* Ah_, const void* Al_, int64_t lda, const void* Bh_, con
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
     if (cudaFuncSetAttribute(tc::gemm_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<1>::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(tc::gemm_tch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(tc::gemm_tch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2>::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::gemm_tch2n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Geo<2, 128>::SMEM_BYTES) != cudaSuccess)
       return DSVGP_ERR_LAUNCH;
     attr_set[dev & 63] = true;
   }
   const int mtiles = cg == 2 ? ((ceil_div(M, tc::BM) + 1) & ~1) : ceil_div(M, tc::BM);
   auto launch = [&](const tc::Params& pp, int nz) {
-    dim3 grid(mtiles, ceil_div(N, tc::BN), nz);
-    if (cg == 2) tc::gemm_tch2_kernel<<<grid, tc::THREADS, tc::Geo<2>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+    dim3 grid(mtiles, ceil_div(N, bnt), nz);
+    if (bnt == 128) tc::gemm_tch2n_kernel<<<grid, tc::Geo<2, 128>::NTHREADS, tc::Geo<2, 128>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
+    else if (cg == 2) tc::gemm_tch2_kernel<<<grid, tc::THREADS, tc::Geo<2>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
     else tc::gemm_tch_kernel<<<grid, tc::THREADS, tc::Geo<1>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, pp);
   };
   if (nsplit > 1) {

@@ -35,6 +35,9 @@ int gemm_tch(const void* Ah, const void* Al, int64_t lda, const void* Bh, const 
 // 1: one CTA per 128x256 tile (tcgen05 cta_group::1); 2: CTA pairs on 256x256 tiles (cta_group::2, 2-SM TMA, multicast commit)
 void set_tc_cta_group(int cg);
 int get_tc_cta_group();
+// 3xFP16 CTA-pair kernel: N extent of a tile, 256 (one pair per SM pair) or 128 (two pairs resident per SM pair)
+void set_tc_tile_n(int n);
+int get_tc_tile_n();
 
 int split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, cudaStream_t st);
 int transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, cudaStream_t st);

@@ -171,6 +171,10 @@ int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int 
 /* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles
  * (cta_group::2: each CTA stages half of the operands, 2-SM TMA loads, multicast commits).  Returns the value in force. */
 int dsvgp_set_tc_cta_group(int cg);
+/* N extent of a CTA-pair tile of dsvgp_gemm_tch_f32: 256 = one pair per SM pair (3 stages of 64 KB, 512 columns of tensor
+ * memory), 128 = TWO pairs resident per SM pair (2 stages of 48 KB, 256 columns each, 4 epilogue warps): one pair's fixed
+ * phases (set-up, pipeline fill, store of its tile) run under the other pair's main loop.  Returns the value in force. */
+int dsvgp_set_tc_tile_n(int n);
 int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s);
 int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s);
 

@@ -20,7 +20,7 @@ for _ in range(3):
     ops.cholesky_inverse(Aw, L, W, nb0, nlev, info)
 torch.cuda.synchronize()
 t = dbg.cpu().tolist()
-print("entry -> end of own loads", t[0] - t[61], " -> after barrier", t[1] - t[61])
+print("cluster kernel: entry->loads", t[52]-t[61], "Z", t[53]-t[52], "SYRK", t[54]-t[53], "barrier1", t[55]-t[54], "gather", t[56]-t[55], "barrier2", t[57]-t[56], "zero Ws + first sync", t[1]-t[57])
 for j in range(12):
     s1w0 = t[2 + 4 * j] - (t[1] if j == 0 else t[5 + 4 * (j - 1)])
     s1 = t[3 + 4 * j] - (t[1] if j == 0 else t[5 + 4 * (j - 1)])
