@@ -269,6 +269,167 @@ gemm_kernel(GemmParams<T> p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fp64 variant with an asynchronous operand pipeline (round 2).  ncu of the kernel above on the Cholesky-backward products
+// (profiles/r01_ncu_prof_tail.txt): DMMA pipe 73 % busy, 30 M shared-memory bank conflicts per launch -- all of them in the
+// register -> shared staging stores of the TRANSPOSED operand layouts (stride 20 doubles: 4-way) -- and a barrier pair per
+// 16-wide k-tile.  Here the operands go global -> shared with cp.async (no register staging, no staging stores), a k-major
+// shared layout (row stride 68 doubles: conflict-free DMMA fragments) is used whenever the operand is contiguous along its
+// non-contracted index, three stages are in flight and there is ONE barrier per k-tile.
+constexpr int AS_STAGES = 3;
+constexpr int AS_LDK = BK + 4;       // [row][k] layout (operand contiguous along k):   row stride 20 doubles
+constexpr int AS_LDM = BM + 4;       // [k][row] layout (operand contiguous along rows): row stride 68 doubles
+constexpr int AS_TILE = (BM * AS_LDK > BK * AS_LDM) ? BM * AS_LDK : BK * AS_LDM;    // doubles per operand per stage
+
+__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GEMM_THREADS, 3)
+gemm64_async_kernel(GemmParams<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);                  // [AS_STAGES][AS_TILE]
+  double* Bs = As + AS_STAGES * AS_TILE;                             // [AS_STAGES][AS_TILE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int by = (p.a_tri == 1) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;      // heavy tiles first
+  const int bx = (p.b_tri == 2) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int m0 = by * BM, n0 = bx * BN;
+  if (p.c_tri == 1 && n0 >= m0 + BM + p.c_off) return;
+  const double* A = p.A + (int64_t)blockIdx.z * p.sA;
+  const double* B = p.B + (int64_t)blockIdx.z * p.sB;
+  double* C = p.C + (int64_t)blockIdx.z * p.sC;
+  const double* D = p.D ? p.D : C;
+  const int64_t ldd = p.D ? p.ldd : p.ldc;
+
+  int kbeg = 0, kend = p.K;
+  if (p.a_tri == 1) kend = min(kend, m0 + BM);
+  if (p.a_tri == 2) kbeg = max(kbeg, m0);
+  if (p.b_tri == 1) kbeg = max(kbeg, n0);
+  if (p.b_tri == 2) kend = min(kend, n0 + BN);
+  kbeg = (kbeg / BK) * BK;
+  const int nkt = kbeg < kend ? (kend - kbeg + BK - 1) / BK : 0;
+
+  // element (r, k) of op(A): TA ? A[k*lda + r] : A[r*lda + k].  Shared: TA ? [k][r] (stride AS_LDM) : [r][k] (stride AS_LDK).
+  auto issue = [&](int kt, int stage) {
+    const int k0 = kbeg + kt * BK;
+    double* as = As + stage * AS_TILE;
+    double* bs = Bs + stage * AS_TILE;
+#pragma unroll
+    for (int q = 0; q < BM * BK / GEMM_THREADS; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int r, k;
+      if (!TA) { r = e / BK; k = e % BK; } else { k = e / BM; r = e % BM; }
+      const int gr = m0 + r, gk = k0 + k;
+      bool ok = gr < p.M && gk < p.K;
+      if (p.a_tri == 1) ok = ok && gk <= gr;
+      if (p.a_tri == 2) ok = ok && gk >= gr;
+      const double* src = ok ? (TA ? A + (int64_t)gk * p.lda + gr : A + (int64_t)gr * p.lda + gk) : A;
+      cp_async8_zfill(TA ? as + k * AS_LDM + r : as + r * AS_LDK + k, src, ok);
+    }
+#pragma unroll
+    for (int q = 0; q < BN * BK / GEMM_THREADS; ++q) {
+      const int e = tid + q * GEMM_THREADS;
+      int c, k;
+      if (TB) { c = e / BK; k = e % BK; } else { k = e / BN; c = e % BN; }
+      const int gc = n0 + c, gk = k0 + k;
+      bool ok = gc < p.N && gk < p.K;
+      if (p.b_tri == 1) ok = ok && gk >= gc;
+      if (p.b_tri == 2) ok = ok && gk <= gc;
+      const double* src = ok ? (TB ? B + (int64_t)gc * p.ldb + gk : B + (int64_t)gk * p.ldb + gc) : B;
+      cp_async8_zfill(TB ? bs + c * AS_LDK + k : bs + k * AS_LDM + c, src, ok);
+    }
+  };
+
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < AS_STAGES - 1; ++s) {
+    if (s < nkt) issue(s, s);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  for (int kt = 0; kt < nkt; ++kt) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(AS_STAGES - 2) : "memory");      // tile kt has landed (this thread's part)
+    __syncthreads();                                     // ... everybody's part; and everybody is done with tile kt-1's buffer
+    if (kt + AS_STAGES - 1 < nkt) issue(kt + AS_STAGES - 1, (kt + AS_STAGES - 1) % AS_STAGES);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const double* as = As + (kt % AS_STAGES) * AS_TILE;
+    const double* bs = Bs + (kt % AS_STAGES) * AS_TILE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = TA ? as[(kk + t) * AS_LDM + wm + 8 * i + g] : as[(wm + 8 * i + g) * AS_LDK + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = TB ? bs[(wn + 8 * j + g) * AS_LDK + kk + t] : bs[(kk + t) * AS_LDM + wn + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_f64(acc[i][j], af[i], bf[j]);
+    }
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+
+  auto put = [&](int r, int c, double v) {
+    if (r < p.M && c < p.N) {
+      const double res = (p.beta == 0.0) ? p.alpha * v : p.alpha * v + p.beta * D[(int64_t)r * ldd + c];
+      C[(int64_t)r * p.ldc + c] = res;
+      if (p.C2) p.C2[(int64_t)r * p.ldc2 + c] = res + p.D2[(int64_t)r * p.ldd2 + c];
+    }
+  };
+  const bool v2 = ((p.ldc | ldd | (p.C2 ? (p.ldc2 | p.ldd2) : 0)) & 1) == 0 && (((uintptr_t)C | (uintptr_t)D) & 15) == 0 &&
+                  (!p.C2 || ((((uintptr_t)p.C2 | (uintptr_t)p.D2) & 15) == 0));
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm + 8 * i + g, c = n0 + wn + 8 * j + 2 * t;
+      if (v2 && r < p.M && c + 1 < p.N) {
+        double2 res = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+        if (p.beta != 0.0) {
+          const double2 dd = *reinterpret_cast<const double2*>(D + (int64_t)r * ldd + c);
+          res.x += p.beta * dd.x;
+          res.y += p.beta * dd.y;
+        }
+        *reinterpret_cast<double2*>(C + (int64_t)r * p.ldc + c) = res;
+        if (p.C2) {
+          const double2 ee = *reinterpret_cast<const double2*>(p.D2 + (int64_t)r * p.ldd2 + c);
+          *reinterpret_cast<double2*>(p.C2 + (int64_t)r * p.ldc2 + c) = make_double2(res.x + ee.x, res.y + ee.y);
+        }
+      } else {
+        put(r, c, acc[i][j][0]);
+        put(r, c + 1, acc[i][j][1]);
+      }
+    }
+}
+
+static int g_gemm64_async = 1;
+void set_gemm64_async(int on) { g_gemm64_async = on ? 1 : 0; }
+int get_gemm64_async() { return g_gemm64_async; }
+
+template <bool TA, bool TB>
+static int launch_gemm64_async(const GemmParams<double>& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = 2 * AS_STAGES * AS_TILE * (int)sizeof(double);
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    if (cudaFuncSetAttribute(gemm64_async_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return DSVGP_ERR_LAUNCH;
+    attr[dev & 63] = true;
+  }
+  gemm64_async_kernel<TA, TB><<<grid, GEMM_THREADS, smem, st>>>(p);
+  return DSVGP_OK;
+}
+
 template <typename T>
 int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
          T* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC,
@@ -277,6 +438,18 @@ int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda
   if (!A || !B || !C || K < 0 || (C2 && !D2)) return DSVGP_ERR_ARG;
   GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri, c_off};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
+  if constexpr (sizeof(T) == 8) {
+    if (g_gemm64_async && K > 128) {      // (short contractions -- the rank-96 Cholesky updates -- do not amortise the pipeline fill)
+      int rc;
+      if (!ta && !tb) rc = launch_gemm64_async<false, false>(p, grid, st);
+      else if (!ta && tb) rc = launch_gemm64_async<false, true>(p, grid, st);
+      else if (ta && !tb) rc = launch_gemm64_async<true, false>(p, grid, st);
+      else rc = launch_gemm64_async<true, true>(p, grid, st);
+      if (rc) return rc;
+      CHECK_LAUNCH();
+      return DSVGP_OK;
+    }
+  }
   if (!ta && !tb) gemm_kernel<T, false, false><<<grid, GEMM_THREADS, 0, st>>>(p);
   else if (!ta && tb) gemm_kernel<T, false, true><<<grid, GEMM_THREADS, 0, st>>>(p);
   else if (ta && !tb) gemm_kernel<T, true, false><<<grid, GEMM_THREADS, 0, st>>>(p);

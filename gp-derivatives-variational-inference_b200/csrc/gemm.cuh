@@ -22,4 +22,8 @@ inline int gemm1(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int
   return gemm<T>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, a_tri, b_tri, c_tri, 1, 0, 0, 0, st);
 }
 
+// fp64 products: 1 (default) = cp.async-pipelined kernel, 0 = the register-staged kernel of round 1 (A/B knob)
+void set_gemm64_async(int on);
+int get_gemm64_async();
+
 }  // namespace dsvgp

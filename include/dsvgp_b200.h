@@ -121,6 +121,11 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s);
 int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const double* D, int64_t ldd, double* C2, int64_t ldc2, const double* D2, int64_t ldd2, dsvgp_stream_t s);
 
+/* A/B knob of dsvgp_gemm_f64: 1 (default) = cp.async-pipelined kernel (3 stages, k-major shared layouts for operands that are
+ * contiguous along their non-contracted index: no staging stores, conflict-free DMMA fragments, one barrier per k-tile),
+ * 0 = the register-staged kernel of round 1.  Returns the value in force. */
+int dsvgp_set_gemm64_async(int on);
+
 /* The same product on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA-fed, accumulators in tensor memory)
  * for the fp32 model's big whitening products -- TriangularLazyTensor.inv_matmul and the L_s products of
  * DirectionalGradVariationalStrategy.py:181-205 and their backward.  A: M x K row-major with explicit zeros outside

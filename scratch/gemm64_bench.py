@@ -33,3 +33,10 @@ print("check lower x lower:", float((C.tril() - ref).abs().max() / ref.abs().max
 for name, (fn, flops) in cases.items():
     ms = t(fn)
     print(f"{name:40s} {ms:7.3f} ms  {flops / ms / 1e9:6.1f} TFLOP/s")
+from dsvgp_b200 import _lib
+print("--- register-staged kernel of round 1 (dsvgp_set_gemm64_async(0))")
+_lib.call_raw("dsvgp_set_gemm64_async", 0)
+for name, (fn, flops) in cases.items():
+    ms = t(fn)
+    print(f"{name:40s} {ms:7.3f} ms  {flops / ms / 1e9:6.1f} TFLOP/s")
+_lib.call_raw("dsvgp_set_gemm64_async", 1)
