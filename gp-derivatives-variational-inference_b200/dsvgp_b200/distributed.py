@@ -13,6 +13,8 @@ after which every rank runs the identical O(M'^3) tail (Cholesky backward is lin
 reduce-then-tail equals tail-then-reduce) and ends with identical parameter gradients -- no second collective.
 The data term is normalised by the GLOBAL n' (the reference divides by the batch's event size, VariationalELBO).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -43,16 +45,24 @@ class Reducer:
 
     One Reducer per model (model.variational_strategy._reducer), so that other models of the process stay unsharded."""
 
-    def __init__(self, group=None, shard_tail=True):
+    def __init__(self, group=None, shard_tail=True, overlap=None):
         self.group = group
+        # overlap=False: the [G | t] all-reduce is issued blocking at `end` (after dK_zx / kdir_bwd) instead of underneath them
+        self.overlap = (os.environ.get("DSVGP_REDUCE_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.shard_tail = shard_tail      # also split the replicated O(M'^3) Cholesky-backward tail over the ranks (engine._tail_panel)
         self._pending = None
 
     def begin(self, big):
-        self._pending = dist.all_reduce(big, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if self.overlap:
+            self._pending = dist.all_reduce(big, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            self._big = big
 
     def end(self, small):
+        if not self.overlap and getattr(self, "_big", None) is not None:
+            dist.all_reduce(self._big, op=dist.ReduceOp.SUM, group=self.group)
+            self._big = None
         w = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         if self._pending is not None:
             self._pending.wait()
