@@ -113,6 +113,14 @@ int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float
   return gemm_tc(Ah, Al, lda, Bh, Bl, ldb, b_kmajor, M, N, K, (float)alpha, (float)beta, C, ldc, D, ldd, C2, ldc2, D2, ldd2, a_tri, c_lower, chunk, Clo, C2lo, nsplit, split_ws, ST(s));
 }
 int dsvgp_set_tc_tile_n(int n) { set_tc_tile_n(n); return get_tc_tile_n(); }
+int dsvgp_set_tc_persistent(int on) { set_tc_persistent(on); return get_tc_persistent(); }
+int dsvgp_set_tc_trace(void* buf, int cap_items) { set_tc_trace(static_cast<long long*>(buf), cap_items); return DSVGP_OK; }
+int dsvgp_tc_work_list(int M, int N, int K, int a_tri, int c_lower, int nsplit, int pairs, int bke, int* out, int cap) {
+  if (M <= 0 || N <= 0 || K <= 0 || nsplit < 1 || pairs < 1 || bke < 1 || cap < 0 || (cap > 0 && !out)) return DSVGP_ERR_ARG;
+  const std::vector<int> t = tc::build_sched(M, N, K, a_tri, c_lower, nsplit, pairs, bke, nullptr);
+  for (int i = 0; i < cap && i < (int)t.size(); ++i) out[i] = t[i];
+  return (int)t.size();
+}
 int dsvgp_set_tc_cta_group(int cg) { set_tc_cta_group(cg); return get_tc_cta_group(); }
 int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s) { return split_lo(x, ldx, lo, ldl, rows, cols, ST(s)); }
 int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s) { return transpose_f32(src, lds, dst, ldd, rows, cols, ST(s)); }

@@ -1,5 +1,7 @@
 // tcgen05 / TMA 3xTF32 GEMM (definitions in trmm_tc.cu).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace dsvgp {
@@ -38,8 +40,21 @@ int get_tc_cta_group();
 // 3xFP16 CTA-pair kernel: N extent of a tile, 256 (one pair per SM pair) or 128 (two pairs resident per SM pair)
 void set_tc_tile_n(int n);
 int get_tc_tile_n();
+// CTA-pair kernels: 1 (default) = persistent pairs walking a host-balanced work list (set-up once per SM, operand ring kept
+// full across tiles, the next tile's first chunks under the previous tile's store phase); 0 = one CTA pair per tile
+void set_tc_persistent(int on);
+// profiling aid of the persistent kernels: when buf != null, the MMA warp and the first epilogue warp of every pair leader write
+// SM clock stamps for each of their first cap_items work items: buf[8 * item + {0: MMA warp reaches the item, 1: first k-block
+// issued, 2: last k-block issued, 3: epilogue reaches the item, 4: first chunk complete, 5: last chunk added, 6: tile stored}]
+void set_tc_trace(long long* buf, int cap_items);
+int get_tc_persistent();
 
 int split_lo(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, cudaStream_t st);
 int transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, cudaStream_t st);
+
+namespace tc {
+// work lists of the persistent kernels (pure host function; see trmm_tc.cu)
+std::vector<int> build_sched(int M, int N, int K, int a_tri, int c_lower, int nz, int P, int bke, int* nz_eff);
+}
 
 }  // namespace dsvgp

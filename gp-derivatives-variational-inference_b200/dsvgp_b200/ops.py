@@ -141,6 +141,11 @@ def set_tc_tile_n(n):
     return call_raw("dsvgp_set_tc_tile_n", int(n))
 
 
+def set_tc_persistent(on):
+    """CTA-pair tensor-core products as persistent pairs over a balanced work list (default) or one pair per tile."""
+    return call_raw("dsvgp_set_tc_persistent", int(bool(on)))
+
+
 def gemm_tch(A, B, C, M, N, K, ab_inv, b_kmajor=False, alpha=1.0, beta=0.0, D=None, C2=None, D2=None, Ch=None, c_scale=None,
              C2h=None, c2_scale=None, a_tri=TRI_NONE, c_lower=False, chunk=1, nsplit=1, split_ws=None):
     """tcgen05 3xFP16 product.  A, B, Ch, C2h are (hi, lo) pairs of float16 matrices holding the split of x * scale;

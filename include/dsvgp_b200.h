@@ -180,6 +180,19 @@ int dsvgp_set_tc_cta_group(int cg);
  * memory), 128 = TWO pairs resident per SM pair (2 stages of 48 KB, 256 columns each, 4 epilogue warps): one pair's fixed
  * phases (set-up, pipeline fill, store of its tile) run under the other pair's main loop.  Returns the value in force. */
 int dsvgp_set_tc_tile_n(int n);
+/* CTA-pair tensor-core products: 1 (default) = persistent CTA pairs (one per SM pair) walking a host-balanced list of
+ * (256 x 256 tile, split-K slice) work items; 0 = one CTA pair per tile.  Returns the value in force. */
+int dsvgp_set_tc_persistent(int on);
+/* Profiling aid of the persistent products: with buf != NULL (device memory, 8 * cap_items int64) the MMA warp and the first
+ * epilogue warp of every pair leader stamp the SM clock for each work item with list index < cap_items: buf[8 i + 0..6] = MMA warp
+ * reaches item i, its first k-block issued, its last k-block issued, epilogue reaches the item, first chunk complete, last
+ * chunk added (store phase starts), tile stored.  buf = NULL switches it off. */
+int dsvgp_set_tc_trace(void* buf, int cap_items);
+/* The work list the persistent kernels would use for a product on `pairs` CTA pairs (host only, no GPU needed): writes
+ * at most `cap` ints [offsets (pairs + 1, padded to a multiple of 4) | items {pair-tile row, tile column, slice, kb0 | kb1 << 16}]
+ * to `out` and returns the number of ints of the full table (call with cap = 0 to size the buffer).  bke = elements per
+ * k-block (64 for the 3xFP16 product, 32 for 3xTF32). */
+int dsvgp_tc_work_list(int M, int N, int K, int a_tri, int c_lower, int nsplit, int pairs, int bke, int* out, int cap);
 int dsvgp_split_lo_f32(const float* x, int64_t ldx, float* lo, int64_t ldl, int rows, int cols, dsvgp_stream_t s);
 int dsvgp_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, dsvgp_stream_t s);
 
