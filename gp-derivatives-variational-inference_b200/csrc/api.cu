@@ -102,7 +102,15 @@ int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, co
 }
 int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s) {
   if (!A || !C || !m || !gmu || !gvar || !tp || !t || !dAh || !dAl || !Agh || !Agl || !s_dA || !s_Ag) return DSVGP_ERR_ARG;
-  return dA_apply_half(A, C, ld, rows, nq, m, gmu, gvar, tp, nslab, t, dAh, dAl, Agh, Agl, ldh, s_dA, s_Ag, ST(s));
+  return dA_apply_half(A, C, ld, rows, nq, m, gmu, gvar, tp, nslab, t, dAh, dAl, Agh, Agl, ldh, s_dA, s_Ag, nullptr, nullptr, nullptr, ST(s));
+}
+int dsvgp_dA_half_h_f32(const void* Ah, const void* Al, const float* a_scale, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s) {
+  if (!Ah || !Al || !a_scale || !C || !m || !gmu || !gvar || !tp || !t || !dAh || !dAl || !Agh || !Agl || !s_dA || !s_Ag) return DSVGP_ERR_ARG;
+  return dA_apply_half(nullptr, C, ld, rows, nq, m, gmu, gvar, tp, nslab, t, dAh, dAl, Agh, Agl, ldh, s_dA, s_Ag, Ah, Al, a_scale, ST(s));
+}
+int dsvgp_col_dots_h_f32(const void* Ah, const void* Al, int64_t ldh, const float* a_scale, const float* C, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, unsigned int* cmax_bits, dsvgp_stream_t s) {
+  if (!m || !pm || !pv) return DSVGP_ERR_ARG;
+  return col_dots_half(Ah, Al, ldh, a_scale, C, ld, rows, nq, m, pm, pv, nslab, cmax_bits, ST(s));
 }
 int dsvgp_gemm_tch_supported_f32(const void* A, int64_t lda, const void* B, int64_t ldb, int b_kmajor, int N) { return gemm_tch_supported(A, lda, B, ldb, b_kmajor, N); }
 int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* Bh, const void* Bl, int64_t ldb, int b_kmajor, int M, int N, int K, double alpha, double beta, const float* ab_inv, float* C, int64_t ldc, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, void* Ch, void* Cl, int64_t ldch, const float* c_scale, void* C2h, void* C2l, int64_t ldc2h, const float* c2_scale, int a_tri, int c_lower, int chunk, int nsplit, float* split_ws, dsvgp_stream_t s) {

@@ -169,6 +169,78 @@ col_dots_kernel(const T* __restrict__ A, const T* __restrict__ C, int64_t ld, in
   }
 }
 
+// 3xFP16 training step: A exists only as the two-half split (hi, lo) of A * *a_scale written by the whitening product (its fp32
+// copy is not written at all: half of that product's store phase).  Same partial sums as col_dots_kernel with
+// A_ij = (hi_ij + lo_ij) / a_scale; a thread owns two adjacent columns (half2 / float2 accesses).
+__global__ void __launch_bounds__(256)
+col_dots_h_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Al, int64_t ldh, const float* __restrict__ a_scale,
+                  const float* __restrict__ C, int64_t ld, int rows, int nq, const float* __restrict__ m, int rows_per_slab,
+                  float* __restrict__ pm, float* __restrict__ pv, unsigned* __restrict__ cmax_bits) {
+  // 64 columns per CTA like col_dots_kernel (same grid, same slabs): a warp covers them as 32 x 2, the 8 warps take rows i, i + 8, ...
+  __shared__ float sm[8][64], sv[8][64];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 64 + 2 * cl;
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
+  const float inv = 1.f / *a_scale;
+  float am0 = 0.f, am1 = 0.f, av0 = 0.f, av1 = 0.f, cm = 0.f;
+  if (j + 1 < nq) {
+    int i = r0 + rl;
+    for (; i + 24 < r1; i += 32) {
+      __half2 h[4], l[4];
+      float2 c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        h[q] = *reinterpret_cast<const __half2*>(Ah + (int64_t)(i + 8 * q) * ldh + j);
+        l[q] = *reinterpret_cast<const __half2*>(Al + (int64_t)(i + 8 * q) * ldh + j);
+        c[q] = *reinterpret_cast<const float2*>(C + (int64_t)(i + 8 * q) * ld + j);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 hf = __half22float2(h[q]), lf = __half22float2(l[q]);
+        const float a0 = (hf.x + lf.x) * inv, a1 = (hf.y + lf.y) * inv, mi = m[i + 8 * q];
+        am0 += a0 * mi; am1 += a1 * mi;
+        av0 += a0 * c[q].x; av1 += a1 * c[q].y;
+        cm = fmaxf(cm, fmaxf(fabsf(c[q].x), fabsf(c[q].y)));
+      }
+    }
+    for (; i < r1; i += 8) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(Ah + (int64_t)i * ldh + j));
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(Al + (int64_t)i * ldh + j));
+      const float2 c = *reinterpret_cast<const float2*>(C + (int64_t)i * ld + j);
+      const float a0 = (hf.x + lf.x) * inv, a1 = (hf.y + lf.y) * inv, mi = m[i];
+      am0 += a0 * mi; am1 += a1 * mi;
+      av0 += a0 * c.x; av1 += a1 * c.y;
+      cm = fmaxf(cm, fmaxf(fabsf(c.x), fabsf(c.y)));
+    }
+  } else if (j < nq) {                  // odd last column
+    for (int i = r0 + rl; i < r1; i += 8) {
+      const float a0 = (__half2float(Ah[(int64_t)i * ldh + j]) + __half2float(Al[(int64_t)i * ldh + j])) * inv;
+      const float c = C[(int64_t)i * ld + j];
+      am0 += a0 * m[i];
+      av0 += a0 * c;
+      cm = fmaxf(cm, fabsf(c));
+    }
+  }
+  if (cmax_bits != nullptr) {           // order-independent maximum on the bit pattern: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if ((threadIdx.x & 31) == 0 && cm > 0.f) atomicMax(cmax_bits, __float_as_uint(cm));
+  }
+  sm[rl][2 * cl] = am0; sm[rl][2 * cl + 1] = am1;
+  sv[rl][2 * cl] = av0; sv[rl][2 * cl + 1] = av1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c_ = threadIdx.x, jc = blockIdx.x * 64 + c_;
+    if (jc < nq) {
+      float a = 0.f, v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { a += sm[r][c_]; v += sv[r][c_]; }
+      pm[(int64_t)blockIdx.y * nq + jc] = a;
+      pv[(int64_t)blockIdx.y * nq + jc] = v;
+    }
+  }
+}
+
 // partial column sums  pv[s][j] = sum_i B'_ij (2 A_ij + B'_ij) = sum_i (B_ij^2 - A_ij^2) with B' = B - A
 // (prediction path: no backward, so C is never formed)
 template <typename T>
@@ -373,12 +445,15 @@ __global__ void __launch_bounds__(256)
 dA_half_kernel(const float* __restrict__ A, const float* __restrict__ C, int64_t ld, int rows, int nq,
                const float* __restrict__ m, const float* __restrict__ gmu, const float* __restrict__ gvar, int cols_per_slab,
                float* __restrict__ tp, __half* __restrict__ dAh, __half* __restrict__ dAl, __half* __restrict__ Agh,
-               __half* __restrict__ Agl, int64_t ldh, const float* __restrict__ s_dA, const float* __restrict__ s_Ag) {
+               __half* __restrict__ Agl, int64_t ldh, const float* __restrict__ s_dA, const float* __restrict__ s_Ag,
+               const __half* __restrict__ Ah, const __half* __restrict__ Al, const float* __restrict__ a_scale) {
+  // A comes as the fp32 matrix, or (A == nullptr) as the two-half split (Ah, Al; leading dimension ldh) of A * *a_scale
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 8 + warp;
   if (i >= rows) return;
   const int c0 = blockIdx.y * cols_per_slab, c1 = min(nq, c0 + cols_per_slab);
   const float mi = m[i], sd = *s_dA, sg = *s_Ag;
+  const float ainv = A ? 1.f : 1.f / *a_scale;
   float t = 0.f;
   auto put = [&](int64_t oh, float dA, float ag) {
     const float x = dA * sd, y = ag * sg;
@@ -391,6 +466,7 @@ dA_half_kernel(const float* __restrict__ A, const float* __restrict__ C, int64_t
   const bool al = ((ld & 3) == 0) && ((ldh & 3) == 0) && ((c0 & 3) == 0) &&
                   (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(gmu) |
                      reinterpret_cast<uintptr_t>(gvar)) & 15) == 0) &&
+                  (((reinterpret_cast<uintptr_t>(Ah) | reinterpret_cast<uintptr_t>(Al)) & 7) == 0) &&
                   (((reinterpret_cast<uintptr_t>(dAh) | reinterpret_cast<uintptr_t>(dAl) | reinterpret_cast<uintptr_t>(Agh) |
                      reinterpret_cast<uintptr_t>(Agl)) & 7) == 0);
   int jstart = c0;
@@ -398,7 +474,14 @@ dA_half_kernel(const float* __restrict__ A, const float* __restrict__ C, int64_t
     const int cvec = c0 + ((c1 - c0) & ~3);
     for (int j = c0 + 4 * lane; j < cvec; j += 128) {
       const int64_t o = (int64_t)i * ld + j, oh = (int64_t)i * ldh + j;
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(A + o));
+      float4 a;
+      if (A) a = __ldcs(reinterpret_cast<const float4*>(A + o));
+      else {
+        const uint2 hv = __ldcs(reinterpret_cast<const uint2*>(Ah + oh)), lv = __ldcs(reinterpret_cast<const uint2*>(Al + oh));
+        const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+        const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&lv.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&lv.y));
+        a = make_float4((h01.x + l01.x) * ainv, (h01.y + l01.y) * ainv, (h23.x + l23.x) * ainv, (h23.y + l23.y) * ainv);
+      }
       const float4 c = __ldcs(reinterpret_cast<const float4*>(C + o));
       const float4 gm = *reinterpret_cast<const float4*>(gmu + j);
       const float4 gv = *reinterpret_cast<const float4*>(gvar + j);
@@ -423,7 +506,8 @@ dA_half_kernel(const float* __restrict__ A, const float* __restrict__ C, int64_t
   }
   for (int j = jstart + lane; j < c1; j += 32) {
     const int64_t o = (int64_t)i * ld + j;
-    const float a = A[o], gm = gmu[j], gv = gvar[j];
+    const float a = A ? A[o] : (__half2float(Ah[(int64_t)i * ldh + j]) + __half2float(Al[(int64_t)i * ldh + j])) * ainv;
+    const float gm = gmu[j], gv = gvar[j];
     t += a * gm;
     put((int64_t)i * ldh + j, mi * gm + 2.f * gv * C[o], a * gv);
   }
@@ -592,6 +676,20 @@ int col_dots(const T* A, const T* C, const T* B, int64_t ld, int rows, int nq, c
   return DSVGP_OK;
 }
 
+int col_dots_half(const void* Ah, const void* Al, int64_t ldh, const float* a_scale, const float* C, int64_t ld, int rows, int nq,
+                  const float* m, float* pm, float* pv, int nslab, unsigned* cmax_bits, cudaStream_t st) {
+  if (rows <= 0 || nq <= 0) return DSVGP_OK;
+  if (nslab < 1 || !Ah || !Al || !a_scale || !C || (ld & 1) || (ldh & 1) || (reinterpret_cast<uintptr_t>(C) & 7) ||
+      ((reinterpret_cast<uintptr_t>(Ah) | reinterpret_cast<uintptr_t>(Al)) & 3))
+    return DSVGP_ERR_ARG;
+  const int rps = ceil_div(rows, nslab);
+  dim3 grid(ceil_div(nq, 64), nslab);
+  col_dots_h_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(Ah), static_cast<const __half*>(Al), ldh, a_scale, C, ld, rows,
+                                          nq, m, rps, pm, pv, cmax_bits);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+
 template <typename T>
 int predict_finish(const T* pm, const T* pv, int nslab, int nq, int p2, const double* hyp, double pred_jitter,
                    int add_noise, double min_var, T* mu, T* var, cudaStream_t st) {
@@ -657,14 +755,15 @@ int dA_apply(const T* A, T* C, T* Ag, int64_t ld, int rows, int nq, const T* m, 
 
 int dA_apply_half(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu,
                   const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh,
-                  const float* s_dA, const float* s_Ag, cudaStream_t st) {
+                  const float* s_dA, const float* s_Ag, const void* Ah, const void* Al, const float* a_scale, cudaStream_t st) {
   if (rows <= 0 || nq <= 0) return DSVGP_OK;
+  if (!A && (!Ah || !Al || !a_scale)) return DSVGP_ERR_ARG;
   const int cps = ceil_div(ceil_div(nq, nslab), 32) * 32;
   const int ns = ceil_div(nq, cps);
   dim3 grid(ceil_div(rows, 8), ns);
   dA_half_kernel<<<grid, 256, 0, st>>>(A, C, ld, rows, nq, m, gmu, gvar, cps, tp, static_cast<__half*>(dAh),
                                        static_cast<__half*>(dAl), static_cast<__half*>(Agh), static_cast<__half*>(Agl), ldh,
-                                       s_dA, s_Ag);
+                                       s_dA, s_Ag, static_cast<const __half*>(Ah), static_cast<const __half*>(Al), a_scale);
   CHECK_LAUNCH();
   sum_parts_kernel<float><<<ceil_div(rows, 256), 256, 0, st>>>(tp, ns, rows, t);
   CHECK_LAUNCH();

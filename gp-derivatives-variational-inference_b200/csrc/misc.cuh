@@ -27,7 +27,11 @@ int elbo_terms(const T* mu, const T* var, const T* y, int nq, const double* hyp,
                T* gvar, double* sc, double* ws, cudaStream_t st);
 int dA_apply_half(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu,
                   const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh,
-                  const float* s_dA, const float* s_Ag, cudaStream_t st);
+                  const float* s_dA, const float* s_Ag, const void* Ah, const void* Al, const float* a_scale, cudaStream_t st);
+// A == nullptr: A is read as the two-half split (Ah, Al; leading dimension ldh) of A * *a_scale
+// col_dots with A given only as that split (3xFP16 training step: the whitening product writes no fp32 A)
+int col_dots_half(const void* Ah, const void* Al, int64_t ldh, const float* a_scale, const float* C, int64_t ld, int rows, int nq,
+                  const float* m, float* pm, float* pv, int nslab, unsigned* cmax_bits, cudaStream_t st);
 template <typename T>
 int pll_terms(const T* mu, const T* var, const T* y, int nq, double w, double min_var, T* gmu, T* gvar, double* sc,
               double* ws, cudaStream_t st);

@@ -41,6 +41,11 @@ WHITEN_FP64 = "auto"  # fp32 model: run the two products that multiply by W = L^
 WHITEN_FP64_MAX_NQ = 2048
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
+HALF_A = False     # 3xFP16 training step (DENSE_D): True = A = W K_zx leaves the whitening product ONLY as its two-half split (the operand
+                   # of C = (S - I) A and of the Gram product) and the column reductions / the dA pass read that split (A_ij = (hi + lo) / s_A,
+                   # 22 significand bits).  The product's store phase is bound by the SM's 32 B/clk write port and exposed, so 8 instead of
+                   # 16 bytes per element shortens the product (0.98 -> 0.91 ms alone), but the half-reading column pass costs 0.03 ms more
+                   # and the whole step does not move (11.34 / 11.42 ms, A/B in one process: the step is power-capped there) -- off.
 F16 = torch.float16
 _PARAM_NAMES = ("Z", "Vz", "m", "Ls_raw", "c", "raw_os", "raw_ell", "raw_noise")
 
@@ -396,12 +401,17 @@ class Engine:
                 ops.gemm(f.W, ws.B64, ws.A64, a_tri=TRI_LOWER, M=Mq, N=nq, K=Mq)
                 ops.cast2d(ws.A64, A, Mq, nq)
                 ops.split_half(ws.A64, sc[3:4], ws.Ah, ws.Al, rows=Mq, cols=nq)
+                ws.a_half = False
             else:
-                ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
+                ws.a_half = bool(HALF_A and need_C and DENSE_D)
+                ops.gemm_tch((f.Wh, f.Wl), (ws.Kh, ws.Kl), None if ws.a_half else A, Mq, nq, Mq, sc[8:9], a_tri=TRI_LOWER, chunk=H,
                              Ch=(ws.Ah, ws.Al), c_scale=sc[3:4])                              # A = L^-1 K_zx (+ its split)
             if need_C and DENSE_D:
                 ops.gemm_tch((ws.Dh, ws.Dl), (ws.Ah, ws.Al), C, Mq, nq, Mq, sc[13:14], chunk=H)   # C = (S - I) A, dense
-                ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C, cmax=f.maxbits[5:6])
+                if ws.a_half:
+                    ops.col_dots_half((ws.Ah, ws.Al), sc[3:4], P.m, ws.pm, ws.pv, Mq, nq, C, cmax=f.maxbits[5:6])
+                else:
+                    ops.col_dots(A, P.m, ws.pm, ws.pv, Mq, nq, C=C, cmax=f.maxbits[5:6])
             elif need_C:
                 ops.gemm_tch((ws.ETh, ws.ETl), (ws.Ah, ws.Al), ws.Bp, Mq, nq, Mq, sc[9:10], a_tri=TRI_UPPER, chunk=H,
                              D2=A, C2h=(ws.Kh, ws.Kl), c2_scale=sc[4:5])                      # B' = E^T A ; split of B = A + B'
@@ -457,7 +467,11 @@ class Engine:
             ops.absmax(gvar, f.maxbits[3:4])
             ops.tc_scales(f.hyp, f.jitter, f.maxbits, Mq, sc, 1)
             # dA = m g_mu^T + 2 C diag(g_var) and A_g = A diag(g_var) leave only as two-half splits; t = A g_mu
-            ops.dA_apply_half(A, C, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t, ws.Kh, ws.Kl, ws.Agh, ws.Agl, sc[5:6], sc[6:7])
+            if getattr(ws, "a_half", False):
+                ops.dA_apply_half(None, C, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t, ws.Kh, ws.Kl, ws.Agh, ws.Agl, sc[5:6], sc[6:7],
+                                  A_half=(ws.Ah, ws.Al), a_scale=sc[3:4])
+            else:
+                ops.dA_apply_half(A, C, Mq, nq, P.m, gmu, gvar, ws.tp, ws.t, ws.Kh, ws.Kl, ws.Agh, ws.Agl, sc[5:6], sc[6:7])
             ops.gemm_tch((ws.Agh, ws.Agl), (ws.Ah, ws.Al), ws.G, Mq, Mq, nq, sc[12:13], b_kmajor=True, c_lower=True,
                          chunk=TCH_CHUNK, nsplit=ws.syrk_split, split_ws=ws.split_ws)                                     # G = A_g A^T
             ops.mirror_lower(ws.G, Mq)

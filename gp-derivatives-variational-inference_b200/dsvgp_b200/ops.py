@@ -193,7 +193,12 @@ def kdir_fwd_half(x1, u1, p1, x2, w2, p2, hyp, K, Kh, Kl, hscale, canon=None, us
     return rc == 2
 
 
-def dA_apply_half(A, C, rows, nq, m, gmu, gvar, tp, t, dAh, dAl, Agh, Agl, s_dA, s_Ag):
+def dA_apply_half(A, C, rows, nq, m, gmu, gvar, tp, t, dAh, dAl, Agh, Agl, s_dA, s_Ag, A_half=None, a_scale=None):
+    """dA and A_g as two-half splits; A as the fp32 matrix, or (A_half = (Ah, Al), a_scale) as the split of A * a_scale."""
+    if A_half is not None:
+        call("dsvgp_dA_half_h_f32", A_half[0], A_half[1], a_scale, C, _ld(C), rows, nq, m, gmu, gvar, tp, tp.shape[0], t, dAh, dAl,
+             Agh, Agl, _ld(dAh), s_dA, s_Ag)
+        return
     call("dsvgp_dA_half_f32", A, C, _ld(A), rows, nq, m, gmu, gvar, tp, tp.shape[0], t, dAh, dAl, Agh, Agl, _ld(dAh), s_dA, s_Ag)
 
 
@@ -276,6 +281,11 @@ def col_dots(A, m, pm, pv, rows, nq, C=None, Bp=None, cmax=None):
     B = Bp
     nslab = pm.shape[0]
     call("dsvgp_col_dots_" + suffix(A.dtype), A, C, B, _ld(A), rows, nq, m, pm, pv, nslab, cmax if C is not None else None)
+
+
+def col_dots_half(A_half, a_scale, m, pm, pv, rows, nq, C, cmax=None):
+    """col_dots with A given only as the two-half split (Ah, Al) of A * a_scale (1-element device tensor)."""
+    call("dsvgp_col_dots_h_f32", A_half[0], A_half[1], _ld(A_half[0]), a_scale, C, _ld(C), rows, nq, m, pm, pv, pm.shape[0], cmax)
 
 
 def predict_finish(pm, pv, nq, p2, hyp, mu, var, add_noise, pred_jitter=1e-4):

@@ -159,7 +159,10 @@ int dsvgp_gemm_tch_f32(const void* Ah, const void* Al, int64_t lda, const void* 
  *   mode 0: src, 1: tril(src), 2: tril(src) - I.
  * dsvgp_kdir_fwd_half_f32: dsvgp_kdir_fwd_canon_f32 that writes ONLY the split (Kh, Kl) of K * *hscale; returns 2 when
  *   it did, otherwise K (fp32) was written instead (shape not taken by the vectorised kernel) and 0 is returned.
- * dsvgp_dA_half_f32: dsvgp_dA_f32 whose outputs are only the splits of dA * *s_dA and A_g * *s_Ag (C is not modified). */
+ * dsvgp_dA_half_f32: dsvgp_dA_f32 whose outputs are only the splits of dA * *s_dA and A_g * *s_Ag (C is not modified).
+ * dsvgp_dA_half_h_f32 / dsvgp_col_dots_h_f32: the same pass / dsvgp_col_dots_f32 with A given ONLY as the split (Ah, Al) of
+ *   A * *a_scale (leading dimension ldh, the one of the outputs for dA_half_h): the training step's whitening product then
+ *   writes no fp32 A at all -- half of its store phase, which is bound by the 32 B/clk write port of an SM. */
 int dsvgp_absmax_f32(const float* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s);
 int dsvgp_absmax_f64(const double* x, int64_t ld, int rows, int cols, int mode, unsigned int* out_bits, dsvgp_stream_t s);
 int dsvgp_tc_scales_f32(const double* hyp, double jitter, const unsigned int* maxbits, int Mq, float* scales, int stage, dsvgp_stream_t s);
@@ -173,6 +176,8 @@ int dsvgp_build_d_split_f32(const float* E, int64_t lde, const float* P, int64_t
 int dsvgp_build_d_absmax_f32(const float* E, int64_t lde, const float* P, int64_t ldp, int n, unsigned int* out_bits, dsvgp_stream_t s);
 int dsvgp_kdir_fwd_half_f32(const float* x1, const float* u1, int n1, int p1, const float* x2, const float* w2, const int* cidx2, const int* canon_flag, int n2, int p2, int d, const double* hyp, int use_os, double diag_add, float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, const float* hscale, dsvgp_stream_t s);
 int dsvgp_dA_half_f32(const float* A, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s);
+int dsvgp_dA_half_h_f32(const void* Ah, const void* Al, const float* a_scale, const float* C, int64_t ld, int rows, int nq, const float* m, const float* gmu, const float* gvar, float* tp, int nslab, float* t, void* dAh, void* dAl, void* Agh, void* Agl, int64_t ldh, const float* s_dA, const float* s_Ag, dsvgp_stream_t s);
+int dsvgp_col_dots_h_f32(const void* Ah, const void* Al, int64_t ldh, const float* a_scale, const float* C, int64_t ld, int rows, int nq, const float* m, float* pm, float* pv, int nslab, unsigned int* cmax_bits, dsvgp_stream_t s);
 /* tile scheme of dsvgp_gemm_tc_f32: 1 = one CTA per 128x256 tile (cta_group::1), 2 = CTA pairs on 256x256 tiles
  * (cta_group::2: each CTA stages half of the operands, 2-SM TMA loads, multicast commits).  Returns the value in force. */
 int dsvgp_set_tc_cta_group(int cg);
