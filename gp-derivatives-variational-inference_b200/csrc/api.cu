@@ -14,12 +14,16 @@ using namespace dsvgp;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 namespace dsvgp { unsigned long long g_launch_count = 0; }
-namespace dsvgp { extern int g_fwd_tib, g_fwd_stream_stores; }
+namespace dsvgp { extern int g_fwd_tib, g_fwd_stream_stores, g_bwd_vpl; }
 
 extern "C" {
 
 int dsvgp_version(void) { return 100; }
 int64_t dsvgp_launch_count(void) { return (int64_t)dsvgp::g_launch_count; }
+int dsvgp_set_kdir_bwd_vpl(int vpl) {
+  if (vpl == 2 || vpl == 4) dsvgp::g_bwd_vpl = vpl;
+  return dsvgp::g_bwd_vpl;
+}
 int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores) {
   const int old = dsvgp::g_fwd_tib * 4 + dsvgp::g_fwd_stream_stores;
   if (tib >= 8 && tib <= 64 && tib % 8 == 0) dsvgp::g_fwd_tib = tib;
@@ -81,6 +85,8 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 int dsvgp_set_potrf_debug(void* p) { set_potrf_debug(static_cast<long long*>(p)); return 0; }
 int dsvgp_set_gemm64_async(int on) { set_gemm64_async(on); return get_gemm64_async(); }
 int dsvgp_set_chol_variant(int v) { set_chol_variant(v); return get_chol_variant(); }
+int dsvgp_set_chol_lookahead(int on) { set_chol_lookahead(on); return get_chol_lookahead(); }
+int dsvgp_set_chol_priority(int on) { set_chol_priority(on); return get_chol_priority(); }
 
 int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s) {
   return gemm<float>(ta != 0, tb != 0, M, N, K, (float)alpha, A, lda, B, ldb, (float)beta, C, ldc, a_tri, b_tri, c_tri, batch, sA, sB, sC, ST(s), D, ldd, C2, ldc2, D2, ldd2);

@@ -870,6 +870,14 @@ void set_potrf_debug(long long* p) { cudaMemcpyToSymbol(g_potrf_dbg, &p, sizeof(
 static int g_chol_variant = 3;
 void set_chol_variant(int v) { g_chol_variant = (v >= 1 && v <= 3) ? v : 3; }
 int get_chol_variant() { return g_chol_variant; }
+static int g_chol_lookahead = 0;  // 1: trailing update split into the part the next two links need (side stream) and the bulk (own stream);
+                                  // measured: no gain (C3 step 11.43 -> 11.46 ms, A/B in one process) -- off
+void set_chol_lookahead(int on) { g_chol_lookahead = on ? 1 : 0; }
+int get_chol_lookahead() { return g_chol_lookahead; }
+static int g_chol_priority = 0;   // 1: the three chains of the factorisation on the library's high-priority streams; 0: diagonal chain on the caller's
+                                  // stream (measured: no difference on any workload -- off)
+void set_chol_priority(int on) { g_chol_priority = on ? 1 : 0; }
+int get_chol_priority() { return g_chol_priority; }
 
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st) {
@@ -913,24 +921,41 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // update of everything below block row k+1 (a lower trapezoid: block column k+1 included, the diagonal block (k+1,k+1)
   // excluded -- potrf(k+1) owns it).  The 32 latency-bound single-CTA kernels overlap the throughput-bound GEMMs.
   // Fork/join with events keeps the whole factorisation capturable in a CUDA graph.
-  struct SideCtx { cudaStream_t side = nullptr, inv = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_inv; bool ready = false; };
+  // All three chains run on the library's own HIGH-PRIORITY streams (the diagonal chain forks from the caller's stream and joins
+  // it at the end): the engine fills the SMs this latency-bound phase leaves idle with the K_zx assembly and the L_s operand
+  // products on another stream, and at equal priority those filler CTAs delayed the first links of the chain by 0.1 - 0.2 ms
+  // each (torch.profiler trace of the C3 step: 0.49 ms of gaps between the first six diagonal blocks).
+  struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_inv, ev_entry, ev_done; bool ready = false; };
   static SideCtx ctxs[16];                              // one side stream + event pool per device
   int dev = 0;
   cudaGetDevice(&dev);
   SideCtx& sc = ctxs[dev & 15];
   if (!sc.ready) {
-    if (cudaStreamCreateWithFlags(&sc.side, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
-    if (cudaStreamCreateWithFlags(&sc.inv, cudaStreamNonBlocking) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&sc.diag, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    if (cudaStreamCreateWithPriority(&sc.side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    if (cudaStreamCreateWithPriority(&sc.inv, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    if (cudaStreamCreateWithPriority(&sc.bulk, cudaStreamNonBlocking, prio_least) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     for (int i = 0; i < 64; ++i) {
       cudaEventCreateWithFlags(&sc.ev_main[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&sc.ev_side[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&sc.ev_panel[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&sc.ev_bulk[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&sc.ev_inv, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sc.ev_entry, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sc.ev_done, cudaEventDisableTiming);
     sc.ready = true;
   }
   cudaStream_t side = sc.side, inv = sc.inv;
   const bool two_chains = nblk <= 64;
+  cudaStream_t caller = st;
+  if (two_chains && g_chol_priority) {                  // the diagonal chain moves to the high-priority stream
+    cudaEventRecord(sc.ev_entry, caller);
+    cudaStreamWaitEvent(sc.diag, sc.ev_entry, 0);
+    st = sc.diag;
+  }
   // Eager inverse (round 2): the recursive-doubling inverse W = [[W11, 0], [-W22 (L21 W11), W22]] does not wait for the end
   // of the factorisation.  For every pair of every level, T = L21 W11 is issued (third stream) as soon as the pair's top half
   // is factorised and inverted, and W21 = -W22 T as soon as its bottom half is: after the last diagonal block only ONE product
@@ -938,7 +963,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // T lives in the dead upper-right quadrant of the pair inside W (the work matrix' lower-left quadrant is still read by the
   // next diag_prepare).
   const bool eager_inv = two_chains && nlev >= 1 && g_chol_variant >= 2;
-  int last_side = -1;
+  int last_side = -1, last_bulk = -1;
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
     // (more than 64 blocks: more steps than pooled events -- everything goes on the caller's stream, in order)
@@ -972,15 +997,43 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
       if (rc) return rc;
       if (eager_inv) cudaEventRecord(sc.ev_panel[k], side);
       const int m2 = m - nb0;
-      if (m2 > 0) {
+      // (worth it only while the bulk is long: one product per step keeps up with the chain once panel + update fit into one link)
+      const bool split = two_chains && g_chol_lookahead && m2 >= 16 * nb0;
+      if (m2 > 0 && split) {
+        // Trailing update with a lookahead of two.  Of the lower trapezoid below block row k+1, the next two links of the chain
+        // need only its first two block COLUMNS (k+1: the input of panel(k+1); tiles (k+2, k+1) and (k+2, k+2): read by
+        // potrf(k+2)).  That thin product (m2 x 192 x 96) stays on the side stream; the rest -- the lower triangle from block
+        // (k+3, k+3) on, 0.8 GFLOP / 60 us at the first links of M' = 3072 -- goes to a low-priority stream of its own and has two
+        // links' time to finish: the next thin product (which accumulates onto tiles it writes) waits for it, nobody else.  With
+        // one product per step, potrf(k+2) waited for all of it and the first ten links ran at 75 - 100 us instead of 50.
+        const double* L21b = L21 + (int64_t)nb0 * ldl;
+        double* A22b = Awork + (o + 2 * nb0) * lda + (o + nb0);
+        if (last_bulk >= 0) cudaStreamWaitEvent(side, sc.ev_bulk[last_bulk], 0);
+        rc = gemm<double>(false, true, m2, 2 * nb0, nb0, -1.0, L21b, ldl, L21, ldl, 1.0, A22b, lda, TRI_NONE, TRI_NONE, 0, 1, 0, 0, 0,
+                          side);
+        if (rc) return rc;
+        cudaEventRecord(sc.ev_side[k], side);             // what potrf(k+2) waits for
+        last_side = k;
+        cudaStreamWaitEvent(sc.bulk, sc.ev_side[k], 0);   // (after the thin product: they share the SMs)
+        const double* L21c = L21b + (int64_t)nb0 * ldl;   // rows from block k+3
+        rc = gemm<double>(false, true, m2 - nb0, m2 - nb0, nb0, -1.0, L21c, ldl, L21c, ldl, 1.0,
+                          A22b + (int64_t)nb0 * lda + 2 * nb0, lda, TRI_NONE, TRI_NONE, 1, 1, 0, 0, 0, sc.bulk);
+        if (rc) return rc;
+        cudaEventRecord(sc.ev_bulk[k], sc.bulk);
+        last_bulk = k;
+      } else if (m2 > 0) {
         // trailing update below block row k+1:  A22[nb0:, :] -= L21[nb0:, :] * L21^T  on the tiles with col <= row + nb0
         const double* L21b = L21 + (int64_t)nb0 * ldl;
         double* A22b = Awork + (o + 2 * nb0) * lda + (o + nb0);
+        if (last_bulk >= 0) {
+          cudaStreamWaitEvent(gs, sc.ev_bulk[last_bulk], 0);
+          last_bulk = -1;
+        }
         rc = gemm<double>(false, true, m2, m, nb0, -1.0, L21b, ldl, L21, ldl, 1.0, A22b, lda, TRI_NONE, TRI_NONE, 1, 1, 0, 0, 0,
                           gs, nullptr, 0, nullptr, 0, nullptr, 0, nb0);
         if (rc) return rc;
       }
-      if (two_chains) {
+      if (two_chains && !(m2 > 0 && split)) {
         cudaEventRecord(sc.ev_side[k], side);
         last_side = k;
       }
@@ -1009,7 +1062,13 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
       }
     }
   }
+  if (st != caller) {                                   // join: the caller's stream continues after all three chains
+    cudaEventRecord(sc.ev_done, st);
+    cudaStreamWaitEvent(caller, sc.ev_done, 0);
+    st = caller;
+  }
   if (two_chains && last_side >= 0) cudaStreamWaitEvent(st, sc.ev_side[last_side], 0);
+  if (last_bulk >= 0) cudaStreamWaitEvent(st, sc.ev_bulk[last_bulk], 0);
   if (eager_inv) {
     cudaEventRecord(sc.ev_inv, inv);
     cudaStreamWaitEvent(st, sc.ev_inv, 0);

@@ -16,6 +16,13 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
 // 1: round-1 diagonal-block kernel (in-kernel DMMA prologue, scalar updates); 2 (default): diag_prepare + all-DMMA block kernel
 void set_chol_variant(int v);
 int get_chol_variant();
+// 1: diagonal-block chain, panel / trailing-update chain and eager-inverse chain all on high-priority streams of the
+// library (forked from and joined to the caller's stream); 0: the diagonal chain stays on the caller's stream
+// 1: trailing update of a step split into the thin part the next two links need and the bulk on a stream of its own
+void set_chol_lookahead(int on);
+int get_chol_lookahead();
+void set_chol_priority(int on);
+int get_chol_priority();
 void set_potrf_debug(long long* p);   // profiling aid: device buffer of 64 clock64() stamps (nullptr = off)
 
 }  // namespace dsvgp

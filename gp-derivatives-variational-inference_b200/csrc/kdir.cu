@@ -200,6 +200,8 @@ __device__ __forceinline__ float tf32_lo_part(float x) {
 // products, and the per-pair work drops from (1+p1)(1+p2) to (1+p1) FMAs per coordinate.
 constexpr int V4_TJ = 128, V4_TIB = 64;
 
+int g_bwd_vpl = 4;             // column points per lane of kdir_bwd_v4: 4, or 2 = two CTAs per SM (benchmarking knob; measured equal:
+                               // 0.50 / 0.54 ms at C3 -- the kernel is bound by shared-memory reads + FMA issue, not by latency)
 int g_fwd_tib = V4_TIB;        // row points per CTA of kdir_fwd_v4 (benchmarking knob, multiple of 8, <= V4_TIB)
 int g_fwd_stream_stores = 2;   // 1: st.global.cs (evict-first) for the K / K_lo rows; 2 (default): when the output is
                                // larger than half of the 126 MB L2 (measured on C3: K only 0.144 -> 0.136 ms, K + lo 0.209 -> 0.195 ms)
@@ -727,17 +729,30 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[NV], int lane) {
   }
 }
 
-template <int P1, int P2, int DP>
+// VPL = column points per lane: 4 (a warp spans 128 column points; ~250 registers, one CTA per SM) or 2 (64 column points per
+// warp and per CTA tile; half the per-lane arrays, two CTAs = 16 warps per SM -- the kernel is issue-bound on dependent FMA
+// chains, ncu: 49 % issue-active with 2 warps per scheduler, so the extra warps are what it needs).
+template <int P1, int P2, int DP, int VPL>
 size_t bwd_v4_smem_bytes() {
-  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * DP + (P2 + 1) * DP * V4_TJ) + 64 * sizeof(double);
+  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * DP + (P2 + 1) * DP * 32 * VPL) + 64 * sizeof(double);
 }
 
-template <int P1, int P2, int DP>
-__global__ void __launch_bounds__(256, 1)
+template <int VPL> __device__ __forceinline__ void ld_vpl(const float* p, float (&o)[VPL]) {
+  if constexpr (VPL == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    o[0] = t.x; o[1] = t.y;
+  }
+}
+
+template <int P1, int P2, int DP, int VPL>
+__global__ void __launch_bounds__(256, VPL == 4 ? 1 : 2)
 kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, const float* __restrict__ x2,
             const float* __restrict__ w2, int n2, int d, const double* __restrict__ hyp, int use_os,
             const float* __restrict__ dK, int64_t lddk, float* __restrict__ part, double* __restrict__ part_sc) {
-  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = V4_TJ, TIB = V4_TIB, NV = Q1 * DP, NG = (NV + 31) / 32;
+  constexpr int Q1 = P1 + 1, Q2 = P2 + 1, TJ = 32 * VPL, TIB = V4_TIB, NV = Q1 * DP, NG = (NV + 31) / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* red = reinterpret_cast<double*>(smem_raw);       // [64]
   float* rs = reinterpret_cast<float*>(red + 64);          // [TIB][Q1][DP]
@@ -753,8 +768,8 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     rs[e] = v;
   }
   {
-    const int j = tid & 127;
-    for (int row = tid >> 7; row < Q2 * DP; row += 2) {
+    const int j = tid & (TJ - 1);
+    for (int row = tid / TJ; row < Q2 * DP; row += 256 / TJ) {
       const int b = row / DP, cc = row % DP;
       float v = 0.f;
       if (j0 + j < n2 && cc < d)
@@ -775,9 +790,9 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     if (gi >= n1) break;                                   // warp-uniform
     const float* rbase = rs + (il * Q1) * DP;
     // ---- recompute the 4 kernel blocks of this lane
-    float r2[4], al[P1 > 0 ? P1 : 1][4], be[P2 > 0 ? P2 : 1][4], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][4];
+    float r2[VPL], al[P1 > 0 ? P1 : 1][VPL], be[P2 > 0 ? P2 : 1][VPL], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][VPL];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < VPL; ++q) {
       r2[q] = 0.f;
 #pragma unroll
       for (int a = 0; a < P1; ++a) al[a][q] = 0.f;
@@ -790,20 +805,16 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     }
 #pragma unroll
     for (int c = 0; c < DP; ++c) {
-      const float4 xj4 = *reinterpret_cast<const float4*>(cs + c * TJ + 4 * lane);
-      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
-      float wj[P2 > 0 ? P2 : 1][4];
+      float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
+      ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
 #pragma unroll
-      for (int b = 0; b < P2; ++b) {
-        const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * DP + c) * TJ + 4 * lane);
-        wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
-      }
+      for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
       const float xi = rbase[c];
       float ui[P1 > 0 ? P1 : 1];
 #pragma unroll
       for (int a = 0; a < P1; ++a) ui[a] = rbase[(1 + a) * DP + c];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < VPL; ++q) {
         const float dl = xi - xj[q];
         r2[q] = fmaf(dl, dl, r2[q]);
 #pragma unroll
@@ -817,26 +828,34 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
       }
     }
     // ---- upstream blocks: row (gi, a) holds this lane's 4*Q2 consecutive floats
-    float g[Q1][4 * Q2];
+    // (VPL * Q2 consecutive floats per lane: float4 pieces when VPL = 4, float2 pieces when VPL = 2 -- 8-byte aligned for any Q2)
+    constexpr int VW = VPL == 4 ? 4 : 2, NPIECE = VPL * Q2 / VW;
+    static_assert((VPL * Q2) % VW == 0, "upstream segment must split into whole vector pieces");
+    float g[Q1][VPL * Q2];
 #pragma unroll
     for (int a = 0; a < Q1; ++a) {
-      const float* grow = dK + (int64_t)(gi * Q1 + a) * lddk + (int64_t)j0 * Q2 + lane * 4 * Q2;
+      const float* grow = dK + (int64_t)(gi * Q1 + a) * lddk + (int64_t)j0 * Q2 + lane * VPL * Q2;
 #pragma unroll
-      for (int v = 0; v < Q2; ++v) {
-        const int col = lane * 4 * Q2 + 4 * v;
-        if (vec_ok && col + 3 < cols) {
-          const float4 t = *reinterpret_cast<const float4*>(grow + 4 * v);
-          g[a][4 * v] = t.x; g[a][4 * v + 1] = t.y; g[a][4 * v + 2] = t.z; g[a][4 * v + 3] = t.w;
+      for (int v = 0; v < NPIECE; ++v) {
+        const int col = lane * VPL * Q2 + VW * v;
+        if (vec_ok && col + VW - 1 < cols) {
+          if constexpr (VW == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(grow + 4 * v);
+            g[a][4 * v] = t.x; g[a][4 * v + 1] = t.y; g[a][4 * v + 2] = t.z; g[a][4 * v + 3] = t.w;
+          } else {
+            const float2 t = *reinterpret_cast<const float2*>(grow + 2 * v);
+            g[a][2 * v] = t.x; g[a][2 * v + 1] = t.y;
+          }
         } else {
 #pragma unroll
-          for (int z = 0; z < 4; ++z) g[a][4 * v + z] = (col + z < cols) ? grow[4 * v + z] : 0.f;
+          for (int z = 0; z < VW; ++z) g[a][VW * v + z] = (col + z < cols) ? grow[VW * v + z] : 0.f;
         }
       }
     }
     // ---- coefficients per pair
-    float e0[4], ea[P1 > 0 ? P1 : 1][4], eb[P2 > 0 ? P2 : 1][4], hab[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][4];
+    float e0[VPL], ea[P1 > 0 ? P1 : 1][VPL], eb[P2 > 0 ? P2 : 1][VPL], hab[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][VPL];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < VPL; ++q) {
       const float k = os * expf(-0.5f * r2[q] * il2);
       float as[P1 > 0 ? P1 : 1], bs[P2 > 0 ? P2 : 1];
 #pragma unroll
@@ -881,19 +900,15 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
       s_os += (double)(qk * k / os);
     }
     // ---- accumulate d/dx1_i and d/du_ia over this lane's 4 pairs
-    float acc[NG * 32];
+    float acc[NV];
 #pragma unroll
-    for (int f = 0; f < NG * 32; ++f) acc[f] = 0.f;
+    for (int f = 0; f < NV; ++f) acc[f] = 0.f;
 #pragma unroll
     for (int c = 0; c < DP; ++c) {
-      const float4 xj4 = *reinterpret_cast<const float4*>(cs + c * TJ + 4 * lane);
-      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
-      float wj[P2 > 0 ? P2 : 1][4];
+      float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
+      ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
 #pragma unroll
-      for (int b = 0; b < P2; ++b) {
-        const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * DP + c) * TJ + 4 * lane);
-        wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
-      }
+      for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
       const float xi = rbase[c];
       float ui[P1 > 0 ? P1 : 1];
 #pragma unroll
@@ -902,7 +917,7 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
       for (int a = 0; a < P1; ++a) gu[a] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < VPL; ++q) {
         const float dl = xi - xj[q];
         gx = fmaf(e0[q], dl, gx);
 #pragma unroll
@@ -921,16 +936,30 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     }
     // ---- sum over the 32 lanes, one partial row per (column tile, row point)
     float* prow = part + ((int64_t)blockIdx.x * n1 * Q1 + (int64_t)gi * Q1) * d;
+    constexpr int NFULL = NV / 32, REM = NV % 32;       // whole groups of 32 values: transposing butterfly; a short remainder: plain sums
 #pragma unroll
-    for (int grp = 0; grp < NG; ++grp) {
+    for (int grp = 0; grp < NFULL + (REM > 8 ? 1 : 0); ++grp) {
       float v[32];
 #pragma unroll
-      for (int f = 0; f < 32; ++f) v[f] = acc[grp * 32 + f];
+      for (int f = 0; f < 32; ++f) v[f] = (grp * 32 + f < NV) ? acc[(grp * 32 + f < NV) ? grp * 32 + f : 0] : 0.f;
       warp_transpose_sum<32>(v, lane);
       const int f = grp * 32 + lane;                        // flattened (a', c) with pitch DP
       if (f < NV) {
         const int a = f / DP, c = f % DP;
         if (c < d) prow[a * d + c] = v[0];
+      }
+    }
+    if constexpr (REM > 0 && REM <= 8) {
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < REM; ++r) {
+        const float sr = warp_sum(acc[NFULL * 32 + r]);
+        if (lane == r) mine = sr;
+      }
+      const int f = NFULL * 32 + lane;
+      if (lane < REM) {
+        const int a = f / DP, c = f % DP;
+        if (c < d) prow[a * d + c] = mine;
       }
     }
   }
@@ -1190,13 +1219,13 @@ int kdir_diag(int n, int p, const double* hyp, int use_os, TK* out, cudaStream_t
 
 // workspace (bytes) the backward needs for an (n1,p1) x (n2,p2) call
 bool bwd_v4_ok(int n1, int p1, int n2, int p2, int d) {
-  return d <= 16 && n2 >= 512 && ((p1 == 1 && p2 == 1) || (p1 == 2 && p2 == 2) || (p1 == 1 && p2 == 0) || (p1 == 2 && p2 == 0));
+  return d <= 20 && n2 >= 512 && ((p1 == 1 && p2 == 1) || (p1 == 2 && p2 == 2) || (p1 == 1 && p2 == 0) || (p1 == 2 && p2 == 0));
 }
 
 template <typename TK>
 size_t kdir_bwd_workspace(int n1, int p1, int n2, int p2, int d) {
   if (sizeof(TK) == 4 && bwd_v4_ok(n1, p1, n2, p2, d)) {
-    const size_t nt = ceil_div(n2, 128), nrc = ceil_div(n1, 64);
+    const size_t nt = ceil_div(n2, 64), nrc = ceil_div(n1, 64);      // (64-point column tiles: the VPL = 2 variant; 128 needs half)
     const size_t v4 = sizeof(float) * nt * n1 * (p1 + 1) * d + sizeof(double) * 2 * nt * nrc + 512;
     const int rt0 = ceil_div(n1, BWD_TI), nch0 = bwd_num_chunks(n1, n2);
     const size_t old = sizeof(float) * (size_t)nch0 * n1 * (p1 + 1) * d + sizeof(double) * 2 * (size_t)rt0 * nch0 + 256;
@@ -1257,25 +1286,29 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
   if (ws_bytes < kdir_bwd_workspace<TK>(n1, p1, n2, p2, d)) return DSVGP_ERR_WORKSPACE;
   if constexpr (sizeof(T) == 4 && sizeof(TK) == 4) {
     if (bwd_v4_ok(n1, p1, n2, p2, d) && !dk_trans) {
-      const int nt = ceil_div(n2, V4_TJ), nrc = ceil_div(n1, V4_TIB);
+      const int vpl = g_bwd_vpl;
+      const int nt = ceil_div(n2, 32 * vpl), nrc = ceil_div(n1, V4_TIB);
       float* part = reinterpret_cast<float*>(ws);
       const size_t part_bytes = round_up64(sizeof(float) * (size_t)nt * n1 * (p1 + 1) * d, 16);
       double* part_sc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + part_bytes);
       const int DPr = (d + 3) & ~3;
       dim3 grid(nt, nrc);
       int launched = 0;
-#define BV4(A, B, DPV)                                                                                         \
-  if (!launched && p1 == A && p2 == B && DPr == DPV) {                                                         \
-    const size_t smem = bwd_v4_smem_bytes<A, B, DPV>();                                                        \
-    auto kern = kdir_bwd_v4<A, B, DPV>;                                                                        \
+#define BV4V(A, B, DPV, VPLV)                                                                                  \
+  if (!launched && p1 == A && p2 == B && DPr == DPV && vpl == VPLV) {                                          \
+    const size_t smem = bwd_v4_smem_bytes<A, B, DPV, VPLV>();                                                  \
+    auto kern = kdir_bwd_v4<A, B, DPV, VPLV>;                                                                  \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     kern<<<grid, 256, smem, st>>>(x1, u1, n1, x2, w2, n2, d, hyp, use_os, dK, lddk, part, part_sc);            \
     launched = 1;                                                                                              \
   }
+#define BV4(A, B, DPV) BV4V(A, B, DPV, 4) BV4V(A, B, DPV, 2)
 #define BV4_ALL(A, B) BV4(A, B, 4) BV4(A, B, 8) BV4(A, B, 12) BV4(A, B, 16)
       BV4_ALL(1, 1) BV4_ALL(2, 2) BV4_ALL(1, 0) BV4_ALL(2, 0)
+      BV4(2, 0, 20) BV4(1, 0, 20)                            // d = 17..20 without data-side directions (uci_dfree-shaped, d = 18)
 #undef BV4_ALL
 #undef BV4
+#undef BV4V
       if (launched) {
         CHECK_LAUNCH();
         kdir_bwd_reduce_rows<float><<<ceil_div(n1 * (p1 + 1), 8), 256, 0, st>>>(part, nt, n1, p1, d, u1, inv1, scale, gx, gv);

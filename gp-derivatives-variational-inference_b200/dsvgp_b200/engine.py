@@ -178,6 +178,13 @@ class Engine:
             ev = self._events[key] = torch.cuda.Event()
         return ev
 
+    def _scales_event(self, device):
+        key = "scales:" + str(device)
+        ev = self._events.get(key)
+        if ev is None:
+            ev = self._events[key] = torch.cuda.Event()
+        return ev
+
     def _side_stream(self, device):
         key = str(device)
         st = self._streams.get(key)
@@ -269,8 +276,9 @@ class Engine:
         ops.tc_scales(f.hyp, f.jitter if jitter is None else jitter, f.maxbits, f.Mq, f.scales, 0)
 
     @staticmethod
-    def _factorise(f, P, T, extra_jitter, prep=True):
-        """[hyper-parameter transforms, direction normalisation,] K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1."""
+    def _factorise(f, P, T, extra_jitter, prep=True, wait=None):
+        """[hyper-parameter transforms, direction normalisation,] K_zz + (1e-3 + extra) I in fp64 -> L, W = L^-1.
+        wait: event after which f.scales is valid (elbo_step computes the scales on its side stream)."""
         if prep:
             Engine._prep(f, P, T)
         if f.Mp > f.Mq:
@@ -284,6 +292,8 @@ class Engine:
         if f.tch:
             if prep:
                 Engine._scales0(f, P)
+            if wait is not None:
+                torch.cuda.current_stream(f.W.device).wait_event(wait)
             ops.split_half(f.W, f.scales[0:1], f.Wh, f.Wl, mode=1, hiT=f.WTh, loT=f.WTl, rows=f.Mq, cols=f.Mq)
         f.Wt_fresh = T != F32
         if T == F32 and not f.tch:                  # (the 3xFP16 path reads W only through its two-half split: see _wt)
@@ -361,8 +371,13 @@ class Engine:
                 ops.split_lo(ws.E, ws.E_lo)
                 ops.transpose(ws.E, ws.ET)
                 ops.split_lo(ws.ET, ws.ET_lo)
+                # (one CTA pair per tile here, not the persistent kernel: this product is a filler under the latency-bound Cholesky,
+                # and persistent CTAs hold every SM for its whole 0.1 ms -- the next diagonal block of the factorisation, a 4-CTA
+                # cluster, then waits for it: seen as a 45 us + 70 us hole in the chain in the profiler trace)
+                ops.set_tc_persistent(False)
                 ops.gemm_tc(ws.E, ws.E_lo, ws.E, ws.E_lo, ws.P, Mq, Mq, Mq, b_kmajor=True, a_tri=TRI_LOWER, c_lower=True,
                             chunk=TC_CHUNK)                                                   # lower tiles of E E^T
+                ops.set_tc_persistent(True)
                 # the scale of D from its MEASURED maximum (the a-priori bound is loose by ~M' max|E| for a trained q(u))
                 ops.build_d_absmax(ws.E, ws.P, f.maxbits[4:5], Mq)
                 ops.tc_scales(f.hyp, f.jitter, f.maxbits, Mq, f.scales, 2)
@@ -624,8 +639,6 @@ class Engine:
         nq_global = (n_global if n_global is not None else n) * (p2 + 1)
         wx = self._data_dirs(ws, Vx, T)
         self._prep(f, P, T)
-        if f.tch:
-            self._scales0(f, P, KZZ_JITTER)
         # K_zx assembly and the L_s operands do not depend on the factor: they run on a side stream underneath the
         # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle).  The host has just come out of the
         # previous step's status read, so the GPU is waiting for launches: the factorisation (the critical path) is
@@ -635,11 +648,21 @@ class Engine:
         fork = torch.cuda.Event() if capturing else self._fork_event(dev)
         fork.record(cur)
         for extra in (0.0,) + CHOL_RETRY:
+            scales_ready = None
             if f.tch and extra != 0.0:
                 self._scales0(f, P, KZZ_JITTER + extra)
-            self._factorise(f, P, T, extra, prep=False)
-            if extra == 0.0:
+            elif f.tch:
+                # the operand scales (a 30 us pass over L_s) are first needed by the split of W AFTER the factorisation and by the
+                # side-stream assembly: they go to the side stream too instead of in front of the K_zz assembly
                 side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    self._scales0(f, P, KZZ_JITTER)
+                    scales_ready = torch.cuda.Event() if capturing else self._scales_event(dev)
+                    scales_ready.record(side)
+            self._factorise(f, P, T, extra, prep=False, wait=scales_ready)
+            if extra == 0.0:
+                if not f.tch:
+                    side.wait_event(fork)
                 with torch.cuda.stream(side):
                     self._assemble(ws, f, P, x, wx)
                     ws.kl.zero_()                      # KL(q(u) || p(u)) needs the parameters only: also under the Cholesky

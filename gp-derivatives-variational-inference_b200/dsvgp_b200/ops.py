@@ -131,6 +131,21 @@ def transpose(src, dst, rows=None, cols=None):
     return dst
 
 
+def set_chol_lookahead(on):
+    """Trailing updates of the factorisation split into an urgent thin part and a bulk part on its own stream (default off)."""
+    return call_raw("dsvgp_set_chol_lookahead", int(bool(on)))
+
+
+def set_chol_priority(on):
+    """Factorisation chains on the library's high-priority streams, or (default) the diagonal chain on the caller's stream."""
+    return call_raw("dsvgp_set_chol_priority", int(bool(on)))
+
+
+def set_kdir_bwd_vpl(vpl):
+    """Column points per lane of the vectorised fp32 assembly backward (2 or 4)."""
+    return call_raw("dsvgp_set_kdir_bwd_vpl", int(vpl))
+
+
 def set_tc_cta_group(cg):
     """1: one CTA per 128x256 tile; 2: CTA pairs (tcgen05 cta_group::2) on 256x256 tiles."""
     return call_raw("dsvgp_set_tc_cta_group", int(cg))

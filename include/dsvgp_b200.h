@@ -49,6 +49,9 @@ int64_t dsvgp_launch_count(void);
  * evict-first (st.global.cs) stores of the covariance rows (0 off, 1 on, 2 = when the output exceeds 64 MB, the
  * default).  Negative = leave unchanged.  Returns tib*4 + stream_stores as set before the call. */
 int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores);
+/* column points per lane of the vectorised fp32 assembly backward: 4 (default; 128-point column tiles, one CTA per SM) or 2
+ * (64-point tiles, two CTAs per SM).  Returns the value in force. */
+int dsvgp_set_kdir_bwd_vpl(int vpl);
 
 /* Positive()/GreaterThan(1e-4) transforms of gpytorch that the reference reaches through
  * self.lengthscale (RBFKernelDirectionalGrad.py:67), ScaleKernel.outputscale (directional_vi.py:56) and
@@ -109,6 +112,18 @@ int dsvgp_pad_identity_f64(double* A, int64_t ld, int Mq, int Mp, dsvgp_stream_t
  * rank-8 updates and inverse), 2 (default) = a small multi-CTA kernel forms the update of the next diagonal block and the
  * block kernel does every bulk operation as 8x8 DMMA tiles.  Returns the value in force.  Results agree to rounding. */
 int dsvgp_set_chol_variant(int v);
+/* 1: the factorisation's three chains (diagonal blocks; panels + trailing updates; eager inverse) run on high-priority
+ * streams owned by the library, forked from / joined to the caller's stream, so that work the caller overlaps with the
+ * latency-bound factorisation on other streams cannot delay it; 0 (default; measured equal): the diagonal chain stays on the
+ * caller's stream.
+ * Returns the value in force. */
+int dsvgp_set_chol_priority(int on);
+/* 1: while the trailing matrix is large, the update of step k is split into the first two block columns of the
+ * trapezoid (all that the diagonal block k+2 and the panel k+1 read; side stream) and the rest (a low-priority stream of its
+ * own, two links' time to finish);
+ * 0 (default; the split measured no gain): one product per step, which the diagonal block k+2 waits for.  Returns the value
+ * in force. */
+int dsvgp_set_chol_lookahead(int on);
 /* profiling aid: a device buffer of 64 int64 that one diagonal-block kernel fills with clock64() stamps at its phase
  * boundaries (NULL switches it off); see scratch/potrf_phases.py */
 int dsvgp_set_potrf_debug(void* buf);

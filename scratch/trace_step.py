@@ -58,3 +58,7 @@ for s0, e0, nm in iv[1:]:
     if s0 > cur_end: idle += s0 - cur_end
     cur_end = max(cur_end, e0)
 print(f"total idle inside the step: {idle/1000:.3f} ms")
+if len(sys.argv) > 2:
+    print("first kernels of the last step (start us, duration us, stream, name):")
+    for e in last[: int(sys.argv[2])]:
+        print(f"  {(e.time_range.start - t_first):8.1f} {(e.time_range.end - e.time_range.start):7.1f}  s{getattr(e, 'device_index', 0)}:{getattr(e, 'device_resource_id', getattr(e, 'stream', -1))}  {e.name.split('(')[0][-60:]}")
