@@ -75,6 +75,15 @@ def stream():
 def call(name, *args):
     """Call an int-returning entry point on torch's current stream; raise on a negative status.
     Returns the (non-negative) status: a few entry points use 1 to report an optional extra output."""
+    # per-device state (streams, function attributes, work lists) follows the CURRENT device: refuse tensors that live elsewhere
+    # instead of launching on the wrong device / stream (one process per GPU is the supported layout)
+    cur = None
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            cur = torch.cuda.current_device() if cur is None else cur
+            if a.device.index != cur:
+                raise DsvgpError(f"{name}: tensor on cuda:{a.device.index} but the current device is cuda:{cur} "
+                                 "(use torch.cuda.set_device / torch.cuda.device(...) around the call)")
     rc = getattr(_lib, name)(*[_arg(a) for a in args], stream())
     if rc < 0:
         raise DsvgpError(f"{name} failed: {ERRORS.get(rc, rc)}")
