@@ -474,9 +474,10 @@ def main():
         ops.kdir_fwd_half(P_Z, fac.uzT, p, x, wx, p2, fac.hyp, ws.Kzx, ws.Kh, ws.Kl, fac.scales[1:2], canon=ws.canon)
         whiten = lambda: ops.gemm_tch((fac.Wh, fac.Wl), (ws.Kh, ws.Kl), ws.A, Mq, nq, Mq, fac.scales[8:9], a_tri=ops.TRI_LOWER,
                                       chunk=_eng.TCH_CHUNK, Ch=(ws.Ah, ws.Al), c_scale=fac.scales[3:4])
-        kname = ("gemm_tch2_kernel (A = L^-1 K_zx: tcgen05.mma kind::f16 x3 (3xFP16 on power-of-two-scaled two-half operands, "
-                 f"22 significand bits), TMA-fed, CTA pairs, TMEM accumulators restarted every {_eng.TCH_CHUNK} k-block(s) of 64, "
-                 "fp32 master sums; epilogue also writes the split of A for the next product)")
+        kname = ("gemm_tch2p_kernel (A = L^-1 K_zx: tcgen05.mma kind::f16 x3 (3xFP16 on power-of-two-scaled two-half operands, "
+                 f"22 significand bits), TMA-fed, PERSISTENT CTA pairs walking a host-balanced work list, TMEM accumulators restarted "
+                 f"every {_eng.TCH_CHUNK} k-block(s) of 64, fp32 master sums in registers moved to the epilogue warps with setmaxnreg; "
+                 "epilogue also writes the split of A for the next product)")
     elif use_tc:
         ops.split_lo(ws.Kzx, ws.lo1, Mq, nq)
         whiten = lambda: ops.gemm_tc(fac.Wt, fac.Wt_lo, ws.Kzx, ws.lo1, ws.A, Mq, nq, Mq, a_tri=ops.TRI_LOWER,
