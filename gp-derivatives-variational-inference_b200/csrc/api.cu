@@ -68,7 +68,8 @@ size_t dsvgp_kdir_bwd_workspace_f64(int n1, int p1, int n2, int p2, int d) { ret
   int NAME(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T* x2, const TK* w2, int n2, int p2,   \
            int d, const double* hyp, int use_os, const TK* dK, int64_t lddk, int dk_trans, double scale,           \
            double* gx, double* gv, double* gsc, void* ws, size_t ws_bytes, dsvgp_stream_t s) {                     \
-    if (!x1 || !x2 || !hyp || !dK || !ws || (p1 > 0 && (!u1 || !inv1)) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG;  \
+    /* (inv1 = 1/|v1| is read only by the normalisation chain of gv) */                                            \
+    if (!x1 || !x2 || !hyp || !dK || !ws || (p1 > 0 && (!u1 || (gv && !inv1))) || (p2 > 0 && !w2)) return DSVGP_ERR_ARG; \
     return kdir_bwd<T, TK>(x1, u1, inv1, n1, p1, x2, w2, n2, p2, d, hyp, use_os, dK, lddk, dk_trans, scale, gx,    \
                            gv, gsc, ws, ws_bytes, ST(s));                                                          \
   }

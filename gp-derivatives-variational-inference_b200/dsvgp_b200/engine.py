@@ -521,6 +521,13 @@ class Engine:
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
         if reducer is not None:
             reducer.end(ws.small)
+        self._backward_tail(ws, f, P, T, inv_num_data, reducer)
+
+    def _backward_tail(self, ws, f, P, T, inv_num_data, reducer=None):
+        """The O(M'^3) part of the backward pass, identical on every rank: from G (symmetric, with dA A^T = m t^T + 2 (S - I) G),
+        t = A g_mu and the K_zx contributions already in ws.small to the gradients of m, L_s, Z, V_z, ell, os."""
+        Mq = ws.Mq
+        tc = ws.tc and f.tc
         # ---- replicated tail: O(M'^3), identical on every rank
         W = f.W
         if tc:
@@ -756,7 +763,7 @@ class Engine:
         return ws.mu.clone(), ws.var.clone()
 
     # ----------------------------------------------------------- public: full predictive covariance and samples
-    def predict_full(self, P, x, Vx, p, p2, add_noise, reuse_factor=False):
+    def predict_full(self, P, x, Vx, p, p2, add_noise, reuse_factor=False, return_ctx=False):
         """mean (n') and the dense n' x n' covariance of q(f(X)) [+ noise]:
         K_xx + 1e-4 I + A^T (S - I) A  (DGVS.py:192-205; SURVEY section 8f rank 4 -- what `preds.sample` of the BO
         callers consumes, experiments/rover/test_turbo.py:119-150).  The training path never forms this matrix."""
@@ -789,7 +796,51 @@ class Engine:
         if add_noise:
             cov.diagonal().add_((f.hyp[2] * int(add_noise)).to(T))
         ops.gemm(ws.A, ws.C, cov, ta=True, beta=1.0, M=nq, N=nq, K=Mq)            # += A^T (S - I) A
+        if return_ctx:
+            ws.wx = wx
+            return (ws, f), ws.mu.clone(), cov
         return ws.mu.clone(), cov
+
+    # ----------------------------------------------------------------- public: differentiable FULL predictive covariance
+    def full_forward(self, P, x, Vx, p, p2, add_noise):
+        """(ctx, mean, dense covariance) with everything full_backward needs kept in the workspace: the differentiable form of
+        predict_full (the reference's lazy predictive covariance is differentiable, DGVS.py:192-208)."""
+        return self.predict_full(P, x, Vx, p, p2, add_noise, reuse_factor=False, return_ctx=True)
+
+    def full_backward(self, ctx, P, x, gmean, gcov, add_noise):
+        """Gradients of a scalar whose derivatives w.r.t. (mean, covariance) of q(f(X)) are (gmean, gcov).
+        Sigma = K_xx + 1e-4 I + A^T D A (+ noise), D = S - I:  with Gs = gcov + gcov^T,
+            dA = m gmean^T + D (A Gs),   G = 1/2 (A Gs) A^T  (then dA A^T = m t^T + 2 D G, t = A gmean, dL_s = tril(2 G L_s)),
+        i.e. the same (dA, G, t) interface as the diagonal case, after which dK_zx = W^T dA, the assembly backward and the
+        O(M'^3) tail are the training step's own (_backward_tail).  K_xx contributes to the lengthscale / outputscale only.
+        Evaluation sizes (BO candidates: n' of a few hundred to a few thousand): every product on the generic mma.sync GEMM."""
+        ws, f = ctx
+        T, Mq, nq = x.dtype, ws.Mq, ws.nq
+        wx = ws.wx
+        ws.small.zero_()
+        if ws.B is None:                              # (the 3xFP16 training path has no use for this M' x n' buffer)
+            ws.B = torch.empty(Mq, ws.ldn, dtype=T, device=x.device)
+        A, AG, Bp, B2 = ws.A, ws.B, ws.Bp, ws.Kzx
+        gmean = gmean.contiguous()
+        Gs = (gcov + gcov.transpose(0, 1)).contiguous()
+        ops.pred_bwd_scalars(gmean, gcov.diagonal().contiguous(), ws.p2, f.hyp, add_noise, ws.sc[4:], ws.scratch)   # d noise, d c
+        ops.gemm(A, Gs, AG, M=Mq, N=nq, K=nq)                                                   # A Gs
+        torch.mv(A[:, :nq], gmean, out=ws.t)                                                    # t = A gmean
+        ops.gemm(AG, A, ws.G, tb=True, alpha=0.5, M=Mq, N=Mq, K=nq)                             # G = 1/2 (A Gs) A^T (symmetric)
+        # D (A Gs) without forming D:  B' = E^T Y,  D Y = E (Y + B') + B'   (E = tril(L_s) - I; no cancellation against Y)
+        ops.gemm(ws.E, AG, Bp, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq, C2=B2, D2=AG)
+        ops.gemm(ws.E, B2, Bp, a_tri=TRI_LOWER, beta=1.0, M=Mq, N=nq, K=Mq)
+        Bp[:, :nq].addr_(P.m, gmean)                                                            # dA = m gmean^T + D A Gs
+        dKzx = ws.Kzx
+        ops.gemm(self._wt(f), Bp, dKzx, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)             # dK_zx = L^-T dA
+        ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
+        # K_xx: only the kernel hyper-parameters depend on it (x and the data directions are inputs, not parameters).  Its DIAGONAL
+        # (closed form in ell, os) is already in pred_bwd_scalars' terms above: the assembly backward gets the off-diagonal part.
+        goff = gcov.clone()
+        goff.diagonal().zero_()
+        ops.kdir_bwd(x, wx if ws.p2 else None, None, ws.p2, x, wx if ws.p2 else None, ws.p2, f.hyp, goff, None, None, ws.sc[4:6])
+        self._backward_tail(ws, f, P, T, 0.0)
+        return self._collect(ws, f, P, T, ws.sc[6])
 
     def sample_mvn(self, mean, cov, num_samples, generator=None):
         """num_samples draws of N(mean, cov): fp64 Cholesky of cov on the library's own blocked factorisation (same

@@ -466,10 +466,37 @@ class _Predictive(torch.autograd.Function):
         return (None, None, None, *out)
 
 
+class _FullPredictive(torch.autograd.Function):
+    """(mean, dense covariance) of q(f(X)) [+ noise] as differentiable tensors: what gpytorch's lazy predictive covariance gives the
+    reference (DirectionalGradVariationalStrategy.py:192-208).  Used by PredictiveDistribution.covariance_matrix / .rsample when
+    gradients are enabled and a parameter requires them."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, Vx, *params):
+        P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, params)))
+        ectx, mean, cov = ENGINE.full_forward(P, x, Vx, cfg["p"], cfg["p2"], cfg["add_noise"])
+        ctx.ectx, ctx.P, ctx.x, ctx.cfg = ectx, P, x, cfg
+        ctx.generation = (ectx[0].generation, ectx[1].generation)
+        return mean, cov
+
+    @staticmethod
+    def backward(ctx, gmean, gcov):
+        if (ctx.ectx[0].generation, ctx.ectx[1].generation) != ctx.generation:
+            raise RuntimeError("dsvgp_b200: the predictive workspace was overwritten by a later forward pass before "
+                               "backward ran; call backward before evaluating the model again on the same shape")
+        grads = ENGINE.full_backward(ctx.ectx, ctx.P, ctx.x, gmean, gcov, ctx.cfg["add_noise"])
+        out = []
+        for name, need in zip(_PARAM_ORDER, ctx.needs_input_grad[3:]):
+            g = grads.get(name)
+            out.append(g if (need and g is not None) else None)
+        return (None, None, None, *out)
+
+
 class PredictiveDistribution:
     """Lazy q(f(X)) returned by a variational strategy (stands in for gpytorch's MultivariateNormal with a lazy
     covariance).  Only what the reference's callers consume is offered: .mean / .loc, .variance, .stddev
-    (directional_vi.py:256-257, :297-298).  The full predictive covariance (.covariance_matrix) and .sample / .rsample are evaluated without autograd."""
+    (directional_vi.py:256-257, :297-298), plus the full predictive covariance (.covariance_matrix, differentiable) and
+    .sample / .rsample (the draw itself is not reparameterised)."""
 
     def __init__(self, strategy, x, Vx, likelihood=None, noise_mult=0):
         self._strategy, self._x, self._Vx, self._likelihood = strategy, x, Vx, likelihood
@@ -502,12 +529,17 @@ class PredictiveDistribution:
 
     @property
     def mean(self):
+        if self._cache is None and self._full is not None:      # the dense evaluation already has it (and owns the workspace:
+            return self._full[0]                                 #  a second, diagonal pass would invalidate its pending backward)
         return self._evaluate()[0]
 
     loc = mean
 
     @property
     def variance(self):
+        if self._cache is None and self._full is not None:
+            min_var = 1e-10 if self._full[1].dtype == torch.float64 else 1e-6      # gpytorch settings.min_variance
+            return self._full[1].diagonal().clamp_min(min_var)
         return self._evaluate()[1]
 
     @property
@@ -515,13 +547,19 @@ class PredictiveDistribution:
         return self.variance.sqrt()
 
     def _evaluate_full(self):
-        """(mean, dense covariance) -- evaluated without autograd (the BO callers sample under eval / no_grad)."""
+        """(mean, dense covariance): differentiable w.r.t. the parameters when gradients are enabled (the reference's lazy
+        covariance is, DGVS.py:192-208); the BO callers sample under eval / no_grad and take the plain evaluation."""
         if self._full is None:
             st = self._strategy
-            P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, (t.detach() if t is not None else None for t in self._params()))))
-            with torch.no_grad():
-                self._full = ENGINE.predict_full(P, self._x, self._Vx, st._p(), st._p2(), self._noise_mult,
-                                                 reuse_factor=not st.training)
+            params = self._params()
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params):
+                cfg = dict(p=st._p(), p2=st._p2(), add_noise=self._noise_mult)
+                self._full = _FullPredictive.apply(cfg, self._x, self._Vx, *params)
+            else:
+                P = types.SimpleNamespace(**dict(zip(_PARAM_ORDER, (t.detach() if t is not None else None for t in params))))
+                with torch.no_grad():
+                    self._full = ENGINE.predict_full(P, self._x, self._Vx, st._p(), st._p2(), self._noise_mult,
+                                                     reuse_factor=not st.training)
         return self._full
 
     @property
@@ -532,7 +570,7 @@ class PredictiveDistribution:
     lazy_covariance_matrix = covariance_matrix
 
     def rsample(self, sample_shape=torch.Size(), base_samples=None):
-        mean, cov = self._evaluate_full()
+        mean, cov = (t.detach() for t in self._evaluate_full())      # (the draw is not reparameterised: no gradient through it)
         shape = torch.Size(sample_shape)
         num = int(math.prod(shape)) if len(shape) else 1
         out = ENGINE.sample_mvn(mean, cov, num)

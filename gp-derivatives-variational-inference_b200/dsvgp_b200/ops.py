@@ -96,7 +96,7 @@ def kdir_bwd(x1, u1, inv1, p1, x2, w2, p2, hyp, dK, gx, gv, gsc, use_os=True, dk
     n2 = x2.shape[0]
     nbytes = call_raw("dsvgp_kdir_bwd_workspace_" + suffix(dK.dtype), n1, p1, n2, p2, d)
     ws = _workspace(nbytes, x1.device, "kdir_bwd")
-    call("dsvgp_kdir_bwd_" + _pair_suffix(x1.dtype, dK.dtype), x1, u1 if p1 else None, inv1 if p1 else None, n1, p1,
+    call("dsvgp_kdir_bwd_" + _pair_suffix(x1.dtype, dK.dtype), x1, u1 if p1 else None, inv1 if (p1 and gv is not None) else None, n1, p1,
          x2, w2 if p2 else None, n2, p2, d, hyp, int(use_os), dK, _ld(dK), int(dk_trans), float(scale), gx,
          gv if p1 else None, gsc, ws, ws.numel())
 

@@ -369,6 +369,54 @@ def test_full_predictive_covariance_matches_oracle(variant, n, d, M, p, dtype):
             assert dist.lazy_covariance_matrix.shape == (mean.numel(), mean.numel())
 
 
+@pytest.mark.parametrize("variant,n,d,M,p,dtype,noisy", [
+    ("dsvgp", 60, 3, 40, 1, F64, False), ("dsvgp", 90, 10, 64, 2, F32, True), ("dfree", 80, 6, 32, 2, F64, True),
+    ("grad", 30, 3, 20, 3, F64, False), ("dsvgp", 700, 10, 192, 2, F32, False)])
+def test_gradients_through_the_full_predictive_covariance(variant, n, d, M, p, dtype, noisy):
+    """The reference's predictive covariance is a differentiable lazy tensor (DGVS.py:192-208): a scalar of (mean, dense
+    covariance) -- random, NON-symmetric weights on the covariance -- must give the oracle's parameter gradients."""
+    P, x, Vx, y, num_data = O.make_problem(n, d, M, p, dtype, seed=11 + n, variant=variant, N=10 * n)
+    up = lambda t: None if t is None else t.double()
+    model, lik = build(variant, P, d, dtype)
+    model.train(), lik.train()                  # (training mode: a fresh factorisation, as an acquisition optimiser would run it)
+    kw = {} if variant == "grad" else {"derivative_directions": Vx}
+    dist = model(x.cuda(), **kw)
+    dist = lik(dist) if noisy else dist
+    cov, mean = dist.covariance_matrix, dist.mean
+    assert cov.requires_grad and mean.requires_grad
+    nq = mean.numel()
+    g = torch.Generator().manual_seed(5)
+    Wc = torch.randn(nq, nq, generator=g, dtype=torch.float64) / nq
+    wm = torch.randn(nq, generator=g, dtype=torch.float64)
+    val = (cov * Wc.to(dtype).cuda()).sum() + (mean * wm.to(dtype).cuda()).sum()
+    val.backward()
+    Q = P.clone(F64).requires_grad_(True)
+    rmean, rcov = O.predictive_full(Q, up(x), up(Vx), variant, add_noise=noisy)
+    rval = (rcov * Wc).sum() + (rmean * wm).sum()
+    names = [k for k, t_ in Q.tensors().items() if not (variant == "grad" and k == "Vz")]
+    rg = torch.autograd.grad(rval, [getattr(Q, k) for k in names], allow_unused=True)
+    ref = {k: (gk if gk is not None else torch.zeros_like(getattr(Q, k))) for k, gk in zip(names, rg)}
+    t = 1e-9 if dtype == F64 else 1e-4
+    assert abs(float(val.detach()) - float(rval.detach())) <= t * abs(float(rval.detach()))
+    got = grads_of(model, lik)
+    for k, gk in ref.items():
+        if k == "raw_noise" and not noisy:
+            continue
+        if float(gk.abs().max()) == 0.0:
+            assert got.get(k) is None or float(got[k].abs().max()) == 0.0, k
+            continue
+        assert got.get(k) is not None, k
+        r = rel(got[k], gk)
+        assert r < t, (k, r)
+    # a second evaluation on the same shape invalidates a pending backward instead of corrupting it
+    d1 = model(x.cuda(), **kw)
+    c1 = d1.covariance_matrix
+    d2 = model(x.cuda(), **kw)
+    _ = d2.covariance_matrix
+    with pytest.raises(RuntimeError):
+        c1.sum().backward()
+
+
 def test_samples_follow_the_predictive_distribution():
     """preds.sample(torch.Size([n_samples])) (experiments/rover/test_turbo.py:138): shape, and first two moments of
     many draws against the oracle's mean / covariance (statistical tolerance)."""
