@@ -20,6 +20,8 @@ Multi-GPU (distributed.py): everything up to and including G is local to a minib
 sums the two buffers that have to be summed over ranks before the replicated tail runs ([G | t] underneath the
 dK_zx product and the K_zx assembly backward).
 """
+import os
+
 import torch
 
 from . import ops
@@ -41,6 +43,7 @@ WHITEN_FP64 = "auto"  # fp32 model: run the two products that multiply by W = L^
 WHITEN_FP64_MAX_NQ = 2048
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
+PERSISTENT_UNDER_REDUCE = os.environ.get("DSVGP_PERSISTENT_UNDER_REDUCE", "1") != "0"   # N > 1: dK_zx product under the [G | t] all-reduce
 HALF_A = False     # 3xFP16 training step (DENSE_D): True = A = W K_zx leaves the whitening product ONLY as its two-half split (the operand
                    # of C = (S - I) A and of the Gram product) and the column reductions / the dA pass read that split (A_ij = (hi + lo) / s_A,
                    # 22 significand bits).  The product's store phase is bound by the SM's 32 B/clk write port and exposed, so 8 instead of
@@ -499,7 +502,14 @@ class Engine:
                 ops.gemm(f.W, ws.B64, ws.A64, ta=True, a_tri=TRI_UPPER, M=Mq, N=nq, K=Mq)
                 ops.cast2d(ws.A64, dKzx, Mq, nq)
             else:
+                # (under an overlapping all-reduce the collective's CTAs hold a few SMs when this product starts: the persistent
+                # kernel's static work lists assume all pairs start together, one pair per tile absorbs the late SMs)
+                under_reduce = reducer is not None and getattr(reducer, "overlap", False) and not PERSISTENT_UNDER_REDUCE
+                if under_reduce:
+                    ops.set_tc_persistent(False)
                 ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
+                if under_reduce:
+                    ops.set_tc_persistent(True)
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             # (E, E^T as fp32 + lo for the two M'^3 products of the tail were made by _assemble)
         else:
