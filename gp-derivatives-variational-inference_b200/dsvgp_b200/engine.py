@@ -43,6 +43,7 @@ WHITEN_FP64 = "auto"  # fp32 model: run the two products that multiply by W = L^
 WHITEN_FP64_MAX_NQ = 2048
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
+WORKSPACE_CACHE = 6    # problem shapes whose buffers are kept (least recently used evicted)
 PERSISTENT_UNDER_REDUCE = os.environ.get("DSVGP_PERSISTENT_UNDER_REDUCE", "1") != "0"   # N > 1: dK_zx product under the [G | t] all-reduce
 HALF_A = False     # 3xFP16 training step (DENSE_D): True = A = W K_zx leaves the whitening product ONLY as its two-half split (the operand
                    # of C = (S - I) A and of the Gram product) and the column reductions / the dA pass read that split (A_ij = (hi + lo) / s_A,
@@ -197,21 +198,26 @@ class Engine:
 
     def workspace(self, device, dtype, n, d, M, p, p2):
         key = (str(device), dtype, n, d, M, p, p2)
-        ws = self._ws.get(key)
+        ws = self._ws.pop(key, None)
         if ws is None:
-            if len(self._ws) > 3:          # eval batches of many sizes: do not hoard HBM
-                self._ws.clear()
-            ws = self._ws[key] = Workspace(device, dtype, n, d, M, p, p2)
+            # eval batches of many sizes: do not hoard HBM -- but evict the LEAST recently used shape only (a training loop with a
+            # ragged last minibatch and an evaluation loop alternate between four or five shapes; clearing everything made each
+            # of them re-allocate gigabytes per epoch)
+            while len(self._ws) >= WORKSPACE_CACHE:
+                self._ws.pop(next(iter(self._ws)))
+            ws = Workspace(device, dtype, n, d, M, p, p2)
+        self._ws[key] = ws            # (re-inserted last: dict order is the LRU order)
         ws.generation += 1            # every user overwrites it: a saved-for-backward reference can tell (gp._Predictive)
         return ws
 
     def factor(self, device, dtype, d, M, p):
         key = (str(device), dtype, d, M, p)
-        f = self._fac.get(key)
+        f = self._fac.pop(key, None)
         if f is None:
-            if len(self._fac) > 3:
-                self._fac.clear()
-            f = self._fac[key] = Factor(device, dtype, d, M, p)
+            while len(self._fac) >= WORKSPACE_CACHE:
+                self._fac.pop(next(iter(self._fac)))
+            f = Factor(device, dtype, d, M, p)
+        self._fac[key] = f
         f.generation += 1
         return f
 

@@ -4,7 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gp-derivatives-variational-inference_b200"))
 import torch, bench, collections
 from torch.profiler import profile, ProfilerActivity
-from dsvgp_b200 import gp
+from dsvgp_b200 import gp, ops
+if os.environ.get("CHOL_PRIORITY"): ops.set_chol_priority(int(os.environ["CHOL_PRIORITY"]))
+if os.environ.get("CHOL_LOOKAHEAD"): ops.set_chol_lookahead(int(os.environ["CHOL_LOOKAHEAD"]))
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 wl = dict(bench.WORKLOADS[name]); dtype = torch.float64 if wl["dtype"] == "f64" else torch.float32
 dev = torch.device("cuda", 0)
