@@ -85,6 +85,7 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 
 int dsvgp_set_potrf_debug(void* p) { set_potrf_debug(static_cast<long long*>(p)); return 0; }
 int dsvgp_set_gemm64_async(int on) { set_gemm64_async(on); return get_gemm64_async(); }
+int dsvgp_set_rank_update(int on) { set_rank_update(on); return get_rank_update(); }
 int dsvgp_set_chol_variant(int v) { set_chol_variant(v); return get_chol_variant(); }
 int dsvgp_set_chol_lookahead(int on) { set_chol_lookahead(on); return get_chol_lookahead(); }
 int dsvgp_set_chol_priority(int on) { set_chol_priority(on); return get_chol_priority(); }

@@ -411,6 +411,100 @@ gemm64_async_kernel(GemmParams<double> p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fp64 rank-K update  C = alpha * A * B^T + beta * C  with a SHORT contraction (K <= 128: the rank-96 trailing updates of the
+// blocked Cholesky).  An EXPERIMENT, off by default (see g_rank_update below).  The general kernel spends a barrier pair and a register-staged, bank-conflicted store per 16-wide k-tile and
+// ran these updates at 10-12 TFLOP/s (66-78 us for the 0.8 GFLOP update of the first links at M' = 3072 -- longer than the diagonal
+// block beside it, so the panel/update chain, not the diagonal chain, set the pace of the first ten links).  Here the whole
+// K extent of both operand tiles goes global -> shared in ONE cp.async burst ([row][k] layout, row stride = K rounded up to 16
+// plus 4 doubles: conflict-free DMMA fragments), one barrier, then every warp runs its K/4 DMMA steps back to back.
+constexpr int RK_MAXK = 128;
+__host__ __device__ constexpr int rk_ld(int K) { return ((K + 15) & ~15) + 4; }
+
+__device__ __forceinline__ void cp_async16_zfill(double* smem_dst, const double* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+rank_update64_kernel(GemmParams<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int LD = rk_ld(p.K), K4 = (p.K + 3) & ~3;
+  double* As = reinterpret_cast<double*>(smem_raw);                  // [BM][LD]
+  double* Bs = As + BM * LD;                                         // [BN][LD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (p.c_tri == 1 && n0 >= m0 + BM + p.c_off) return;
+  double* C = p.C;
+  const double* D = p.D ? p.D : C;
+  const int64_t ldd = p.D ? p.ldd : p.ldc;
+  // operands: K contiguous; two doubles per cp.async (K, leading dimensions even and bases 16-byte aligned: checked by the host)
+  const int kp = K4 / 2;                                             // 16-byte pieces per row (zero-filled beyond K)
+  for (int e = tid; e < BM * kp; e += GEMM_THREADS) {
+    const int r = e / kp, k = (e % kp) * 2;
+    const bool ok = (m0 + r < p.M) && (k < p.K);
+    cp_async16_zfill(As + r * LD + k, ok ? p.A + (int64_t)(m0 + r) * p.lda + k : p.A, ok);
+  }
+  for (int e = tid; e < BN * kp; e += GEMM_THREADS) {
+    const int c = e / kp, k = (e % kp) * 2;
+    const bool ok = (n0 + c < p.N) && (k < p.K);
+    cp_async16_zfill(Bs + c * LD + k, ok ? p.B + (int64_t)(n0 + c) * p.ldb + k : p.B, ok);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+#pragma unroll 2
+  for (int kk = 0; kk < K4; kk += 4) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) af[i] = As[(wm + 8 * i + g) * LD + kk + t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn + 8 * j + g) * LD + kk + t];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_f64(acc[i][j], af[i], bf[j]);
+  }
+  const bool v2 = ((p.ldc | ldd) & 1) == 0 && (((uintptr_t)C | (uintptr_t)D) & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm + 8 * i + g, c = n0 + wn + 8 * j + 2 * t;
+      if (r >= p.M) continue;
+      if (v2 && c + 1 < p.N) {
+        double2 res = make_double2(p.alpha * acc[i][j][0], p.alpha * acc[i][j][1]);
+        if (p.beta != 0.0) {
+          const double2 dd = *reinterpret_cast<const double2*>(D + (int64_t)r * ldd + c);
+          res.x += p.beta * dd.x;
+          res.y += p.beta * dd.y;
+        }
+        *reinterpret_cast<double2*>(C + (int64_t)r * p.ldc + c) = res;
+      } else {
+#pragma unroll
+        for (int z = 0; z < 2; ++z)
+          if (c + z < p.N) {
+            const double v = p.alpha * acc[i][j][z];
+            C[(int64_t)r * p.ldc + c + z] = (p.beta == 0.0) ? v : v + p.beta * D[(int64_t)r * ldd + c + z];
+          }
+      }
+    }
+}
+
+static int g_rank_update = 0;   // measured (scratch/rank_update_ab.py, scratch/prio_ab.py): 65 vs 58 us on the first link's update, equal
+                                // later -- both kernels are ramp-bound at K = 96 (13 TFLOP/s) -- and its 100 KB of shared memory per
+                                // CTA crowds the diagonal-block cluster running beside it: the step is 0.1 ms SLOWER.  Off.
+void set_rank_update(int on) { g_rank_update = on ? 1 : 0; }
+int get_rank_update() { return g_rank_update; }
+
 static int g_gemm64_async = 1;
 void set_gemm64_async(int on) { g_gemm64_async = on ? 1 : 0; }
 int get_gemm64_async() { return g_gemm64_async; }
@@ -439,6 +533,22 @@ int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda
   GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri, c_off};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
   if constexpr (sizeof(T) == 8) {
+    if (g_rank_update && !ta && tb && K >= 8 && K <= RK_MAXK && (K & 1) == 0 && batch == 1 && a_tri == 0 && b_tri == 0 && !C2 &&
+        ((lda | ldb) & 1) == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) {
+      const int smem = (BM + BN) * rk_ld(K) * (int)sizeof(double);
+      static bool attr[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr[dev & 63]) {
+        if (cudaFuncSetAttribute(rank_update64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (BM + BN) * rk_ld(RK_MAXK) * (int)sizeof(double)) != cudaSuccess)
+          return DSVGP_ERR_LAUNCH;
+        attr[dev & 63] = true;
+      }
+      rank_update64_kernel<<<grid, GEMM_THREADS, smem, st>>>(p);
+      CHECK_LAUNCH();
+      return DSVGP_OK;
+    }
     if (g_gemm64_async && K > 128) {      // (short contractions -- the rank-96 Cholesky updates -- do not amortise the pipeline fill)
       int rc;
       if (!ta && !tb) rc = launch_gemm64_async<false, false>(p, grid, st);

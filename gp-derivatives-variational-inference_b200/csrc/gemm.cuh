@@ -25,5 +25,8 @@ inline int gemm1(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int
 // fp64 products: 1 (default) = cp.async-pipelined kernel, 0 = the register-staged kernel of round 1 (A/B knob)
 void set_gemm64_async(int on);
 int get_gemm64_async();
+// fp64  C = alpha A B^T + beta C  with K <= 128 (the rank-96 Cholesky updates): 1 = whole-K-in-shared kernel, 0 (default: the former measured no gain) = general kernel
+void set_rank_update(int on);
+int get_rank_update();
 
 }  // namespace dsvgp

@@ -131,6 +131,11 @@ def transpose(src, dst, rows=None, cols=None):
     return dst
 
 
+def set_rank_update(on):
+    """fp64 rank-K update kernel (K <= 128) for A B^T products (default off: measured no gain)."""
+    return call_raw("dsvgp_set_rank_update", int(bool(on)))
+
+
 def set_chol_lookahead(on):
     """Trailing updates of the factorisation split into an urgent thin part and a bulk part on its own stream (default off)."""
     return call_raw("dsvgp_set_chol_lookahead", int(bool(on)))

@@ -140,6 +140,10 @@ int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const doub
  * contiguous along their non-contracted index: no staging stores, conflict-free DMMA fragments, one barrier per k-tile),
  * 0 = the register-staged kernel of round 1.  Returns the value in force. */
 int dsvgp_set_gemm64_async(int on);
+/* fp64 products op(A) = A, op(B) = B^T with a short contraction (8 <= K <= 128, even; no triangle flags on the operands, no
+ * batch): 1 = rank-update kernel (whole K extent of both operand tiles in shared memory in one cp.async burst, one barrier) --
+ * the trailing updates of the blocked Cholesky; 0 (default: the former measured no gain) = the general kernel.  Returns the value in force. */
+int dsvgp_set_rank_update(int on);
 
 /* The same product on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA-fed, accumulators in tensor memory)
  * for the fp32 model's big whitening products -- TriangularLazyTensor.inv_matmul and the L_s products of

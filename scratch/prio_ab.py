@@ -19,6 +19,7 @@ for name, n in (("C3", 16384), ("C3", 512), ("C5", 16384), ("C2", 4096)):
     arm = bench.Arm(wl, dev, 0, 1)
     x, V, y = (t_.to(dev) for t_ in arm.batch(n, 1))
     for rnd in range(2):
-        for la, pr in ((0, 0), (0, 1), (1, 1)):
-            ops.set_chol_lookahead(la); ops.set_chol_priority(pr)
-            print(f"{name} n={n} lookahead={la} priority={pr}: step {t(lambda: arm.step(x, V, y)):.3f} ms", flush=True)
+        for ru, la, pr in ((0, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 1)):
+            ops.set_rank_update(ru); ops.set_chol_lookahead(la); ops.set_chol_priority(pr)
+            print(f"{name} n={n} rank_update={ru} lookahead={la} priority={pr}: step {t(lambda: arm.step(x, V, y)):.3f} ms", flush=True)
+ops.set_rank_update(0); ops.set_chol_lookahead(0); ops.set_chol_priority(0)
