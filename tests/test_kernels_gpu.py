@@ -377,19 +377,22 @@ def _padded(t, ld):
     return out[:, :t.shape[1]]
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg,persistent", [(1, 1), (2, 1), (2, 0)])
 @pytest.mark.parametrize("M,N,K,kw", [
     (128, 256, 64, {}), (200, 300, 100, {}), (384, 1000, 384, dict(a_tri=1)), (384, 1000, 384, dict(a_tri=2)),
     (384, 1000, 384, dict(a_tri=1, alpha=2.0, beta=-2.0, dual=True)), (300, 300, 1000, dict(b_kmajor=True)),
     (512, 512, 2048, dict(b_kmajor=True, c_lower=True)), (512, 512, 8192, dict(b_kmajor=True, c_lower=True, nsplit=4)),
-    (256, 700, 512, dict(chunk=2))])
-def test_gemm_tch_matches_fp64(ops, cg, M, N, K, kw):
+    (256, 700, 512, dict(chunk=2)), (3200, 2100, 3200, dict(a_tri=1, dual=True)), (1536, 1536, 40000, dict(b_kmajor=True, c_lower=True, nsplit=8))])
+def test_gemm_tch_matches_fp64(ops, cg, persistent, M, N, K, kw):
     """tcgen05 kind::f16 x3 on scaled two-half operands against an fp64 product of the SAME quantised operands (so the
-    tolerance measures the kernel: fp32 accumulation + the dropped lo*lo term), every epilogue output included."""
+    tolerance measures the kernel: fp32 accumulation + the dropped lo*lo term), every epilogue output included.
+    (cg, persistent): one CTA per tile; CTA pairs as persistent pairs over a work list (the default -- stream-K for the split-K
+    cases, more items than pairs for the last two shapes); CTA pairs, one pair per tile."""
     F16 = torch.float16
     b_kmajor, a_tri, c_lower = kw.get("b_kmajor", False), kw.get("a_tri", 0), kw.get("c_lower", False)
     alpha, beta, dual, nsplit, chunk = kw.get("alpha", 1.0), kw.get("beta", 0.0), kw.get("dual", False), kw.get("nsplit", 1), kw.get("chunk", 1)
     prev = ops.set_tc_cta_group(cg)
+    ops.set_tc_persistent(persistent)
     try:
         g = torch.Generator(device="cuda").manual_seed(M + N + K)
         A = torch.randn(M, K, device="cuda", dtype=F64, generator=g)
@@ -415,8 +418,19 @@ def test_gemm_tch_matches_fp64(ops, cg, M, N, K, kw):
             assert rel(C2, ref + D2.double()) < 2e-6
             assert rel((Ch[0].double() + Ch[1].double()) / 8.0, ref) < 2e-6
             assert rel((C2h[0].double() + C2h[1].double()) / 4.0, ref + D2.double()) < 2e-6
+        if cg == 2 and persistent and nsplit == 1:
+            # the persistent kernel adds the same chunks in the same order: bit-identical to one pair per tile
+            Cp = C.clone()
+            C.fill_(float("nan"))
+            ops.set_tc_persistent(0)
+            ops.gemm_tch((Ah, Al), (Bh, Bl), C, M, N, K, inv, b_kmajor=b_kmajor, alpha=alpha, beta=beta, D=D if beta else None,
+                         C2=C2 if dual else None, D2=D2 if dual else None, Ch=Ch if dual else None, c_scale=cs,
+                         C2h=C2h if dual else None, c2_scale=c2s, a_tri=a_tri, c_lower=c_lower, chunk=chunk, nsplit=nsplit, split_ws=ws)
+            a_, b_ = (Cp.tril(), C.tril()) if c_lower else (Cp, C)
+            assert torch.equal(a_.contiguous().view(torch.int32), b_.contiguous().view(torch.int32))
     finally:
         ops.set_tc_cta_group(prev)
+        ops.set_tc_persistent(1)
 
 
 def test_tc_operand_scales_and_splits(ops):
