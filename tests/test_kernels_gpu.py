@@ -433,6 +433,47 @@ def test_gemm_tch_matches_fp64(ops, cg, persistent, M, N, K, kw):
         ops.set_tc_persistent(1)
 
 
+@pytest.mark.parametrize("cg,persistent", [(1, 1), (2, 1), (2, 0)])
+@pytest.mark.parametrize("M,N,K,kw", [
+    (128, 256, 64, {}), (200, 300, 100, {}), (384, 1000, 384, dict(a_tri=1, alpha=2.0, beta=2.0)),
+    (384, 1000, 384, dict(a_tri=2, dual=True)), (512, 512, 512, dict(b_kmajor=True, a_tri=1, c_lower=True)),
+    (600, 600, 4096, dict(b_kmajor=True, c_lower=True, nsplit=4)), (3072, 3072, 3072, dict(a_tri=2, dual=True))])
+def test_gemm_tc_3xtf32_matches_fp64(ops, cg, persistent, M, N, K, kw):
+    """tcgen05 kind::tf32 x3 on (fp32, lo) operands (the M'^3 products of the backward tail and E E^T) against an fp64 product
+    of the same fp32 inputs: 3xTF32 keeps 22 significand bits per operand, so the result is fp32-grade."""
+    b_kmajor, a_tri, c_lower = kw.get("b_kmajor", False), kw.get("a_tri", 0), kw.get("c_lower", False)
+    alpha, beta, dual, nsplit = kw.get("alpha", 1.0), kw.get("beta", 0.0), kw.get("dual", False), kw.get("nsplit", 1)
+    prev = ops.set_tc_cta_group(cg)
+    ops.set_tc_persistent(persistent)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(3 * M + N + K)
+        lda, ldn = (K + 7) // 8 * 8, (N + 31) // 32 * 32
+        A = torch.randn(M, K, device="cuda", dtype=F32, generator=g)
+        A = A.tril() if a_tri == 1 else A.triu() if a_tri == 2 else A
+        B = torch.randn((N, K) if b_kmajor else (K, N), device="cuda", dtype=F32, generator=g)
+        Af, Bf = _padded(A, lda), _padded(B, lda if b_kmajor else ldn)
+        Alo, Blo = _padded(torch.zeros_like(A), lda), _padded(torch.zeros_like(B), lda if b_kmajor else ldn)   # (same leading dimensions)
+        ops.split_lo(Af, Alo)
+        ops.split_lo(Bf, Blo)
+        D, D2 = (_padded(torch.randn(M, N, device="cuda", dtype=F32, generator=g), ldn) for _ in range(2))
+        C, C2, Clo, C2lo = (_padded(torch.full((M, N), float("nan"), device="cuda", dtype=F32), ldn) for _ in range(4))
+        ref = alpha * (A.double() @ (B.double().T if b_kmajor else B.double())) + beta * D.double()
+        ws = torch.empty(nsplit * M * ((N + 3) // 4 * 4), device="cuda") if nsplit > 1 else None
+        ops.gemm_tc(Af, Alo, Bf, Blo, C, M, N, K, b_kmajor=b_kmajor, alpha=alpha, beta=beta, D=D if beta else None,
+                    C2=C2 if dual else None, D2=D2 if dual else None, a_tri=a_tri, c_lower=c_lower, chunk=2,
+                    C_lo=Clo if dual else None, C2_lo=C2lo if dual else None, nsplit=nsplit, split_ws=ws)
+        assert (rel(C.tril(), ref.tril()) if c_lower else rel(C, ref)) < 2e-6
+        if dual:
+            assert rel(C2, ref + D2.double()) < 2e-6
+            # the lo companions: what the tensor core does not see of the fp32 outputs (x = trunc_tf32(x) + lo to 2^-22 |x|)
+            trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(F32)
+            assert float((C - trunc(C) - Clo).abs().max()) <= 2.0 ** -21 * float(C.abs().max())
+            assert float((C2 - trunc(C2) - C2lo).abs().max()) <= 2.0 ** -21 * float(C2.abs().max())
+    finally:
+        ops.set_tc_cta_group(prev)
+        ops.set_tc_persistent(1)
+
+
 def test_tc_operand_scales_and_splits(ops):
     """absmax (order-independent), power-of-two scales from the a-priori bounds, and the two-half split kernels."""
     F16 = torch.float16
