@@ -84,6 +84,8 @@ int dsvgp_chol_f64(double* Awork, int64_t lda, double* L, int64_t ldl, double* W
 }
 
 int dsvgp_set_potrf_debug(void* p) { set_potrf_debug(static_cast<long long*>(p)); return 0; }
+int dsvgp_collect_grads_f32(const double* small, int nZ, int nV, const double* hyp, int noise_mode, float* out, dsvgp_stream_t s) { return collect_grads<float>(small, nZ, nV, hyp, noise_mode, out, ST(s)); }
+int dsvgp_collect_grads_f64(const double* small, int nZ, int nV, const double* hyp, int noise_mode, double* out, dsvgp_stream_t s) { return collect_grads<double>(small, nZ, nV, hyp, noise_mode, out, ST(s)); }
 int dsvgp_set_gemm64_async(int on) { set_gemm64_async(on); return get_gemm64_async(); }
 int dsvgp_set_rank_update(int on) { set_rank_update(on); return get_rank_update(); }
 int dsvgp_set_chol_variant(int v) { set_chol_variant(v); return get_chol_variant(); }

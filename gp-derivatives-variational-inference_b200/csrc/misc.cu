@@ -793,6 +793,31 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
   return DSVGP_OK;
 }
 
+// All the small gradients of a step in ONE launch (they used to be ~20 one-microsecond torch kernels at the very end of the step,
+// launch-bound: 0.1 ms): out = [dZ (nZ) | dV_z (nV) | d c | d raw_outputscale | d raw_lengthscale | d raw_noise] in the model dtype
+// from the fp64 buffer small = [scalars(8) | dZ | dV_z]; chain rule of the softplus transforms from hyp[4..6];
+// noise_mode 1: d noise = scalars[1] + scalars[6] (ELBO / PLL step), 0: scalars[6] (generic predictive backward).
+template <typename T>
+__global__ void collect_grads_kernel(const double* __restrict__ small, int nZ, int nV, const double* __restrict__ hyp,
+                                     int noise_mode, T* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = nZ + nV;
+  if (i < n) out[i] = (T)small[8 + i];
+  else if (i == n) out[i] = (T)small[7];
+  else if (i == n + 1) out[i] = (T)(small[5] * hyp[5]);
+  else if (i == n + 2) out[i] = (T)(small[4] * hyp[4]);
+  else if (i == n + 3) out[i] = (T)(((noise_mode ? small[1] : 0.0) + small[6]) * hyp[6]);
+}
+
+template <typename T>
+int collect_grads(const double* small, int nZ, int nV, const double* hyp, int noise_mode, T* out, cudaStream_t st) {
+  if (!small || !hyp || !out || nZ < 0 || nV < 0) return DSVGP_ERR_ARG;
+  collect_grads_kernel<T><<<ceil_div(nZ + nV + 4, 256), 256, 0, st>>>(small, nZ, nV, hyp, noise_mode, out);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+template int collect_grads<float>(const double*, int, int, const double*, int, float*, cudaStream_t);
+template int collect_grads<double>(const double*, int, int, const double*, int, double*, cudaStream_t);
+
 // ------------------------------------------------------------------------------------ fp64 tensor peak (measurement)
 // Register-resident DMMA m8n8k4 chains, 8 independent accumulators per warp, no memory traffic: what the fp64 tensor pipe
 // sustains on this device.  bench.py times it with CUDA events and uses the result as the roofline denominator of every

@@ -49,4 +49,8 @@ int var_grads(const T* H, int64_t ldh, const T* Ls, int64_t ldl, const T* t, con
 
 int dmma_peak(int iters, int ctas, double* out, double* flops_host, cudaStream_t st);
 
+// every small gradient of a step (dZ, dV_z, d c, d raw_os, d raw_ell, d raw_noise) in the model dtype, one launch
+template <typename T>
+int collect_grads(const double* small, int nZ, int nV, const double* hyp, int noise_mode, T* out, cudaStream_t st);
+
 }  // namespace dsvgp

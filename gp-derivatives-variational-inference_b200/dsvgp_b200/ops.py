@@ -308,6 +308,12 @@ def col_dots_half(A_half, a_scale, m, pm, pv, rows, nq, C, cmax=None):
     call("dsvgp_col_dots_h_f32", A_half[0], A_half[1], _ld(A_half[0]), a_scale, C, _ld(C), rows, nq, m, pm, pv, pm.shape[0], cmax)
 
 
+def collect_grads(small, nZ, nV, hyp, noise_mode, out):
+    """out = [dZ | dV_z | d c | d raw_os | d raw_ell | d raw_noise] (model dtype) from the engine's fp64 buffer, one launch."""
+    call("dsvgp_collect_grads_" + suffix(out.dtype), small, int(nZ), int(nV), hyp, int(noise_mode), out)
+    return out
+
+
 def predict_finish(pm, pv, nq, p2, hyp, mu, var, add_noise, pred_jitter=1e-4):
     min_var = 1e-10 if mu.dtype == F64 else 1e-6      # gpytorch settings.min_variance
     call("dsvgp_predict_finish_" + suffix(mu.dtype), pm, pv, pm.shape[0], nq, p2, hyp, float(pred_jitter),

@@ -279,6 +279,11 @@ int dsvgp_kl_f32(const float* m, const float* Ls_raw, int64_t ld, int Mq, double
 int dsvgp_kl_f64(const double* m, const double* Ls_raw, int64_t ld, int Mq, double* out, double* ws, dsvgp_stream_t s);
 
 /* gm = t - m/num_data ; gLs = tril(2 H^T) - (tril(Ls) - diag(1/Ls_ii))/num_data  (H = Ls^T G) */
+/* Every small gradient of a step in one launch: out (model dtype, nZ + nV + 4 elements) = [dZ | dV_z | d c | d raw_outputscale |
+ * d raw_lengthscale | d raw_noise] from the engine's fp64 buffer small = [scalars(8) | dZ (nZ) | dV_z (nV)] and the softplus
+ * derivatives hyp[4..6]; noise_mode 1: d noise = scalars[1] + scalars[6] (ELBO / PLL step), 0: scalars[6]. */
+int dsvgp_collect_grads_f32(const double* small, int nZ, int nV, const double* hyp, int noise_mode, float* out, dsvgp_stream_t s);
+int dsvgp_collect_grads_f64(const double* small, int nZ, int nV, const double* hyp, int noise_mode, double* out, dsvgp_stream_t s);
 int dsvgp_var_grads_f32(const float* H, int64_t ldh, const float* Ls_raw, int64_t ldl, const float* t, const float* m, int Mq, double inv_num_data, float* gm, float* gLs, int64_t ldg, dsvgp_stream_t s);
 int dsvgp_var_grads_f64(const double* H, int64_t ldh, const double* Ls_raw, int64_t ldl, const double* t, const double* m, int Mq, double inv_num_data, double* gm, double* gLs, int64_t ldg, dsvgp_stream_t s);
 
