@@ -180,6 +180,27 @@ kdir_fwd_blocked(const T* __restrict__ x1, const TK* __restrict__ u1, int n1, co
 }
 
 // lo = rn_tf32(x - trunc_tf32(x)): the part of x a TF32 tensor core does not see (see trmm_tc.cu)
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work, and an operand may be a plain
+// fp32 register broadcast to both halves -- make_float2(x, x) costs nothing).  The vectorised assembly kernels are bound by
+// instruction issue on their dot products (ncu: FMA pipe 36 % busy, issue-active 47-74 % with 2-3 warps per scheduler), and
+// a lane's four column points are two such pairs.
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return r;
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return r;
+}
+__device__ __forceinline__ float2 f2bc(float x) { return make_float2(x, x); }
+
 __device__ __forceinline__ float tf32_lo_part(float x) {
   const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   uint32_t t;
@@ -296,6 +317,20 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
         for (int b = 0; b < P2; ++b) ga[a][b][q] = 0.f;
     }
+    // (dot products on packed pairs: pair h holds this lane's column points 2h, 2h + 1)
+    float2 r2p[2], alp[P1 > 0 ? P1 : 1][2], bep[P2 > 0 ? P2 : 1][2], gap[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      r2p[h] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < P1; ++a) alp[a][h] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < P2; ++b) bep[b][h] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P2; ++b) gap[a][b][h] = make_float2(0.f, 0.f);
+    }
     if constexpr (!canon) {
       for (int c4 = 0; c4 < dpad; c4 += 4) {
         const float4 xr = *reinterpret_cast<const float4*>(rbase + c4);
@@ -305,28 +340,29 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 xj4 = *reinterpret_cast<const float4*>(cs + (c4 + k) * TJ + 4 * lane);
-          const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
-          float wj[P2 > 0 ? P2 : 1][4];
+          const float2 xj[2] = {make_float2(xj4.x, xj4.y), make_float2(xj4.z, xj4.w)};
+          float2 wj[P2 > 0 ? P2 : 1][2];
 #pragma unroll
           for (int b = 0; b < P2; ++b) {
             const float4 t = *reinterpret_cast<const float4*>(cs + ((1 + b) * dpad + c4 + k) * TJ + 4 * lane);
-            wj[b][0] = t.x; wj[b][1] = t.y; wj[b][2] = t.z; wj[b][3] = t.w;
+            wj[b][0] = make_float2(t.x, t.y);
+            wj[b][1] = make_float2(t.z, t.w);
           }
-          const float xi = k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w;
-          float ui[P1 > 0 ? P1 : 1];
+          const float2 xi = f2bc(k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w);
+          float2 ui[P1 > 0 ? P1 : 1];
 #pragma unroll
-          for (int a = 0; a < P1; ++a) ui[a] = k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w;
+          for (int a = 0; a < P1; ++a) ui[a] = f2bc(k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float dl = xi - xj[q];
-            r2[q] = fmaf(dl, dl, r2[q]);
+          for (int h = 0; h < 2; ++h) {
+            const float2 dl = f2sub(xi, xj[h]);
+            r2p[h] = f2fma(dl, dl, r2p[h]);
 #pragma unroll
-            for (int b = 0; b < P2; ++b) be[b][q] = fmaf(dl, wj[b][q], be[b][q]);
+            for (int b = 0; b < P2; ++b) bep[b][h] = f2fma(dl, wj[b][h], bep[b][h]);
 #pragma unroll
             for (int a = 0; a < P1; ++a) {
-              al[a][q] = fmaf(dl, ui[a], al[a][q]);
+              alp[a][h] = f2fma(dl, ui[a], alp[a][h]);
 #pragma unroll
-              for (int b = 0; b < P2; ++b) ga[a][b][q] = fmaf(ui[a], wj[b][q], ga[a][b][q]);
+              for (int b = 0; b < P2; ++b) gap[a][b][h] = f2fma(ui[a], wj[b][h], gap[a][b][h]);
             }
           }
         }
@@ -340,20 +376,37 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 xj4 = *reinterpret_cast<const float4*>(cs + (c4 + k) * TJ + 4 * lane);
-          const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w};
-          const float xi = k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w;
-          float ui[P1 > 0 ? P1 : 1];
+          const float2 xj[2] = {make_float2(xj4.x, xj4.y), make_float2(xj4.z, xj4.w)};
+          const float2 xi = f2bc(k == 0 ? xr.x : k == 1 ? xr.y : k == 2 ? xr.z : xr.w);
+          float2 ui[P1 > 0 ? P1 : 1];
 #pragma unroll
-          for (int a = 0; a < P1; ++a) ui[a] = k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w;
+          for (int a = 0; a < P1; ++a) ui[a] = f2bc(k == 0 ? ur[a].x : k == 1 ? ur[a].y : k == 2 ? ur[a].z : ur[a].w);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float dl = xi - xj[q];
-            r2[q] = fmaf(dl, dl, r2[q]);
+          for (int h = 0; h < 2; ++h) {
+            const float2 dl = f2sub(xi, xj[h]);
+            r2p[h] = f2fma(dl, dl, r2p[h]);
 #pragma unroll
-            for (int a = 0; a < P1; ++a) al[a][q] = fmaf(dl, ui[a], al[a][q]);
+            for (int a = 0; a < P1; ++a) alp[a][h] = f2fma(dl, ui[a], alp[a][h]);
           }
         }
       }
+    }
+    // unpack (register renaming only)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      r2[2 * h] = r2p[h].x; r2[2 * h + 1] = r2p[h].y;
+#pragma unroll
+      for (int a = 0; a < P1; ++a) { al[a][2 * h] = alp[a][h].x; al[a][2 * h + 1] = alp[a][h].y; }
+      if constexpr (!canon) {
+#pragma unroll
+        for (int b = 0; b < P2; ++b) { be[b][2 * h] = bep[b][h].x; be[b][2 * h + 1] = bep[b][h].y; }
+#pragma unroll
+        for (int a = 0; a < P1; ++a)
+#pragma unroll
+          for (int b = 0; b < P2; ++b) { ga[a][b][2 * h] = gap[a][b][h].x; ga[a][b][2 * h + 1] = gap[a][b][h].y; }
+      }
+    }
+    if constexpr (canon) {
 #pragma unroll
       for (int b = 0; b < P2; ++b)
 #pragma unroll
@@ -803,28 +856,57 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
 #pragma unroll
         for (int b = 0; b < P2; ++b) ga[a][b][q] = 0.f;
     }
+    {
+      // dot products on packed pairs (FFMA2): pair h = this lane's column points 2h, 2h + 1
+      constexpr int NH = VPL / 2;
+      float2 r2p[NH], alp[P1 > 0 ? P1 : 1][NH], bep[P2 > 0 ? P2 : 1][NH], gap[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][NH];
 #pragma unroll
-    for (int c = 0; c < DP; ++c) {
-      float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
-      ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
+      for (int h = 0; h < NH; ++h) {
+        r2p[h] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
-      const float xi = rbase[c];
-      float ui[P1 > 0 ? P1 : 1];
+        for (int a = 0; a < P1; ++a) alp[a][h] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int a = 0; a < P1; ++a) ui[a] = rbase[(1 + a) * DP + c];
+        for (int b = 0; b < P2; ++b) bep[b][h] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < VPL; ++q) {
-        const float dl = xi - xj[q];
-        r2[q] = fmaf(dl, dl, r2[q]);
+        for (int a = 0; a < P1; ++a)
 #pragma unroll
-        for (int b = 0; b < P2; ++b) be[b][q] = fmaf(dl, wj[b][q], be[b][q]);
+          for (int b = 0; b < P2; ++b) gap[a][b][h] = make_float2(0.f, 0.f);
+      }
 #pragma unroll
-        for (int a = 0; a < P1; ++a) {
-          al[a][q] = fmaf(dl, ui[a], al[a][q]);
+      for (int c = 0; c < DP; ++c) {
+        float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
+        ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
 #pragma unroll
-          for (int b = 0; b < P2; ++b) ga[a][b][q] = fmaf(ui[a], wj[b][q], ga[a][b][q]);
+        for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
+        const float2 xi = f2bc(rbase[c]);
+        float2 ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) ui[a] = f2bc(rbase[(1 + a) * DP + c]);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float2 dl = f2sub(xi, make_float2(xj[2 * h], xj[2 * h + 1]));
+          r2p[h] = f2fma(dl, dl, r2p[h]);
+#pragma unroll
+          for (int b = 0; b < P2; ++b) bep[b][h] = f2fma(dl, make_float2(wj[b][2 * h], wj[b][2 * h + 1]), bep[b][h]);
+#pragma unroll
+          for (int a = 0; a < P1; ++a) {
+            alp[a][h] = f2fma(dl, ui[a], alp[a][h]);
+#pragma unroll
+            for (int b = 0; b < P2; ++b) gap[a][b][h] = f2fma(ui[a], make_float2(wj[b][2 * h], wj[b][2 * h + 1]), gap[a][b][h]);
+          }
         }
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {                      // unpack (register renaming only)
+        r2[2 * h] = r2p[h].x; r2[2 * h + 1] = r2p[h].y;
+#pragma unroll
+        for (int a = 0; a < P1; ++a) { al[a][2 * h] = alp[a][h].x; al[a][2 * h + 1] = alp[a][h].y; }
+#pragma unroll
+        for (int b = 0; b < P2; ++b) { be[b][2 * h] = bep[b][h].x; be[b][2 * h + 1] = bep[b][h].y; }
+#pragma unroll
+        for (int a = 0; a < P1; ++a)
+#pragma unroll
+          for (int b = 0; b < P2; ++b) { ga[a][b][2 * h] = gap[a][b][h].x; ga[a][b][2 * h + 1] = gap[a][b][h].y; }
       }
     }
     // ---- upstream blocks: row (gi, a) holds this lane's 4*Q2 consecutive floats
@@ -903,36 +985,54 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     float acc[NV];
 #pragma unroll
     for (int f = 0; f < NV; ++f) acc[f] = 0.f;
+    {
+      constexpr int NH = VPL / 2;
+      // the coefficients as packed pairs (register renaming), then FFMA2 over the coordinates; the two halves of an accumulator
+      // are added once per coordinate
+      float2 e0p[NH], eap[P1 > 0 ? P1 : 1][NH], ebp[P2 > 0 ? P2 : 1][NH], habp[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][NH];
 #pragma unroll
-    for (int c = 0; c < DP; ++c) {
-      float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
-      ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
+      for (int h = 0; h < NH; ++h) {
+        e0p[h] = make_float2(e0[2 * h], e0[2 * h + 1]);
 #pragma unroll
-      for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
-      const float xi = rbase[c];
-      float ui[P1 > 0 ? P1 : 1];
+        for (int a = 0; a < P1; ++a) eap[a][h] = make_float2(ea[a][2 * h], ea[a][2 * h + 1]);
 #pragma unroll
-      for (int a = 0; a < P1; ++a) ui[a] = rbase[(1 + a) * DP + c];
-      float gx = 0.f, gu[P1 > 0 ? P1 : 1];
+        for (int b = 0; b < P2; ++b) ebp[b][h] = make_float2(eb[b][2 * h], eb[b][2 * h + 1]);
 #pragma unroll
-      for (int a = 0; a < P1; ++a) gu[a] = 0.f;
+        for (int a = 0; a < P1; ++a)
 #pragma unroll
-      for (int q = 0; q < VPL; ++q) {
-        const float dl = xi - xj[q];
-        gx = fmaf(e0[q], dl, gx);
-#pragma unroll
-        for (int b = 0; b < P2; ++b) gx = fmaf(eb[b][q], wj[b][q], gx);
-#pragma unroll
-        for (int a = 0; a < P1; ++a) {
-          gx = fmaf(ea[a][q], ui[a], gx);
-          gu[a] = fmaf(ea[a][q], dl, gu[a]);
-#pragma unroll
-          for (int b = 0; b < P2; ++b) gu[a] = fmaf(hab[a][b][q], wj[b][q], gu[a]);
-        }
+          for (int b = 0; b < P2; ++b) habp[a][b][h] = make_float2(hab[a][b][2 * h], hab[a][b][2 * h + 1]);
       }
-      acc[c] = gx;
 #pragma unroll
-      for (int a = 0; a < P1; ++a) acc[(1 + a) * DP + c] = gu[a];
+      for (int c = 0; c < DP; ++c) {
+        float xj[VPL], wj[P2 > 0 ? P2 : 1][VPL];
+        ld_vpl<VPL>(cs + c * TJ + VPL * lane, xj);
+#pragma unroll
+        for (int b = 0; b < P2; ++b) ld_vpl<VPL>(cs + ((1 + b) * DP + c) * TJ + VPL * lane, wj[b]);
+        const float2 xi = f2bc(rbase[c]);
+        float2 ui[P1 > 0 ? P1 : 1];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) ui[a] = f2bc(rbase[(1 + a) * DP + c]);
+        float2 gx = make_float2(0.f, 0.f), gu[P1 > 0 ? P1 : 1];
+#pragma unroll
+        for (int a = 0; a < P1; ++a) gu[a] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float2 dl = f2sub(xi, make_float2(xj[2 * h], xj[2 * h + 1]));
+          gx = f2fma(e0p[h], dl, gx);
+#pragma unroll
+          for (int b = 0; b < P2; ++b) gx = f2fma(ebp[b][h], make_float2(wj[b][2 * h], wj[b][2 * h + 1]), gx);
+#pragma unroll
+          for (int a = 0; a < P1; ++a) {
+            gx = f2fma(eap[a][h], ui[a], gx);
+            gu[a] = f2fma(eap[a][h], dl, gu[a]);
+#pragma unroll
+            for (int b = 0; b < P2; ++b) gu[a] = f2fma(habp[a][b][h], make_float2(wj[b][2 * h], wj[b][2 * h + 1]), gu[a]);
+          }
+        }
+        acc[c] = gx.x + gx.y;
+#pragma unroll
+        for (int a = 0; a < P1; ++a) acc[(1 + a) * DP + c] = gu[a].x + gu[a].y;
+      }
     }
     // ---- sum over the 32 lanes, one partial row per (column tile, row point)
     float* prow = part + ((int64_t)blockIdx.x * n1 * Q1 + (int64_t)gi * Q1) * d;
