@@ -76,15 +76,22 @@ def call(name, *args):
     """Call an int-returning entry point on torch's current stream; raise on a negative status.
     Returns the (non-negative) status: a few entry points use 1 to report an optional extra output."""
     # per-device state (streams, function attributes, work lists) follows the CURRENT device: refuse tensors that live elsewhere
-    # instead of launching on the wrong device / stream (one process per GPU is the supported layout)
-    cur = None
+    # instead of launching on the wrong device / stream (one process per GPU is the supported layout).  One pass over the
+    # arguments: this runs ~200 times per training step.
+    conv, dev = [], None
     for a in args:
-        if isinstance(a, torch.Tensor) and a.is_cuda:
-            cur = torch.cuda.current_device() if cur is None else cur
-            if a.device.index != cur:
-                raise DsvgpError(f"{name}: tensor on cuda:{a.device.index} but the current device is cuda:{cur} "
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise DsvgpError("dsvgp_b200 kernels take CUDA tensors only (there is no CPU path)")
+            if dev is None:
+                dev = torch.cuda.current_device()
+            if a.device.index != dev:
+                raise DsvgpError(f"{name}: tensor on cuda:{a.device.index} but the current device is cuda:{dev} "
                                  "(use torch.cuda.set_device / torch.cuda.device(...) around the call)")
-    rc = getattr(_lib, name)(*[_arg(a) for a in args], stream())
+            conv.append(ctypes.c_void_p(a.data_ptr()))
+        else:
+            conv.append(a)
+    rc = getattr(_lib, name)(*conv, stream())
     if rc < 0:
         raise DsvgpError(f"{name} failed: {ERRORS.get(rc, rc)}")
     return rc

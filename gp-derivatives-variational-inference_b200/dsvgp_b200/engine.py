@@ -384,9 +384,11 @@ class Engine:
                 # and persistent CTAs hold every SM for its whole 0.1 ms -- the next diagonal block of the factorisation, a 4-CTA
                 # cluster, then waits for it: seen as a 45 us + 70 us hole in the chain in the profiler trace)
                 ops.set_tc_persistent(False)
-                ops.gemm_tc(ws.E, ws.E_lo, ws.E, ws.E_lo, ws.P, Mq, Mq, Mq, b_kmajor=True, a_tri=TRI_LOWER, c_lower=True,
-                            chunk=TC_CHUNK)                                                   # lower tiles of E E^T
-                ops.set_tc_persistent(True)
+                try:
+                    ops.gemm_tc(ws.E, ws.E_lo, ws.E, ws.E_lo, ws.P, Mq, Mq, Mq, b_kmajor=True, a_tri=TRI_LOWER, c_lower=True,
+                                chunk=TC_CHUNK)                                               # lower tiles of E E^T
+                finally:
+                    ops.set_tc_persistent(True)
                 # the scale of D from its MEASURED maximum (the a-priori bound is loose by ~M' max|E| for a trained q(u))
                 ops.build_d_absmax(ws.E, ws.P, f.maxbits[4:5], Mq)
                 ops.tc_scales(f.hyp, f.jitter, f.maxbits, Mq, f.scales, 2)
@@ -513,9 +515,11 @@ class Engine:
                 under_reduce = reducer is not None and getattr(reducer, "overlap", False) and not PERSISTENT_UNDER_REDUCE
                 if under_reduce:
                     ops.set_tc_persistent(False)
-                ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
-                if under_reduce:
-                    ops.set_tc_persistent(True)
+                try:
+                    ops.gemm_tch((f.WTh, f.WTl), (ws.Kh, ws.Kl), dKzx, Mq, nq, Mq, sc[11:12], a_tri=TRI_UPPER, chunk=TCH_CHUNK)   # dK_zx = L^-T dA
+                finally:
+                    if under_reduce:
+                        ops.set_tc_persistent(True)
             ops.kdir_bwd(P.Z, f.uzT, f.invzT, ws.p, x, wx, ws.p2, f.hyp, dKzx, ws.gZ, ws.gVz, ws.sc[4:6])
             # (E, E^T as fp32 + lo for the two M'^3 products of the tail were made by _assemble)
         else:

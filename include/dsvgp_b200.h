@@ -205,7 +205,10 @@ int dsvgp_set_tc_cta_group(int cg);
  * phases (set-up, pipeline fill, store of its tile) run under the other pair's main loop.  Returns the value in force. */
 int dsvgp_set_tc_tile_n(int n);
 /* CTA-pair tensor-core products: 1 (default) = persistent CTA pairs (one per SM pair) walking a host-balanced list of
- * (256 x 256 tile, split-K slice) work items; 0 = one CTA pair per tile.  Returns the value in force. */
+ * (256 x 256 tile, split-K slice) work items; 0 = one CTA pair per tile.  Returns the value in force.
+ * The FIRST product of a given shape / triangle mode / split on a device builds its work list: one cudaMalloc and one
+ * synchronous copy of a few KB (the only host synchronisation of these entry points; never during stream capture -- a
+ * capturing call whose list does not exist yet takes the per-tile kernel). */
 int dsvgp_set_tc_persistent(int on);
 /* Profiling aid of the persistent products: with buf != NULL (device memory, 8 * cap_items int64) the MMA warp and the first
  * epilogue warp of every pair leader stamp the SM clock for each work item with list index < cap_items: buf[8 i + 0..6] = MMA warp
