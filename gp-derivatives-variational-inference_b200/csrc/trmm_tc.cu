@@ -23,6 +23,9 @@
 //               register master sums, release the TMEM buffer; at the end apply alpha/beta and store.
 // Triangular structure of A is exploited by trimming the k-range of each row tile; `c_lower` skips tiles above the
 // diagonal (Gram matrix).
+// Kernels: gemm_tc*_kernel (one CTA per tile), gemm_tc*2_kernel (a CTA PAIR per 256 x 256 tile, tcgen05 cta_group::2) and -- the
+// default -- gemm_tc*2p_kernel: PERSISTENT CTA pairs walking a host-built work list (section "Persistent CTA-pair variant" below:
+// set-up once per SM, operand ring kept full across tiles, setmaxnreg, stream-K for split-K products, per-item clock trace).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
