@@ -290,6 +290,15 @@ class Engine:
         wait: event after which f.scales is valid (elbo_step computes the scales on its side stream)."""
         if prep:
             Engine._prep(f, P, T)
+        Engine._factorise_enqueue(f, P, extra_jitter)
+        if f.tch and prep:
+            Engine._scales0(f, P)
+        Engine._factorise_finish(f, T, wait)
+
+    @staticmethod
+    def _factorise_enqueue(f, P, extra_jitter):
+        """K_zz assembly + the whole factorisation / inverse chain + the status copy: the critical path of a step, and all it
+        needs are hyp and the fp64 inducing directions."""
         if f.Mp > f.Mq:
             ops.pad_identity(f.Kzz, f.Mq)
         ops.kdir_fwd(P.Z, f.uz64, f.p, P.Z, f.uz64, f.p, f.hyp, f.Kzz, diag_add=KZZ_JITTER + extra_jitter)
@@ -298,9 +307,11 @@ class Engine:
             f.info_host.copy_(f.info, non_blocking=True)      #  after the replay: graphs.GraphedStep)
             f.info_event.record()
         f.jitter = KZZ_JITTER + extra_jitter
+
+    @staticmethod
+    def _factorise_finish(f, T, wait=None):
+        """W in the forms the products read (after the operand scales exist: `wait`)."""
         if f.tch:
-            if prep:
-                Engine._scales0(f, P)
             if wait is not None:
                 torch.cuda.current_stream(f.W.device).wait_event(wait)
             ops.split_half(f.W, f.scales[0:1], f.Wh, f.Wl, mode=1, hiT=f.WTh, loT=f.WTl, rows=f.Mq, cols=f.Mq)
@@ -670,38 +681,48 @@ class Engine:
         f = self.factor(dev, T, d, M, p)
         f.valid = False
         nq_global = (n_global if n_global is not None else n) * (p2 + 1)
-        wx = self._data_dirs(ws, Vx, T)
-        self._prep(f, P, T)
-        # K_zx assembly and the L_s operands do not depend on the factor: they run on a side stream underneath the
-        # latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle).  The host has just come out of the
-        # previous step's status read, so the GPU is waiting for launches: the factorisation (the critical path) is
-        # enqueued first, the side-stream work -- forked at an event recorded BEFORE it -- second.
+        # Host order.  The factorisation is the critical path of a step and, when the caller reads the loss back every step, the
+        # GPU is idle until its first diagonal block is launched: everything that block does not need (data-side directions,
+        # fp32 inducing directions, operand scales -- 0.2 ms of host time, scratch/host_latency.py) is enqueued AFTER the chain,
+        # on the side stream, where the K_zx assembly and the L_s operands (which do not depend on the factor either) run
+        # underneath the latency-bound Cholesky (32 sequential diagonal blocks leave most SMs idle).
+        self._hyp(f, P)
+        if f.p:
+            f.uz64, f.invz64 = ops.normalize_dirs(P.Vz, F64)
         cur, side = torch.cuda.current_stream(dev), self._side_stream(dev)
         capturing = torch.cuda.is_current_stream_capturing()
         fork = torch.cuda.Event() if capturing else self._fork_event(dev)
         fork.record(cur)
+        wx = None
         for extra in (0.0,) + CHOL_RETRY:
-            scales_ready = None
-            if f.tch and extra != 0.0:
-                self._scales0(f, P, KZZ_JITTER + extra)
-            elif f.tch:
-                # the operand scales (a 30 us pass over L_s) are first needed by the split of W AFTER the factorisation and by the
-                # side-stream assembly: they go to the side stream too instead of in front of the K_zz assembly
+            if extra == 0.0:
+                self._factorise_enqueue(f, P, 0.0)
+                scales_ready = None
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
-                    self._scales0(f, P, KZZ_JITTER)
-                    scales_ready = torch.cuda.Event() if capturing else self._scales_event(dev)
-                    scales_ready.record(side)
-            self._factorise(f, P, T, extra, prep=False, wait=scales_ready)
-            if extra == 0.0:
-                if not f.tch:
-                    side.wait_event(fork)
+                    if f.p:
+                        f.uzT, f.invzT = (f.uz64, f.invz64) if T == F64 else ops.normalize_dirs(P.Vz, T)
+                    wx = self._data_dirs(ws, Vx, T)
+                    # (allocated while the side stream is current, read by kernels of the caller's stream later in the step:
+                    #  tell the caching allocator, so that a freed block is not handed out again before those have run)
+                    for t_ in (wx, *((f.uzT, f.invzT) if (f.p and T != F64) else ()), *(ws.canon or ())):
+                        if t_ is not None:
+                            t_.record_stream(cur)
+                    if f.tch:
+                        self._scales0(f, P, KZZ_JITTER)
+                        scales_ready = torch.cuda.Event() if capturing else self._scales_event(dev)
+                        scales_ready.record(side)
+                self._factorise_finish(f, T, scales_ready)
                 with torch.cuda.stream(side):
                     self._assemble(ws, f, P, x, wx)
                     ws.kl.zero_()                      # KL(q(u) || p(u)) needs the parameters only: also under the Cholesky
                     if include_kl:
                         ops.kl_divergence(P.m, P.Ls_raw, ws.kl, ws.scratch_kl)
                 cur.wait_stream(side)
+            else:
+                if f.tch:
+                    self._scales0(f, P, KZZ_JITTER + extra)
+                self._factorise(f, P, T, extra, prep=False)
             self._forward(ws, f, P, x, wx, through_likelihood, need_C=True, assembled=(extra == 0.0))
             ws.small.zero_()
             if objective == "pll":
