@@ -68,7 +68,19 @@ def _arg(a):
     return a
 
 
+# torch.cuda.current_stream() costs ~14 us of Python per call (device-index resolution, availability checks) and a step makes ~50
+# calls: the raw accessors torch itself uses underneath are two C calls.
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_GET_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _current_device():
+    return _GET_DEVICE() if _GET_DEVICE is not None else torch.cuda.current_device()
+
+
 def stream():
+    if _RAW_STREAM is not None and _GET_DEVICE is not None:
+        return ctypes.c_void_p(_RAW_STREAM(_GET_DEVICE()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -84,7 +96,7 @@ def call(name, *args):
             if not a.is_cuda:
                 raise DsvgpError("dsvgp_b200 kernels take CUDA tensors only (there is no CPU path)")
             if dev is None:
-                dev = torch.cuda.current_device()
+                dev = _current_device()
             if a.device.index != dev:
                 raise DsvgpError(f"{name}: tensor on cuda:{a.device.index} but the current device is cuda:{dev} "
                                  "(use torch.cuda.set_device / torch.cuda.device(...) around the call)")
