@@ -131,6 +131,7 @@ int dsvgp_gemm_tc_f32(const float* Ah, const float* Al, int64_t lda, const float
   return gemm_tc(Ah, Al, lda, Bh, Bl, ldb, b_kmajor, M, N, K, (float)alpha, (float)beta, C, ldc, D, ldd, C2, ldc2, D2, ldd2, a_tri, c_lower, chunk, Clo, C2lo, nsplit, split_ws, ST(s));
 }
 int dsvgp_set_tc_tile_n(int n) { set_tc_tile_n(n); return get_tc_tile_n(); }
+int dsvgp_set_tc_max_pairs(int n) { set_tc_max_pairs(n); return get_tc_max_pairs(); }
 int dsvgp_set_tc_persistent(int on) { set_tc_persistent(on); return get_tc_persistent(); }
 int dsvgp_set_tc_trace(void* buf, int cap_items) { set_tc_trace(static_cast<long long*>(buf), cap_items); return DSVGP_OK; }
 int dsvgp_tc_work_list(int M, int N, int K, int a_tri, int c_lower, int nsplit, int pairs, int bke, int* out, int cap) {

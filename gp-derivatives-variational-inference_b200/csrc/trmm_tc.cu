@@ -1113,6 +1113,9 @@ static bool map_mnmajor_h(CUtensorMap* m, const __half* base, int64_t ld, int K,
 static long long* g_tc_trace = nullptr;
 static int g_tc_trace_cap = 0;
 void set_tc_trace(long long* buf, int cap_items) { g_tc_trace = buf; g_tc_trace_cap = buf ? cap_items : 0; }
+static int g_tc_max_pairs = 0;     // 0: every CTA pair the device can hold; > 0: at most that many (a product that shares the GPU)
+void set_tc_max_pairs(int n) { g_tc_max_pairs = n > 0 ? n : 0; }
+int get_tc_max_pairs() { return g_tc_max_pairs; }
 static int g_tc_persistent = 1;
 void set_tc_persistent(int on) { g_tc_persistent = on ? 1 : 0; }
 int get_tc_persistent() { return g_tc_persistent; }
@@ -1342,7 +1345,8 @@ int gemm_tc(const float* Ah, const float* Al, int64_t lda, const float* Bh, cons
         if (cudaFuncSetAttribute(tc::gemm_tc2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::P_SMEM_BYTES) != cudaSuccess) return nz;
         attr_set_p[dev & 63] = true;
       }
-      const int P = tc::resident_pairs(tc::gemm_tc2p_kernel, dev);
+      int P = tc::resident_pairs(tc::gemm_tc2p_kernel, dev);
+      if (g_tc_max_pairs > 0) P = std::min(P, g_tc_max_pairs);
       const int* offs; const int4* items; int nz_eff = nz;
       if (tc::get_sched(tc::SchedKey{dev, M, N, K, a_tri, c_lower, nz, P, tc::BK}, st, &offs, &items, &nz_eff)) {
         pp.nz = nz; pp.trace = g_tc_trace; pp.trace_cap = g_tc_trace_cap;
@@ -1424,7 +1428,8 @@ int gemm_tch(const void* Ah_, const void* Al_, int64_t lda, const void* Bh_, con
         if (cudaFuncSetAttribute(tc::gemm_tch2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::P_SMEM_BYTES) != cudaSuccess) return nz;
         attr_set_p[dev & 63] = true;
       }
-      const int P = tc::resident_pairs(tc::gemm_tch2p_kernel, dev);
+      int P = tc::resident_pairs(tc::gemm_tch2p_kernel, dev);
+      if (g_tc_max_pairs > 0) P = std::min(P, g_tc_max_pairs);
       const int* offs; const int4* items; int nz_eff = nz;
       if (tc::get_sched(tc::SchedKey{dev, M, N, K, a_tri, c_lower, nz, P, tc::BKH}, st, &offs, &items, &nz_eff)) {
         pp.nz = nz; pp.trace = g_tc_trace; pp.trace_cap = g_tc_trace_cap;

@@ -42,6 +42,9 @@ void set_tc_tile_n(int n);
 int get_tc_tile_n();
 // CTA-pair kernels: 1 (default) = persistent pairs walking a host-balanced work list (set-up once per SM, operand ring kept
 // full across tiles, the next tile's first chunks under the previous tile's store phase); 0 = one CTA pair per tile
+// persistent kernels: at most n CTA pairs (0 = all the device holds) -- for a product that is to share the GPU with other work
+void set_tc_max_pairs(int n);
+int get_tc_max_pairs();
 void set_tc_persistent(int on);
 // profiling aid of the persistent kernels: when buf != null, the MMA warp and the first epilogue warp of every pair leader write
 // SM clock stamps for each of their first cap_items work items: buf[8 * item + {0: MMA warp reaches the item, 1: first k-block

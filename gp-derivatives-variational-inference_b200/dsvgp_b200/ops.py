@@ -161,6 +161,11 @@ def set_tc_tile_n(n):
     return call_raw("dsvgp_set_tc_tile_n", int(n))
 
 
+def set_tc_max_pairs(n):
+    """Persistent tensor-core products on at most n CTA pairs (0 = all)."""
+    return call_raw("dsvgp_set_tc_max_pairs", int(n))
+
+
 def set_tc_persistent(on):
     """CTA-pair tensor-core products as persistent pairs over a balanced work list (default) or one pair per tile."""
     return call_raw("dsvgp_set_tc_persistent", int(bool(on)))

@@ -210,6 +210,9 @@ int dsvgp_set_tc_tile_n(int n);
  * synchronous copy of a few KB (the only host synchronisation of these entry points; never during stream capture -- a
  * capturing call whose list does not exist yet takes the per-tile kernel). */
 int dsvgp_set_tc_persistent(int on);
+/* Persistent products: use at most n CTA pairs (0 = every pair the device can hold, the default), leaving the other SMs to
+ * whatever runs beside the product.  Returns the value in force. */
+int dsvgp_set_tc_max_pairs(int n);
 /* Profiling aid of the persistent products: with buf != NULL (device memory, 8 * cap_items int64) the MMA warp and the first
  * epilogue warp of every pair leader stamp the SM clock for each work item with list index < cap_items: buf[8 i + 0..6] = MMA warp
  * reaches item i, its first k-block issued, its last k-block issued, epilogue reaches the item, first chunk complete, last
