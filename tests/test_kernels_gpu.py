@@ -256,6 +256,86 @@ def test_cholesky_and_inverse(ops, Mq):
     assert rel(W[:Mq, :Mq].tril().cpu() @ Lr, torch.eye(Mq, dtype=F64)) < 1e-10
 
 
+@pytest.mark.parametrize("knob", ["priority", "lookahead", "rank_update", "priority+lookahead+rank_update"])
+def test_cholesky_scheduling_knobs_keep_the_result(ops, knob):
+    """The experimental schedules of the factorisation (high-priority streams, lookahead-2 split of the trailing update, rank-K
+    update kernel; all off by default) give the same factor and inverse."""
+    Mq = 3072
+    g = torch.Generator().manual_seed(11)
+    R = torch.randn(Mq, Mq + 5, generator=g, dtype=F64)
+    A = (R @ R.T / (Mq + 5) + 1e-3 * torch.eye(Mq, dtype=F64)).cuda()
+    Mp, nb0, nlev = ops.chol_plan(Mq)
+
+    def run():
+        Aw = A.clone()
+        L, W = (torch.full((Mp, Mp), float("nan"), dtype=F64, device="cuda") for _ in range(2))
+        info = torch.ones(1, dtype=torch.int32, device="cuda")
+        ops.cholesky_inverse(Aw, L, W, nb0, nlev, info)
+        assert int(info.item()) == 0
+        return L.tril(), W.tril()
+    L0, W0 = run()
+    try:
+        if "priority" in knob:
+            ops.set_chol_priority(1)
+        if "lookahead" in knob:
+            ops.set_chol_lookahead(1)
+        if "rank_update" in knob:
+            ops.set_rank_update(1)
+        L1, W1 = run()
+    finally:
+        ops.set_chol_priority(0), ops.set_chol_lookahead(0), ops.set_rank_update(0)
+    assert rel(L1, L0) < 1e-12 and rel(W1, W0) < 1e-10
+    assert rel(W0 @ L0, torch.eye(Mp, dtype=F64)) < 1e-9
+
+
+def test_limited_pairs_and_trace_do_not_change_the_product(ops):
+    """dsvgp_set_tc_max_pairs (a persistent product on part of the GPU) and dsvgp_set_tc_trace (per-item clock stamps) are
+    scheduling / profiling aids: the product is bit-identical, and every traced item carries increasing stamps."""
+    from dsvgp_b200 import _lib
+    F16 = torch.float16
+    M, N, K = 768, 4096, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, device="cuda", dtype=F64, generator=g).tril()
+    B = torch.randn(K, N, device="cuda", dtype=F64, generator=g)
+    Ah, Al = _split_ref(A, 2.0 ** 11)
+    Bh, Bl = _split_ref(B, 2.0 ** 12)
+    inv = torch.tensor([2.0 ** -23], device="cuda", dtype=F32)
+
+    def run():
+        C = torch.full((M, N), float("nan"), device="cuda", dtype=F32)
+        ops.gemm_tch((Ah, Al), (Bh, Bl), C, M, N, K, inv, a_tri=1)
+        return C
+    C0 = run()
+    nitems = 3 * 16
+    tr = torch.zeros(8 * nitems, dtype=torch.int64, device="cuda")
+    try:
+        ops.set_tc_max_pairs(5)
+        _lib.call_raw("dsvgp_set_tc_trace", tr, nitems)
+        C1 = run()
+    finally:
+        ops.set_tc_max_pairs(0)
+        _lib.call_raw("dsvgp_set_tc_trace", None, 0)
+    assert torch.equal(C0, C1)
+    t = tr.view(nitems, 8).cpu()
+    assert bool((t[:, 0] > 0).all()) and bool((t[:, 1] >= t[:, 0]).all()) and bool((t[:, 2] >= t[:, 1]).all())
+    assert bool((t[:, 4] >= t[:, 3]).all()) and bool((t[:, 5] >= t[:, 4]).all()) and bool((t[:, 6] > t[:, 5]).all())
+
+
+def test_collect_grads_kernel(ops):
+    """The end-of-step gather of every small gradient: layout, dtype cast and softplus chain rule."""
+    nZ, nV = 70, 140
+    g = torch.Generator().manual_seed(2)
+    small = torch.randn(8 + nZ + nV, generator=g, dtype=F64).cuda()
+    hyp = torch.rand(8, generator=g, dtype=F64).cuda()
+    for dtype in (F32, F64):
+        for mode in (0, 1):
+            out = torch.full((nZ + nV + 4,), float("nan"), dtype=dtype, device="cuda")
+            ops.collect_grads(small, nZ, nV, hyp, mode, out)
+            want = torch.cat([small[8:], small[7:8], small[5:6] * hyp[5], small[4:5] * hyp[4],
+                              ((small[1:2] if mode else 0.0) + small[6:7]) * hyp[6]])
+            assert rel(out, want) < (1e-15 if dtype == F64 else 1e-7)
+
+
 def test_cholesky_reports_non_positive_pivot(ops):
     A = torch.eye(8, dtype=F64)
     A[5, 5] = -1.0
