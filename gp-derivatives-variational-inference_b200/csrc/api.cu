@@ -26,7 +26,7 @@ int dsvgp_set_kdir_bwd_vpl(int vpl) {
 }
 int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores) {
   const int old = dsvgp::g_fwd_tib * 4 + dsvgp::g_fwd_stream_stores;
-  if (tib >= 8 && tib <= 64 && tib % 8 == 0) dsvgp::g_fwd_tib = tib;
+  if (tib == 0 || (tib >= 8 && tib <= 64 && tib % 8 == 0)) dsvgp::g_fwd_tib = tib;      /* 0 = adaptive (default) */
   if (stream_stores >= 0 && stream_stores <= 2) dsvgp::g_fwd_stream_stores = stream_stores;
   return old;
 }

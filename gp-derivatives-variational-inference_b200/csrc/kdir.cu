@@ -223,7 +223,8 @@ constexpr int V4_TJ = 128, V4_TIB = 64;
 
 int g_bwd_vpl = 4;             // column points per lane of kdir_bwd_v4: 4, or 2 = two CTAs per SM (benchmarking knob; measured equal:
                                // 0.50 / 0.54 ms at C3 -- the kernel is bound by shared-memory reads + FMA issue, not by latency)
-int g_fwd_tib = V4_TIB;        // row points per CTA of kdir_fwd_v4 (benchmarking knob, multiple of 8, <= V4_TIB)
+int g_fwd_tib = 0;             // row points per CTA of kdir_fwd_v4: 0 (default) = 64, or 32 when that leaves fewer than 1024 CTAs (small
+                               // minibatches: C4 n = 2048 130 -> 107 us, n = 512 69 -> 40 us; scratch/tib_sweep.py); else a fixed multiple of 8 <= 64
 int g_fwd_stream_stores = 2;   // 1: st.global.cs (evict-first) for the K / K_lo rows; 2 (default): when the output is
                                // larger than half of the 126 MB L2 (measured on C3: K only 0.144 -> 0.136 ms, K + lo 0.209 -> 0.195 ms)
 
@@ -1266,7 +1267,8 @@ static int launch_fwd_v4(const float* x1, const float* u1, int n1, const float* 
                          const int* canon_flag, int n2, int d, const double* hyp, int use_os, double diag_add, float* K,
                          int64_t ldk, float* Klo, cudaStream_t st, __half* Kh = nullptr, __half* Kl = nullptr,
                          int64_t ldkh = 0, const float* hscale = nullptr) {
-  const int tib = g_fwd_tib;
+  int tib = g_fwd_tib;
+  if (tib <= 0) tib = ((int64_t)ceil_div(n2, V4_TJ) * ceil_div(n1, V4_TIB) < 1024) ? V4_TIB / 2 : V4_TIB;
   const int64_t out_bytes = (int64_t)n1 * (P1 + 1) * n2 * (P2 + 1) * 4 * (Klo ? 2 : 1);
   const int stream_stores = g_fwd_stream_stores == 2 ? (out_bytes > (int64_t)(64 << 20)) : g_fwd_stream_stores;
   const size_t smem = fwd_v4_smem_bytes<P1, P2>((d + 3) & ~3, tib);

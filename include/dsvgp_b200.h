@@ -45,7 +45,8 @@ int dsvgp_version(void);
 int dsvgp_built_for_sm(void);
 /* number of CUDA kernels this library has launched in this process (host-side counter) */
 int64_t dsvgp_launch_count(void);
-/* benchmarking knobs of the fp32 assembly kernel: row points per CTA (8..64, multiple of 8; default 64) and
+/* benchmarking knobs of the fp32 assembly kernel: row points per CTA (0 = adaptive, the default: 64, or 32 when that leaves
+ * fewer than 1024 CTAs -- small minibatches; or a fixed 8..64, multiple of 8) and
  * evict-first (st.global.cs) stores of the covariance rows (0 off, 1 on, 2 = when the output exceeds 64 MB, the
  * default).  Negative = leave unchanged.  Returns tib*4 + stream_stores as set before the call. */
 int dsvgp_set_kdir_fwd_knobs(int tib, int stream_stores);

@@ -82,7 +82,7 @@ if dtype == torch.float32 and p2:
             else:
                 res[f"asm_klo_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx, canon=ws.canon, out_lo=ws.lo1), 20)
             res[f"asm_gen_ms_tib{tib}_cs{ss}"] = timed(lambda: ops.kdir_fwd(Z, f.uzT, p, x, wx, p2, f.hyp, ws.Kzx), 20)
-    ops.set_kdir_fwd_knobs(64, 0)
+    ops.set_kdir_fwd_knobs(0, 2)
 res["asm_bytes"] = 4 * (Mq * nq + (M + n) * d + (M * p + n * p2) * d)
 print(json.dumps(res, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
