@@ -786,9 +786,25 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[NV], int lane) {
 // VPL = column points per lane: 4 (a warp spans 128 column points; ~250 registers, one CTA per SM) or 2 (64 column points per
 // warp and per CTA tile; half the per-lane arrays, two CTAs = 16 warps per SM -- the kernel is issue-bound on dependent FMA
 // chains, ncu: 49 % issue-active with 2 warps per scheduler, so the extra warps are what it needs).
+// (+ the staged upstream rows: per warp, two buffers of (P1+1) row segments of 32*VPL*(P2+1) floats -- see the kernel)
 template <int P1, int P2, int DP, int VPL>
 size_t bwd_v4_smem_bytes() {
-  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * DP + (P2 + 1) * DP * 32 * VPL) + 64 * sizeof(double);
+  return sizeof(float) * (size_t)(V4_TIB * (P1 + 1) * DP + (P2 + 1) * DP * 32 * VPL + 8 * 2 * (P1 + 1) * 32 * VPL * (P2 + 1)) +
+         64 * sizeof(double);
+}
+
+// 16- / 8-byte asynchronous global -> shared copies (the upstream block of the NEXT row point is fetched while this one is processed)
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool pred) {   // pred false: writes 0, reads nothing
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_g2s(float* smem_dst, const float* gsrc) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gsrc) : "memory");
 }
 
 template <int VPL> __device__ __forceinline__ void ld_vpl(const float* p, float (&o)[VPL]) {
@@ -813,35 +829,64 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
   float* cs = rs + TIB * Q1 * DP;                          // [Q2][DP][TJ]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = blockIdx.y * TIB, j0 = blockIdx.x * TJ;
+  float* gsw = cs + Q2 * DP * TJ + warp * (2 * Q1 * TJ * Q2);   // this warp's [2][Q1][TJ * Q2] staged upstream rows
 
+  // Both tiles arrive through 4-byte cp.async with zero fill: with one CTA per SM nothing hides this prologue, and as a loop
+  // of dependent global loads (8 + 15 round trips per thread) it was a quarter of the CTA's life (ncu source page).  Now every
+  // element is in flight at once, together with the first row point's upstream rows.
   for (int e = tid; e < TIB * Q1 * DP; e += 256) {
     const int cc = e % DP, ia = e / DP, i = ia / Q1, a = ia % Q1;
-    float v = 0.f;
-    if (i0 + i < n1 && cc < d)
-      v = (a == 0) ? x1[(int64_t)(i0 + i) * d + cc] : u1[(int64_t)((i0 + i) * P1 + a - 1) * d + cc];
-    rs[e] = v;
+    const bool ok = i0 + i < n1 && cc < d;
+    const float* src = !ok ? x1 : (a == 0) ? x1 + (int64_t)(i0 + i) * d + cc : u1 + (int64_t)((i0 + i) * P1 + a - 1) * d + cc;
+    cp_async4_zfill(rs + e, src, ok);
   }
   {
     const int j = tid & (TJ - 1);
     for (int row = tid / TJ; row < Q2 * DP; row += 256 / TJ) {
       const int b = row / DP, cc = row % DP;
-      float v = 0.f;
-      if (j0 + j < n2 && cc < d)
-        v = (b == 0) ? x2[(int64_t)(j0 + j) * d + cc] : w2[(int64_t)((j0 + j) * P2 + b - 1) * d + cc];
-      cs[row * TJ + j] = v;
+      const bool ok = j0 + j < n2 && cc < d;
+      const float* src = !ok ? x2 : (b == 0) ? x2 + (int64_t)(j0 + j) * d + cc : w2 + (int64_t)((j0 + j) * P2 + b - 1) * d + cc;
+      cp_async4_zfill(cs + row * TJ + j, src, ok);
     }
   }
-  __syncthreads();
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
 
   const float ell = (float)hyp[0], os = use_os ? (float)hyp[1] : 1.f;
   const float il2 = 1.f / (ell * ell), iell = 1.f / ell;
   const bool vec_ok = ((lddk & 3) == 0) && ((reinterpret_cast<uintptr_t>(dK) & 15) == 0);
   const int cols = min(TJ * Q2, (n2 - j0) * Q2);
   double s_ell = 0.0, s_os = 0.0;
+  // The upstream rows of a row point are the only large read of the kernel and both warps of a scheduler used to wait for them at
+  // the same place of the iteration (ncu: long-scoreboard was the top stall).  For whole, aligned column tiles every lane now
+  // fetches ITS OWN segments of the next row point with cp.async while the current one is processed (no cross-lane hand-over:
+  // cp.async.wait_group is all the synchronisation there is); ragged / unaligned tiles keep the direct loads.
+  constexpr int VWS = VPL == 4 ? 4 : 2, NPIECES = VPL * Q2 / VWS;
+  const bool staged = vec_ok && cols == TJ * Q2;           // CTA-uniform
+  auto prefetch = [&](int itn) {
+    const int gin = i0 + itn * 8 + warp;
+    if (itn < TIB / 8 && gin < n1) {
+      float* dst = gsw + (itn & 1) * (Q1 * TJ * Q2) + lane * VPL * Q2;
+#pragma unroll
+      for (int a = 0; a < Q1; ++a) {
+        const float* grow = dK + (int64_t)(gin * Q1 + a) * lddk + (int64_t)j0 * Q2 + lane * VPL * Q2;
+#pragma unroll
+        for (int v = 0; v < NPIECES; ++v) cp_async_g2s<VWS * 4>(dst + a * (TJ * Q2) + VWS * v, grow + VWS * v);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");  // (possibly empty: the group count stays uniform)
+  };
+  if (staged) {
+    prefetch(0);
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // the tiles (the upstream rows may still be in flight)
+  } else {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  }
+  __syncthreads();
 
   for (int it = 0; it < TIB / 8; ++it) {
     const int il = it * 8 + warp, gi = i0 + il;
     if (gi >= n1) break;                                   // warp-uniform
+    if (staged) prefetch(it + 1);
     const float* rbase = rs + (il * Q1) * DP;
     // ---- recompute the 4 kernel blocks of this lane
     float r2[VPL], al[P1 > 0 ? P1 : 1][VPL], be[P2 > 0 ? P2 : 1][VPL], ga[P1 > 0 ? P1 : 1][P2 > 0 ? P2 : 1][VPL];
@@ -915,6 +960,22 @@ kdir_bwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
     constexpr int VW = VPL == 4 ? 4 : 2, NPIECE = VPL * Q2 / VW;
     static_assert((VPL * Q2) % VW == 0, "upstream segment must split into whole vector pieces");
     float g[Q1][VPL * Q2];
+    if (staged) {
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      const float* src = gsw + (it & 1) * (Q1 * TJ * Q2) + lane * VPL * Q2;
+#pragma unroll
+      for (int a = 0; a < Q1; ++a)
+#pragma unroll
+        for (int v = 0; v < NPIECE; ++v) {
+          if constexpr (VW == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(src + a * (TJ * Q2) + 4 * v);
+            g[a][4 * v] = t.x; g[a][4 * v + 1] = t.y; g[a][4 * v + 2] = t.z; g[a][4 * v + 3] = t.w;
+          } else {
+            const float2 t = *reinterpret_cast<const float2*>(src + a * (TJ * Q2) + 2 * v);
+            g[a][2 * v] = t.x; g[a][2 * v + 1] = t.y;
+          }
+        }
+    } else
 #pragma unroll
     for (int a = 0; a < Q1; ++a) {
       const float* grow = dK + (int64_t)(gi * Q1 + a) * lddk + (int64_t)j0 * Q2 + lane * VPL * Q2;
@@ -1401,7 +1462,9 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
       float* part = reinterpret_cast<float*>(ws);
       const size_t part_bytes = round_up64(sizeof(float) * (size_t)nt * n1 * (p1 + 1) * d, 16);
       double* part_sc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + part_bytes);
-      const int DPr = (d + 3) & ~3;
+      // coordinates padded to a multiple of 4, except for the shapes of the shipped workloads, which get an exact instantiation
+      // (d = 10: 10 instead of 12 coordinate steps in both FMA phases and one 30-value butterfly; d = 18: 18 instead of 20)
+      const int DPr = ((d == 10 && p1 == 2) || (d == 18 && p2 == 0)) ? d : (d + 3) & ~3;
       dim3 grid(nt, nrc);
       int launched = 0;
 #define BV4V(A, B, DPV, VPLV)                                                                                  \
@@ -1416,6 +1479,7 @@ int kdir_bwd(const T* x1, const TK* u1, const TK* inv1, int n1, int p1, const T*
 #define BV4_ALL(A, B) BV4(A, B, 4) BV4(A, B, 8) BV4(A, B, 12) BV4(A, B, 16)
       BV4_ALL(1, 1) BV4_ALL(2, 2) BV4_ALL(1, 0) BV4_ALL(2, 0)
       BV4(2, 0, 20) BV4(1, 0, 20)                            // d = 17..20 without data-side directions (uci_dfree-shaped, d = 18)
+      BV4(2, 2, 10) BV4(2, 0, 10) BV4(2, 0, 18) BV4(1, 0, 18)
 #undef BV4_ALL
 #undef BV4
 #undef BV4V

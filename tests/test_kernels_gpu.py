@@ -121,6 +121,24 @@ def test_kdir_jitter_and_symmetry(ops):
     (19, 23, 5, 3, 0), (16, 16, 7, 0, 0), (9, 11, 3, 4, 4), (5, 7, 4, 2, 1), (70, 2100, 4, 2, 2),
     (100, 700, 10, 2, 2), (65, 513, 3, 1, 1), (33, 1111, 16, 2, 0), (9, 640, 7, 1, 0), (130, 900, 13, 2, 2)])
 def test_kdir_backward_matches_oracle_autograd(ops, dtype, k_dtype, n1, n2, d, p1, p2):
+    _check_kdir_backward(ops, dtype, k_dtype, n1, n2, d, p1, p2, n2 * (p2 + 1) + 3)
+
+
+@pytest.mark.parametrize("vpl", [4, 2])
+@pytest.mark.parametrize("n1,n2,d,p1,p2", [
+    (100, 1024, 10, 2, 2), (70, 1000, 10, 2, 2), (130, 640, 18, 2, 0), (65, 768, 3, 1, 1), (20, 1300, 18, 1, 0),
+    (40, 512, 10, 2, 0), (9, 896, 12, 2, 2)])
+def test_kdir_backward_staged_upstream_rows(ops, vpl, n1, n2, d, p1, p2):
+    """the layout the training step uses (16-byte aligned rows, leading dimension a multiple of 64): whole column tiles take the
+    cp.async-staged upstream rows, the ragged last tile the direct loads; exact-d instantiations (d = 10, 18) beside padded ones"""
+    ops.set_kdir_bwd_vpl(vpl)
+    try:
+        _check_kdir_backward(ops, F32, F32, n1, n2, d, p1, p2, (n2 * (p2 + 1) + 63) // 64 * 64, second=False)
+    finally:
+        ops.set_kdir_bwd_vpl(4)
+
+
+def _check_kdir_backward(ops, dtype, k_dtype, n1, n2, d, p1, p2, ld, second=True):
     x1, x2, v1, v2, raw_ell, raw_os = _kernel_inputs(n1, n2, d, p1, p2, dtype, 200 + n1 + d)
     g = torch.Generator().manual_seed(7)
     dK = torch.randn(n1 * (p1 + 1), n2 * (p2 + 1), generator=g, dtype=F64)
@@ -135,21 +153,22 @@ def test_kdir_backward_matches_oracle_autograd(ops, dtype, k_dtype, n1, n2, d, p
     hyp = ops.hyp_from_raw(raw_ell.reshape(-1).to(dev), raw_os.to(dev))
     u1, inv1 = ops.normalize_dirs(v1.to(dev), k_dtype) if p1 else (None, None)
     w2, inv2 = ops.normalize_dirs(v2.to(dev), k_dtype) if p2 else (None, None)
-    dKd = torch.zeros(n1 * (p1 + 1), n2 * (p2 + 1) + 3, dtype=k_dtype, device=dev)
+    dKd = torch.zeros(n1 * (p1 + 1), ld, dtype=k_dtype, device=dev)
     dKd[:, : n2 * (p2 + 1)] = dK.to(k_dtype)
     dKd = dKd[:, : n2 * (p2 + 1)]
     z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)
     gx1, gv1, gsc = z(n1, d), (z(n1 * p1, d) if p1 else None), z(2)
     ops.kdir_bwd(x1.to(dev), u1, inv1, p1, x2.to(dev), w2, p2, hyp, dKd, gx1, gv1, gsc)
-    gx2, gv2 = z(n2, d), (z(n2 * p2, d) if p2 else None)
-    ops.kdir_bwd(x2.to(dev), w2, inv2, p2, x1.to(dev), u1, p1, hyp, dKd, gx2, gv2, None, dk_trans=True)
     t = 1e-11 if (dtype == F64) else 2e-5
     assert rel(gx1, X1.grad) < t
-    assert rel(gx2, X2.grad) < t
     if p1:
         assert rel(gv1, V1.grad) < t
-    if p2:
-        assert rel(gv2, V2.grad) < t
+    if second:
+        gx2, gv2 = z(n2, d), (z(n2 * p2, d) if p2 else None)
+        ops.kdir_bwd(x2.to(dev), w2, inv2, p2, x1.to(dev), u1, p1, hyp, dKd, gx2, gv2, None, dk_trans=True)
+        assert rel(gx2, X2.grad) < t
+        if p2:
+            assert rel(gv2, V2.grad) < t
     assert abs(float(gsc[0]) - float(ell.grad)) < t * max(1.0, abs(float(ell.grad)))
     assert abs(float(gsc[1]) - float(osc.grad)) < t * max(1.0, abs(float(osc.grad)))
 
