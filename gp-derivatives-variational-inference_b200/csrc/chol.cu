@@ -874,10 +874,28 @@ static int g_chol_lookahead = 0;  // 1: trailing update split into the part the 
                                   // measured: no gain (C3 step 11.43 -> 11.46 ms, A/B in one process) -- off
 void set_chol_lookahead(int on) { g_chol_lookahead = on ? 1 : 0; }
 int get_chol_lookahead() { return g_chol_lookahead; }
+static int g_chol_mid_link = 20;  // chol_wait_mid(): the diagonal block whose completion releases work the caller deferred (see there); < 0: none
+void set_chol_mid_link(int k) { g_chol_mid_link = k; }
+int get_chol_mid_link() { return g_chol_mid_link; }
 static int g_chol_priority = 0;   // 1: the three chains of the factorisation on the library's high-priority streams; 0: diagonal chain on the caller's
                                   // stream (measured: no difference on any workload -- off)
 void set_chol_priority(int on) { g_chol_priority = on ? 1 : 0; }
 int get_chol_priority() { return g_chol_priority; }
+
+struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_inv, ev_entry, ev_done, ev_mid; bool ready = false, mid_valid = false; };
+static SideCtx g_side_ctxs[16];                         // one set of side streams + event pool per device
+
+// The first links of the chain are throughput-bound (their rank-nb0 trailing updates fill the GPU: potrf(k+2) waits for update(k)),
+// the later ones latency-bound (most SMs idle).  Work a caller overlaps with the factorisation on another stream therefore only
+// costs nothing when it runs beside the LATER links: chol_wait_mid makes stream s wait for diagonal block g_chol_mid_link of the
+// factorisation enqueued last on this device (no-op when that call had fewer blocks, or the knob is negative).
+int chol_wait_mid(cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideCtx& sc = g_side_ctxs[dev & 15];
+  if (sc.ready && sc.mid_valid) cudaStreamWaitEvent(s, sc.ev_mid, 0);
+  return DSVGP_OK;
+}
 
 int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st) {
@@ -925,11 +943,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // it at the end): the engine fills the SMs this latency-bound phase leaves idle with the K_zx assembly and the L_s operand
   // products on another stream, and at equal priority those filler CTAs delayed the first links of the chain by 0.1 - 0.2 ms
   // each (torch.profiler trace of the C3 step: 0.49 ms of gaps between the first six diagonal blocks).
-  struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_inv, ev_entry, ev_done; bool ready = false; };
-  static SideCtx ctxs[16];                              // one side stream + event pool per device
   int dev = 0;
   cudaGetDevice(&dev);
-  SideCtx& sc = ctxs[dev & 15];
+  SideCtx& sc = g_side_ctxs[dev & 15];
+  sc.mid_valid = false;
   if (!sc.ready) {
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
@@ -946,6 +963,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     cudaEventCreateWithFlags(&sc.ev_inv, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sc.ev_entry, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sc.ev_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sc.ev_mid, cudaEventDisableTiming);
     sc.ready = true;
   }
   cudaStream_t side = sc.side, inv = sc.inv;
@@ -987,6 +1005,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     CHECK_LAUNCH();
     const int m = Mp - (int)o - nb0;
     if (two_chains) cudaEventRecord(sc.ev_main[k], st);
+    if (two_chains && nblk >= 8 && k == std::min(g_chol_mid_link, nblk * 5 / 8)) {   // (measured at 32 blocks: 14 .. 26 equal, 6 .. 10 worse)
+      cudaEventRecord(sc.ev_mid, st);
+      sc.mid_valid = true;
+    }
     if (m > 0) {
       cudaStream_t gs = two_chains ? side : st;
       if (two_chains) cudaStreamWaitEvent(side, sc.ev_main[k], 0);

@@ -21,6 +21,9 @@ int get_chol_variant();
 // 1: trailing update of a step split into the thin part the next two links need and the bulk on a stream of its own
 void set_chol_lookahead(int on);
 int get_chol_lookahead();
+void set_chol_mid_link(int k);
+int get_chol_mid_link();
+int chol_wait_mid(cudaStream_t s);
 void set_chol_priority(int on);
 int get_chol_priority();
 void set_potrf_debug(long long* p);   // profiling aid: device buffer of 64 clock64() stamps (nullptr = off)

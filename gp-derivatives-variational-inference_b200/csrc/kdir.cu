@@ -233,6 +233,12 @@ size_t fwd_v4_smem_bytes(int dpad, int tib = V4_TIB) {
   return sizeof(float) * (size_t)(tib * (P1 + 1) * dpad + (P2 + 1) * dpad * V4_TJ + 8 * V4_TJ * (P2 + 1));
 }
 
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool pred) {   // pred false: writes 0, reads nothing
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+
 // MODE 0: general directions only (returns at once if the device flag says canonical); MODE 1: canonical only (returns
 // at once otherwise).  Both are launched back to back when a flag is supplied: the choice is made on the device without
 // a host synchronisation, and the canonical variant compiles to far fewer registers (3 CTAs per SM instead of 2).
@@ -258,23 +264,23 @@ kdir_fwd_v4(const float* __restrict__ x1, const float* __restrict__ u1, int n1, 
   if ((MODE == 1) != flag_set) return;                      // grid-uniform
   constexpr bool canon = MODE == 1;
 
+  // (zero-filling 4-byte cp.async: every element of both tiles in flight at once instead of one global round trip per loop pass)
   for (int e = tid; e < TIB * Q1 * dpad; e += 256) {       // row side: consecutive threads -> consecutive c
     const int cc = e % dpad, ia = e / dpad, i = ia / Q1, a = ia % Q1;
-    float v = 0.f;
-    if (i0 + i < n1 && cc < d)
-      v = (a == 0) ? x1[(int64_t)(i0 + i) * d + cc] : u1[(int64_t)((i0 + i) * P1 + a - 1) * d + cc];
-    rs[e] = v;
+    const bool ok = i0 + i < n1 && cc < d;
+    const float* src = !ok ? x1 : (a == 0) ? x1 + (int64_t)(i0 + i) * d + cc : u1 + (int64_t)((i0 + i) * P1 + a - 1) * d + cc;
+    cp_async4_zfill(rs + e, src, ok);
   }
   {                                                        // column side: consecutive threads -> consecutive j
     const int j = tid & 127, planes = canon ? 1 : Q2;
     for (int row = tid >> 7; row < planes * dpad; row += 2) {
       const int b = row / dpad, cc = row % dpad;
-      float v = 0.f;
-      if (j0 + j < n2 && cc < d)
-        v = (b == 0) ? x2[(int64_t)(j0 + j) * d + cc] : w2[(int64_t)((j0 + j) * P2 + b - 1) * d + cc];
-      cs[row * TJ + j] = v;
+      const bool ok = j0 + j < n2 && cc < d;
+      const float* src = !ok ? x2 : (b == 0) ? x2 + (int64_t)(j0 + j) * d + cc : w2 + (int64_t)((j0 + j) * P2 + b - 1) * d + cc;
+      cp_async4_zfill(cs + row * TJ + j, src, ok);
     }
   }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
 
   // canonical column directions: coordinate index / sign of this lane's 4 points, and x2 at that coordinate
@@ -794,11 +800,6 @@ size_t bwd_v4_smem_bytes() {
 }
 
 // 16- / 8-byte asynchronous global -> shared copies (the upstream block of the NEXT row point is fetched while this one is processed)
-__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool pred) {   // pred false: writes 0, reads nothing
-  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int bytes = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
-}
 template <int BYTES> __device__ __forceinline__ void cp_async_g2s(float* smem_dst, const float* gsrc) {
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
   if constexpr (BYTES == 16)

@@ -41,6 +41,8 @@ WHITEN_FP64 = "auto"  # fp32 model: run the two products that multiply by W = L^
                       # minibatch is small enough for that to be cheap (n' <= WHITEN_FP64_MAX_NQ: every minibatch size the
                       # reference's drivers ship).  DESIGN.md section 4.2 has the measured error table of both forms.
 WHITEN_FP64_MAX_NQ = 2048
+DEFER_SIDE_WORK = True   # elbo_step: the work overlapped with the factorisation (K_zx assembly, L_s operand products, KL) starts after the
+                         # chain's throughput-bound first links (ops.chol_wait_mid) instead of competing with their trailing updates
 TC_CHUNK = 2       # k-blocks (of 32) per tensor-core accumulation chain before the fp32 master sum
 TCH_CHUNK = 1      # the same chain length (K = 64) in k-blocks of 64 halves
 WORKSPACE_CACHE = 6    # problem shapes whose buffers are kept (least recently used evicted)
@@ -714,6 +716,10 @@ class Engine:
                         scales_ready.record(side)
                 self._factorise_finish(f, T, scales_ready)
                 with torch.cuda.stream(side):
+                    if DEFER_SIDE_WORK:
+                        # the first ~10 links of the chain are bound by their trailing updates (the GPU is full) and only the later
+                        # ones leave the SMs idle: the assembly and the L_s operand products start beside THOSE
+                        ops.chol_wait_mid()
                     self._assemble(ws, f, P, x, wx)
                     ws.kl.zero_()                      # KL(q(u) || p(u)) needs the parameters only: also under the Cholesky
                     if include_kl:

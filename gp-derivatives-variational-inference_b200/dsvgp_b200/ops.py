@@ -141,6 +141,16 @@ def set_chol_lookahead(on):
     return call_raw("dsvgp_set_chol_lookahead", int(bool(on)))
 
 
+def set_chol_mid_link(k):
+    """Diagonal block of the factorisation whose completion chol_wait_mid waits for (default 20, capped at 5/8 of the blocks; negative: never)."""
+    return call_raw("dsvgp_set_chol_mid_link", int(k))
+
+
+def chol_wait_mid():
+    """The current stream waits for the mid-chain diagonal block of the factorisation enqueued last (see include/dsvgp_b200.h)."""
+    return call("dsvgp_chol_wait_mid")
+
+
 def set_chol_priority(on):
     """Factorisation chains on the library's high-priority streams, or (default) the diagonal chain on the caller's stream."""
     return call_raw("dsvgp_set_chol_priority", int(bool(on)))

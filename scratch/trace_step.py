@@ -64,3 +64,11 @@ if len(sys.argv) > 2:
     print("first kernels of the last step (start us, duration us, stream, name):")
     for e in last[: int(sys.argv[2])]:
         print(f"  {(e.time_range.start - t_first):8.1f} {(e.time_range.end - e.time_range.start):7.1f}  s{getattr(e, 'device_index', 0)}:{getattr(e, 'device_resource_id', getattr(e, 'stream', -1))}  {e.name.split('(')[0][-60:]}")
+if os.environ.get("TRACE_DUMP"):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", os.environ["TRACE_DUMP"]), "w") as fh:
+        prev_end = None
+        for e in last:
+            s0, e0 = e.time_range.start - t_first, e.time_range.end - t_first
+            fh.write(f"{s0:9.1f} {e0 - s0:8.1f} gap {0.0 if prev_end is None else s0 - prev_end:7.1f} s{getattr(e, 'device_resource_id', -1)} {e.name.split('(')[0][-70:]}\n")
+            prev_end = e0 if prev_end is None else max(prev_end, e0)

@@ -613,3 +613,35 @@ def test_step_is_bitwise_deterministic():
     assert bool(torch.isfinite(ref).all())
     for _ in range(12):
         assert torch.equal(step(), ref)
+
+
+def test_deferred_side_work_is_bit_identical():
+    """engine.DEFER_SIDE_WORK only moves the overlapped assembly / L_s operand products behind a mid-chain diagonal block of the
+    factorisation (ops.chol_wait_mid): results must not change, for any release point, and the wait must be a no-op for
+    factorisations with too few blocks."""
+    import bench
+    from dsvgp_b200 import engine, gp, ops
+    dev = torch.device("cuda", 0)
+    for M in (32, 512):                                                  # M' = 96 (one block: no mid event), 1536 (16 blocks)
+        wl = dict(bench.WORKLOADS["C3"], M=M, n=640, N=20000)
+        model, lik = bench.build_model(wl, F32, dev)
+        mll = gp.VariationalELBO(lik, model, num_data=(wl["d"] + 1) * wl["N"])
+        x, V, y = (t.to(dev) for t in bench.synth_batch(wl["n"], wl["d"], wl["p"], "dsvgp", F32, "cpu", 5))
+        params = list(model.parameters()) + list(lik.parameters())
+
+        def step():
+            for q in params:
+                q.grad = None
+            loss = -mll(lik(model(x, derivative_directions=V)), y)
+            loss.backward()
+            return torch.cat([loss.detach().reshape(1).double()] + [q.grad.reshape(-1).double() for q in params])
+        try:
+            engine.DEFER_SIDE_WORK = False
+            ref = step()
+            engine.DEFER_SIDE_WORK = True
+            for mid in (20, 2, 0, -1, 9):
+                ops.set_chol_mid_link(mid)
+                assert torch.equal(step(), ref), (M, mid)
+        finally:
+            engine.DEFER_SIDE_WORK = True
+            ops.set_chol_mid_link(20)
