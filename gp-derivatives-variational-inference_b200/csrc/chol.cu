@@ -527,11 +527,17 @@ __device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, doub
     if (lane < 8) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) Ws[(k0 + i) * ld + k0 + j] = x[i];       // (x[i] = 0 above the diagonal)
+    }
+    // L11: every lane holds the whole block, so ONE lane writes it, two entries per 16-byte store (rows are 16-byte aligned:
+    // ld and k0 are even).  "lane c writes column c" compiled to 64 compare-and-branch sequences, whose branch-resolution stalls
+    // were 60 % of this warp's samples in the pivot chain (ncu source page, --warp-sampling-interval 0).
+    if (lane == 8) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (lane == c) Ls[(k0 + i) * ld + k0 + c] = (c <= i) ? a[i][c] : 0.0;   // lane c writes column c of L11
+        for (int c = 0; c < 8; c += 2)
+          *reinterpret_cast<double2*>(Ls + (k0 + i) * ld + k0 + c) =
+              make_double2((c <= i) ? a[i][c] : 0.0, (c + 1 <= i) ? a[i][c + 1] : 0.0);
     }
   };
   // one tile of the inverse's block row jp: Tt = L[jp, tc..jp) W[tc..jp, tc] on two independent accumulators (half the
@@ -567,12 +573,15 @@ __device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, doub
     if (warp == 0) {
       factor_diag(k0);
       DBG_T(2 + 4 * j);
-    } else if (j > 0) {
+    } else if ((warp & 3) != 0 && j > 0) {
+      // (warps 4, 8, 12 share warp 0's scheduler and with it the fp64 pipe: their DMMAs, 16 pipe cycles each, were what the pivot
+      //  chain's dependent DFMAs waited for -- the chain took 4.3k cycles per 8 columns against ~2k alone.  They sit this phase out.)
       const int jp = j - 1, kp = 8 * jp;               // previous step: panel jp is final, D_jp sits in Ws[jp,jp]
       // items: [0, jp)  inverse block row jp, tile column tc (longest chains first);
       //        [jp, jp + ntr)  trailing tiles (ti >= tj >= j + 1)
       const int nt = T - (j + 1), ntr = nt * (nt + 1) / 2, nitems = jp + ntr;
-      for (int it = warp - 1; it < nitems; it += POTRF_THREADS / 32 - 1) {
+      constexpr int NWORK = (POTRF_THREADS / 32 / 4) * 3;
+      for (int it = (warp >> 2) * 3 + (warp & 3) - 1; it < nitems; it += NWORK) {
         if (it < jp) {
           inverse_tile(jp, it);
         } else {
