@@ -455,6 +455,10 @@ diag_prepare(const double* __restrict__ Aleft, int64_t lda, const double* __rest
   }
 }
 
+#ifndef POTRF_S0_IDLE
+#define POTRF_S0_IDLE 1     // 1: warps 4, 8, 12 (warp 0's scheduler) take no leftover work during the pivot phase
+#endif
+template <int V> struct IntTag { static constexpr int value = V; };
 __device__ long long* g_potrf_dbg = nullptr;     // profiling aid: clock64() at the phase boundaries of one block kernel
 #define DBG_T(slot) do { if (dbg != nullptr && tid == 0) dbg[slot] = clock64(); } while (0)
 
@@ -573,15 +577,15 @@ __device__ __forceinline__ void factor_invert_smem(double* __restrict__ Ls, doub
     if (warp == 0) {
       factor_diag(k0);
       DBG_T(2 + 4 * j);
-    } else if ((warp & 3) != 0 && j > 0) {
+    } else if ((POTRF_S0_IDLE ? (warp & 3) != 0 : true) && j > 0) {
       // (warps 4, 8, 12 share warp 0's scheduler and with it the fp64 pipe: their DMMAs, 16 pipe cycles each, were what the pivot
       //  chain's dependent DFMAs waited for -- the chain took 4.3k cycles per 8 columns against ~2k alone.  They sit this phase out.)
       const int jp = j - 1, kp = 8 * jp;               // previous step: panel jp is final, D_jp sits in Ws[jp,jp]
       // items: [0, jp)  inverse block row jp, tile column tc (longest chains first);
       //        [jp, jp + ntr)  trailing tiles (ti >= tj >= j + 1)
       const int nt = T - (j + 1), ntr = nt * (nt + 1) / 2, nitems = jp + ntr;
-      constexpr int NWORK = (POTRF_THREADS / 32 / 4) * 3;
-      for (int it = (warp >> 2) * 3 + (warp & 3) - 1; it < nitems; it += NWORK) {
+      constexpr int NWORK = POTRF_S0_IDLE ? (POTRF_THREADS / 32 / 4) * 3 : POTRF_THREADS / 32 - 1;
+      for (int it = POTRF_S0_IDLE ? (warp >> 2) * 3 + (warp & 3) - 1 : warp - 1; it < nitems; it += NWORK) {
         if (it < jp) {
           inverse_tile(jp, it);
         } else {
@@ -758,69 +762,98 @@ potrf_cluster(const double* __restrict__ A, int64_t lda, double* __restrict__ L,
     }
     const int kmax_all = nc > 0 ? 8 * (tcol[nc - 1] + 1) : 0;
     if (nc > 0) {
-      for (int e = tid; e < nbp * (kmax_all >> 1); e += POTRF_THREADS) {        // X = A[k,k-1], 16-byte chunks
-        const int i = e / (kmax_all >> 1), c = 2 * (e - i * (kmax_all >> 1));
-        if (i < nb && c + 1 < nb) {
-          const uint32_t d = (uint32_t)__cvta_generic_to_shared(R0 + i * ld + c);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(Aleft + (int64_t)i * lda + c) : "memory");
-        } else {
-          R0[i * ld + c] = (i < nb && c < nb) ? Aleft[(int64_t)i * lda + c] : 0.0;
-          R0[i * ld + c + 1] = 0.0;
+      // (a warp per row, lanes along the row: no per-element division -- the index arithmetic of the flat loops was most of
+      //  this phase's 5k cycles)
+      for (int i = warp; i < nbp; i += POTRF_THREADS / 32)                       // X = A[k,k-1], 16-byte chunks
+        for (int c = 2 * lane; c < kmax_all; c += 64) {
+          if (i < nb && c + 1 < nb) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(R0 + i * ld + c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(Aleft + (int64_t)i * lda + c) : "memory");
+          } else {
+            R0[i * ld + c] = (i < nb && c < nb) ? Aleft[(int64_t)i * lda + c] : 0.0;
+            R0[i * ld + c + 1] = 0.0;
+          }
         }
-      }
-      for (int e = tid; e < 8 * nc * kmax_all; e += POTRF_THREADS) {            // Y = this CTA's rows of W11(k-1)
-        const int r = e / kmax_all, c = e - r * kmax_all, j = 8 * tcol[r >> 3] + (r & 7);
-        const bool in = j < nb && c <= j;
-        cp_async8(Y + r * ld + c, in ? Wprev + (int64_t)j * ldw + c : Wprev, in);
+      for (int r = warp; r < 8 * nc; r += POTRF_THREADS / 32) {                  // Y = this CTA's rows of W11(k-1)
+        const int j = 8 * tcol[r >> 3] + (r & 7);
+        for (int c = lane; c < kmax_all; c += 32) {
+          const bool in = j < nb && c <= j;
+          cp_async8(Y + r * ld + c, in ? Wprev + (int64_t)j * ldw + c : Wprev, in);
+        }
       }
     }
     cp_async_wait_all();
     __syncthreads();
     DBG_T(52);
-    for (int ti = warp; ti < T && nc > 0; ti += POTRF_THREADS / 32) {          // Z slice: 8 x (8 nc) strips
-      double acc[4][2];
+    // Z slice: 8 x (8 nc) strips.  No conditions inside the k loops of this prologue: with `if (k0 < 8 (tcol[q] + 1)) dmma` /
+    // `if (3 cg + q <= ri) dmma` each DMMA sat behind its own branch and its operand load behind that -- load latency + DMMA
+    // latency serialised per accumulator (4.3k + 5.6k cycles for the two phases).  Y is zero beyond the triangle (zero-filled
+    // above); the accumulator count is a compile-time constant per call and the k range is cut per SEGMENT, outside the loops.
+    auto z_strips = [&](auto nc_tag) {
+      constexpr int NC = decltype(nc_tag)::value;
+      for (int ti = warp; ti < T; ti += POTRF_THREADS / 32) {
+        double acc[NC][2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
-      const double* xa = R0 + (8 * ti + g) * ld + t;
-      for (int k0 = 0; k0 < kmax_all; k0 += 4) {
-        const double a = xa[k0];
+        for (int q = 0; q < NC; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const double* xa = R0 + (8 * ti + g) * ld + t;
+        const double* yb = Y + g * ld + t;
+        // column q of this CTA needs k < 8 (tcol[q] + 1) only (W11 is lower triangular; tcol ascending): segment s of the k range
+        // feeds accumulators s .. NC-1 -- half the DMMAs of the full range, and this phase is bound by the SM's DMMA pipe
+        int k0 = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < nc && k0 < 8 * (tcol[q] + 1)) dmma884(acc[q], a, Y[(8 * q + g) * ld + k0 + t]);
-      }
+        for (int sgm = 0; sgm < NC; ++sgm) {
+          const int kend = 8 * (tcol[sgm] + 1);
+#pragma unroll 2
+          for (; k0 < kend; k0 += 4) {
+            const double a = xa[k0];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < nc) {
+            for (int q = sgm; q < NC; ++q) dmma884(acc[q], a, yb[8 * q * ld + k0]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
           double* z = Zs + (8 * ti + g) * ldz + 8 * q + 2 * t;
           z[0] = acc[q][0];
           z[1] = acc[q][1];
         }
-    }
+      }
+    };
+    if (nc == 3) z_strips(IntTag<3>{});
+    else if (nc == 4) z_strips(IntTag<4>{});
+    else if (nc == 2) z_strips(IntTag<2>{});
+    else if (nc == 1) z_strips(IntTag<1>{});
     __syncthreads();
     DBG_T(53);
     // D_r = Zs Zs^T on the lower tiles (contraction over this CTA's 8 nc columns), into R2 = R0 (X is dead).  Only the
     // blocks (tile row ri, group of 3 tile columns cg <= ri / 3) that touch the lower triangle are dealt out.
+    auto syrk_block = [&](auto nq_tag, int ri, int cg) {
+      constexpr int NQ = decltype(nq_tag)::value;
+      double acc[NQ][2];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = 0.0;
+      const double* za = Zs + (8 * ri + g) * ldz + t;
+      const double* zb = Zs + (8 * 3 * cg + g) * ldz + t;
+#pragma unroll 2
+      for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
+        const double a = za[k0];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) dmma884(acc[q], a, zb[8 * q * ldz + k0]);
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double* dd = R2 + (8 * ri + g) * ld + 8 * (3 * cg + q) + 2 * t;
+        dd[0] = acc[q][0];
+        dd[1] = acc[q][1];
+      }
+    };
     int idx = 0;
     for (int ri = 0; ri < T; ++ri)
       for (int cg = 0; 3 * cg <= ri; ++cg, ++idx) {
         if ((idx & 15) != warp) continue;
-        double acc[3][2];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = 0.0;
-        const double* za = Zs + (8 * ri + g) * ldz + t;
-        for (int k0 = 0; k0 < 8 * nc; k0 += 4) {
-          const double a = za[k0];
-#pragma unroll
-          for (int q = 0; q < 3; ++q)
-            if (3 * cg + q <= ri) dmma884(acc[q], a, Zs[(8 * (3 * cg + q) + g) * ldz + k0 + t]);
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (3 * cg + q <= ri) {
-            double* dd = R2 + (8 * ri + g) * ld + 8 * (3 * cg + q) + 2 * t;
-            dd[0] = acc[q][0];
-            dd[1] = acc[q][1];
-          }
+        const int nq = min(3, ri - 3 * cg + 1);
+        if (nq == 3) syrk_block(IntTag<3>{}, ri, cg);
+        else if (nq == 2) syrk_block(IntTag<2>{}, ri, cg);
+        else syrk_block(IntTag<1>{}, ri, cg);
       }
   }
   DBG_T(54);
@@ -1014,7 +1047,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     CHECK_LAUNCH();
     const int m = Mp - (int)o - nb0;
     if (two_chains) cudaEventRecord(sc.ev_main[k], st);
-    if (two_chains && nblk >= 8 && k == std::min(g_chol_mid_link, nblk * 5 / 8)) {   // (measured at 32 blocks: 14 .. 26 equal, 6 .. 10 worse)
+    if (two_chains && nblk >= 8 && k == std::min(g_chol_mid_link, nblk - 1)) {
       cudaEventRecord(sc.ev_mid, st);
       sc.mid_valid = true;
     }

@@ -142,7 +142,7 @@ def set_chol_lookahead(on):
 
 
 def set_chol_mid_link(k):
-    """Diagonal block of the factorisation whose completion chol_wait_mid waits for (default 20, capped at 5/8 of the blocks; negative: never)."""
+    """Diagonal block of the factorisation whose completion chol_wait_mid waits for (default 20, capped at the last block; negative: never)."""
     return call_raw("dsvgp_set_chol_mid_link", int(k))
 
 

@@ -121,8 +121,8 @@ int dsvgp_set_chol_variant(int v);
 int dsvgp_set_chol_priority(int on);
 /* Deferring a caller's overlapped work to the latency-bound part of the factorisation: the first links of the chain are bound by
  * their trailing updates (which fill the GPU), the later ones leave most SMs idle.  dsvgp_chol_wait_mid makes stream s wait for
- * diagonal block min(k, 5/8 of the blocks) (dsvgp_set_chol_mid_link, default k = 20, negative: never) of the factorisation enqueued
- * last on the current device; a no-op when that factorisation had fewer than 8 blocks.  Capturable (an event edge inside the graph). */
+ * diagonal block min(k, last) (dsvgp_set_chol_mid_link, default k = 20, negative: never) of the factorisation enqueued
+ * last on the current device; a no-op when that factorisation had fewer than 8 blocks.  (Measured at 32 blocks: release points 14 .. 31 equal within noise, 6 .. 10 worse.)  Capturable (an event edge inside the graph). */
 int dsvgp_set_chol_mid_link(int k);
 int dsvgp_chol_wait_mid(dsvgp_stream_t s);
 /* 1: while the trailing matrix is large, the update of step k is split into the first two block columns of the

@@ -29,6 +29,6 @@ def run(name, n, mids):
             if mid is not None: ops.set_chol_mid_link(mid)
             out.append((mid, round(t(), 3)))
     print(name, n, out, flush=True)
-run("C3", 16384, (None, 14, 18, 22, 26))
-run("C3", 512, (None, 14, 18, 22, 26))
-run("C4", 2048, (None, 14, 20))
+run("C3", 16384, (20, 26, 31))
+run("C3", 512, (20, 26, 31))
+run("C4", 2048, (20, 31))
