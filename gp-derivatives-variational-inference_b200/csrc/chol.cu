@@ -919,12 +919,15 @@ int get_chol_lookahead() { return g_chol_lookahead; }
 static int g_chol_mid_link = 20;  // chol_wait_mid(): the diagonal block whose completion releases work the caller deferred (see there); < 0: none
 void set_chol_mid_link(int k) { g_chol_mid_link = k; }
 int get_chol_mid_link() { return g_chol_mid_link; }
+static int g_chol_inv_streams = 1; // eager inverse: 2 = T = L21 W11 products on a second stream (measured equal, eager and graph-replayed: off)
+void set_chol_inv_streams(int n) { g_chol_inv_streams = n >= 2 ? 2 : 1; }
+int get_chol_inv_streams() { return g_chol_inv_streams; }
 static int g_chol_priority = 0;   // 1: the three chains of the factorisation on the library's high-priority streams; 0: diagonal chain on the caller's
                                   // stream (measured: no difference on any workload -- off)
 void set_chol_priority(int on) { g_chol_priority = on ? 1 : 0; }
 int get_chol_priority() { return g_chol_priority; }
 
-struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_inv, ev_entry, ev_done, ev_mid; bool ready = false, mid_valid = false; };
+struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, inv2 = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_T[8], ev_inv, ev_inv2, ev_pre, ev_entry, ev_done, ev_mid; bool ready = false, mid_valid = false; };
 static SideCtx g_side_ctxs[16];                         // one set of side streams + event pool per device
 
 // The first links of the chain are throughput-bound (their rank-nb0 trailing updates fill the GPU: potrf(k+2) waits for update(k)),
@@ -995,6 +998,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     if (cudaStreamCreateWithPriority(&sc.diag, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     if (cudaStreamCreateWithPriority(&sc.side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     if (cudaStreamCreateWithPriority(&sc.inv, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+    if (cudaStreamCreateWithPriority(&sc.inv2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     if (cudaStreamCreateWithPriority(&sc.bulk, cudaStreamNonBlocking, prio_least) != cudaSuccess) return DSVGP_ERR_LAUNCH;
     for (int i = 0; i < 64; ++i) {
       cudaEventCreateWithFlags(&sc.ev_main[i], cudaEventDisableTiming);
@@ -1006,6 +1010,9 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     cudaEventCreateWithFlags(&sc.ev_entry, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sc.ev_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sc.ev_mid, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sc.ev_inv2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sc.ev_pre, cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&sc.ev_T[i], cudaEventDisableTiming);
     sc.ready = true;
   }
   cudaStream_t side = sc.side, inv = sc.inv;
@@ -1024,6 +1031,7 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   // next diag_prepare).
   const bool eager_inv = two_chains && nlev >= 1 && g_chol_variant >= 2;
   int last_side = -1, last_bulk = -1;
+  unsigned t_pending = 0;                               // levels whose T product (second inverse stream) no W21 has waited for yet
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
     // (more than 64 blocks: more steps than pooled events -- everything goes on the caller's stream, in order)
@@ -1112,14 +1120,31 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
           waited = true;
         }
         if (idx & 1) {                                   // a TOP half just ended: T = L21 W11 (needs the panel of column k)
+          // (knob) T products on a stream of their own: nothing after them on `inv` needs them before the pair's bottom half ends
+          // (2^lev blocks later).  The ~20-kernel backlog seen after the last diagonal block in a profiler trace of the
+          // factorisation ALONE turned out to be the host falling behind (~650 launch / event calls per factorisation against
+          // 34 us per block), not stream order: steps measure the same with one or two streams, eager or graph-replayed.
           const int64_t s0 = (int64_t)(idx - 1) * b;
-          cudaStreamWaitEvent(inv, sc.ev_panel[k], 0);
+          cudaStream_t ts = (g_chol_inv_streams >= 2 && lev < 8) ? sc.inv2 : inv;
+          if (ts != inv) {
+            cudaEventRecord(sc.ev_pre, inv);             // W11 of this group is complete (its lower-level W21 were just issued on inv)
+            cudaStreamWaitEvent(ts, sc.ev_pre, 0);
+          }
+          cudaStreamWaitEvent(ts, sc.ev_panel[k], 0);
           int rc = gemm<double>(false, false, b, b, b, 1.0, L + (s0 + b) * ldl + s0, ldl, W + s0 * ldw + s0, ldw, 0.0,
-                                W + s0 * ldw + (s0 + b), ldw, TRI_NONE, TRI_LOWER, 0, 1, 0, 0, 0, inv);
+                                W + s0 * ldw + (s0 + b), ldw, TRI_NONE, TRI_LOWER, 0, 1, 0, 0, 0, ts);
           if (rc) return rc;
+          if (ts != inv) {
+            cudaEventRecord(sc.ev_T[lev], ts);
+            t_pending |= 1u << lev;
+          }
           break;
         }
         const int64_t s0 = (int64_t)(idx - 2) * b;       // a BOTTOM half just ended: W21 = -W22 T, the pair is complete
+        if (t_pending & (1u << lev)) {
+          cudaStreamWaitEvent(inv, sc.ev_T[lev], 0);
+          t_pending &= ~(1u << lev);
+        }
         int rc = gemm<double>(false, false, b, b, b, -1.0, W + (s0 + b) * ldw + (s0 + b), ldw, W + s0 * ldw + (s0 + b), ldw, 0.0,
                               W + (s0 + b) * ldw + s0, ldw, TRI_LOWER, TRI_NONE, 0, 1, 0, 0, 0, inv);
         if (rc) return rc;
@@ -1136,6 +1161,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   if (eager_inv) {
     cudaEventRecord(sc.ev_inv, inv);
     cudaStreamWaitEvent(st, sc.ev_inv, 0);
+    if (g_chol_inv_streams >= 2) {                      // (every T has been consumed by a W21 on inv; the join keeps the fork/join
+      cudaEventRecord(sc.ev_inv2, sc.inv2);             //  structure explicit for graph capture)
+      cudaStreamWaitEvent(st, sc.ev_inv2, 0);
+    }
     return DSVGP_OK;
   }
   // recursive inverse; Awork (no longer needed) is the scratch for T = L21 * W11

@@ -151,6 +151,11 @@ def chol_wait_mid():
     return call("dsvgp_chol_wait_mid")
 
 
+def set_chol_inv_streams(n):
+    """Streams of the eager inverse (1: one stream, default; 2: T products beside the W21 chain -- measured equal)."""
+    return call_raw("dsvgp_set_chol_inv_streams", int(n))
+
+
 def set_chol_priority(on):
     """Factorisation chains on the library's high-priority streams, or (default) the diagonal chain on the caller's stream."""
     return call_raw("dsvgp_set_chol_priority", int(bool(on)))

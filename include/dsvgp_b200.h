@@ -125,6 +125,10 @@ int dsvgp_set_chol_priority(int on);
  * last on the current device; a no-op when that factorisation had fewer than 8 blocks.  (Measured at 32 blocks: release points 14 .. 31 equal within noise, 6 .. 10 worse.)  Capturable (an event edge inside the graph). */
 int dsvgp_set_chol_mid_link(int k);
 int dsvgp_chol_wait_mid(dsvgp_stream_t s);
+/* Streams of the eager inverse: 1 (default) = one stream; 2 = the T = L21 W11 products (issued when a pair's top half is complete,
+ * needed only when its bottom half is) run on a stream of their own beside the W21 = -W22 T chain (measured equal on every
+ * workload, eager and graph-replayed; results bit-identical).  Returns the value in force. */
+int dsvgp_set_chol_inv_streams(int n);
 /* 1: while the trailing matrix is large, the update of step k is split into the first two block columns of the
  * trapezoid (all that the diagonal block k+2 and the panel k+1 read; side stream) and the rest (a low-priority stream of its
  * own, two links' time to finish);

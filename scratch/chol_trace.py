@@ -27,7 +27,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run(); torch.cuda.synchronize()
 ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
 t0 = ev[0].time_range.start
-rows = [(e.time_range.start - t0, e.time_range.end - t0, e.name[:40]) for e in ev]
+rows = [(e.time_range.start - t0, e.time_range.end - t0, f"s{getattr(e, 'device_resource_id', -1)} " + e.name[:40]) for e in ev]
 print(f"Mq={Mq} variant={variant}: {len(rows)} kernels, span {rows[-1][1] / 1e3:.3f} ms")
 import collections
 agg = collections.defaultdict(lambda: [0, 0.0])
@@ -42,3 +42,8 @@ print("first 40 events:")
 for s, e, n in rows[:40]:
     print(f"  {s:8.1f} {e - s:7.1f}  {n}")
 print("last potrf end", pot[-1][1], "total end", rows[-1][1])
+print("events from the 28th diagonal block on (start, duration, stream, name):")
+t28 = pot[-1][0] if len(pot) > 27 else 0
+for s, e, n in rows:
+    if s >= t28:
+        print(f"  {s:8.1f} {e - s:7.1f}  {n}")

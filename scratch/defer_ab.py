@@ -29,6 +29,10 @@ def run(name, n, mids):
             if mid is not None: ops.set_chol_mid_link(mid)
             out.append((mid, round(t(), 3)))
     print(name, n, out, flush=True)
-run("C3", 16384, (20, 26, 31))
-run("C3", 512, (20, 26, 31))
-run("C4", 2048, (20, 31))
+for la, pr in ((0, 0), (1, 0), (0, 1), (1, 1)):
+    ops.set_chol_lookahead(la); ops.set_chol_priority(pr)
+    print("lookahead", la, "priority", pr)
+    run("C3", 16384, (20,))
+    run("C3", 512, (20,))
+    run("C4", 2048, (20,))
+ops.set_chol_lookahead(0); ops.set_chol_priority(0)

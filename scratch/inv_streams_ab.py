@@ -1,0 +1,20 @@
+"""A/B of the eager inverse's stream layout (dsvgp_set_chol_inv_streams 1 / 2), eager and CUDA-graph replayed steps."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gp-derivatives-variational-inference_b200"))
+import torch, bench
+from dsvgp_b200 import ops, graphs
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+for name, n in (("C3", 512), ("C3", 4096), ("C4", 512), ("C2", 500)):
+    arm = bench.Arm(dict(bench.WORKLOADS[name]), dev, 0, 1)
+    out = []
+    for rnd in range(2):
+        for ns in (1, 2):
+            ops.set_chol_inv_streams(ns)
+            e = arm.time_steps(n, 1000, 3, 20, collective=False)
+            g = graphs.time_graphed_step(arm, n, 2000, 3, 20)
+            out.append((ns, round(e, 3), round(g, 3)))
+    print(name, n, "(streams, eager ms, graph ms):", out, flush=True)
+    arm.release()
+ops.set_chol_inv_streams(2)
