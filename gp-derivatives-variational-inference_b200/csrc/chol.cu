@@ -1064,8 +1064,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
       if (two_chains) cudaStreamWaitEvent(side, sc.ev_main[k], 0);
       double* L21 = L + (o + nb0) * ldl + o;
       // panel  L21 = A21 * W11^T   (op(B) = W11^T is upper triangular)
+      // (W11 carries explicit zeros above its diagonal, so the triangle flag only saves flops: with the rank-K kernel on, which
+      //  takes dense operands only, the panel goes through it as a dense product)
       int rc = gemm1<double>(false, true, m, nb0, nb0, 1.0, Awork + (o + nb0) * lda + o, lda, W + o * ldw + o, ldw, 0.0,
-                             L21, ldl, TRI_NONE, TRI_UPPER, 0, gs);
+                             L21, ldl, TRI_NONE, get_rank_update() ? TRI_NONE : TRI_UPPER, 0, gs);
       if (rc) return rc;
       if (eager_inv) cudaEventRecord(sc.ev_panel[k], side);
       const int m2 = m - nb0;

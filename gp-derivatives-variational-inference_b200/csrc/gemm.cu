@@ -419,6 +419,7 @@ gemm64_async_kernel(GemmParams<double> p) {
 // K extent of both operand tiles goes global -> shared in ONE cp.async burst ([row][k] layout, row stride = K rounded up to 16
 // plus 4 doubles: conflict-free DMMA fragments), one barrier, then every warp runs its K/4 DMMA steps back to back.
 constexpr int RK_MAXK = 128;
+constexpr int RK_SMALL_GRID = 640;
 __host__ __device__ constexpr int rk_ld(int K) { return ((K + 15) & ~15) + 4; }
 
 __device__ __forceinline__ void cp_async16_zfill(double* smem_dst, const double* gsrc, bool pred) {
@@ -502,7 +503,7 @@ rank_update64_kernel(GemmParams<double> p) {
 static int g_rank_update = 0;   // measured (scratch/rank_update_ab.py, scratch/prio_ab.py): 65 vs 58 us on the first link's update, equal
                                 // later -- both kernels are ramp-bound at K = 96 (13 TFLOP/s) -- and its 100 KB of shared memory per
                                 // CTA crowds the diagonal-block cluster running beside it: the step is 0.1 ms SLOWER.  Off.
-void set_rank_update(int on) { g_rank_update = on ? 1 : 0; }
+void set_rank_update(int on) { g_rank_update = (on >= 0 && on <= 2) ? on : 0; }   // 2: only launches of at most RK_SMALL_GRID tiles (the latency-bound late links)
 int get_rank_update() { return g_rank_update; }
 
 static int g_gemm64_async = 1;
@@ -533,7 +534,7 @@ int gemm(bool ta, bool tb, int M, int N, int K, T alpha, const T* A, int64_t lda
   GemmParams<T> p{A, B, C, D, C2, D2, M, N, K, lda, ldb, ldc, ldd, ldc2, ldd2, sA, sB, sC, alpha, beta, a_tri, b_tri, c_tri, c_off};
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
   if constexpr (sizeof(T) == 8) {
-    if (g_rank_update && !ta && tb && K >= 8 && K <= RK_MAXK && (K & 1) == 0 && batch == 1 && a_tri == 0 && b_tri == 0 && !C2 &&
+    if ((g_rank_update == 1 || (g_rank_update == 2 && (int64_t)grid.x * grid.y <= RK_SMALL_GRID)) && !ta && tb && K >= 8 && K <= RK_MAXK && (K & 1) == 0 && batch == 1 && a_tri == 0 && b_tri == 0 && !C2 &&
         ((lda | ldb) & 1) == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) {
       const int smem = (BM + BN) * rk_ld(K) * (int)sizeof(double);
       static bool attr[64] = {};

@@ -132,8 +132,8 @@ def transpose(src, dst, rows=None, cols=None):
 
 
 def set_rank_update(on):
-    """fp64 rank-K update kernel (K <= 128) for A B^T products (default off: measured no gain)."""
-    return call_raw("dsvgp_set_rank_update", int(bool(on)))
+    """fp64 rank-K update kernel (K <= 128) for A B^T products: 0 off, 1 every eligible product, 2 only small (latency-bound) launches."""
+    return call_raw("dsvgp_set_rank_update", int(on))
 
 
 def set_chol_lookahead(on):

@@ -153,7 +153,9 @@ int dsvgp_gemm_f64(int ta, int tb, int M, int N, int K, double alpha, const doub
 int dsvgp_set_gemm64_async(int on);
 /* fp64 products op(A) = A, op(B) = B^T with a short contraction (8 <= K <= 128, even; no triangle flags on the operands, no
  * batch): 1 = rank-update kernel (whole K extent of both operand tiles in shared memory in one cp.async burst, one barrier) --
- * the trailing updates of the blocked Cholesky; 0 (default: the former measured no gain) = the general kernel.  Returns the value in force. */
+ * the trailing updates of the blocked Cholesky; 2 = that kernel only for launches of at most 640 tiles (the latency-bound late
+ * links; the panel products then go through it as dense products, W11 carrying explicit zeros above its diagonal); 0 (default:
+ * 1 measured slower, 2 equal within 0.02 ms) = the general kernel.  Returns the value in force. */
 int dsvgp_set_rank_update(int on);
 
 /* The same product on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA-fed, accumulators in tensor memory)
