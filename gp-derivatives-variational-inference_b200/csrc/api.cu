@@ -159,6 +159,8 @@ int dsvgp_tril_minus_eye_f32(const float* Ls, int64_t ldl, float* E, int64_t lde
 int dsvgp_tril_minus_eye_f64(const double* Ls, int64_t ldl, double* E, int64_t lde, int n, dsvgp_stream_t s) { return tril_minus_eye<double>(Ls, ldl, E, lde, n, ST(s)); }
 int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return sym_phi(Y, ldy, P, ldp, n, ST(s)); }
 
+int dsvgp_phi_outer_f32(const float* X, int64_t ldx, const float* u, const float* v, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return phi_outer<float>(X, ldx, u, v, P, ldp, n, ST(s)); }
+int dsvgp_phi_outer_f64(const double* X, int64_t ldx, const double* u, const double* v, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return phi_outer<double>(X, ldx, u, v, P, ldp, n, ST(s)); }
 int dsvgp_phi_lower_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s) { return phi_lower(Y, ldy, P, ldp, n, ST(s)); }
 int dsvgp_symmetrize_f64(double* A, int64_t ld, int n, dsvgp_stream_t s) { return symmetrize(A, ld, n, ST(s)); }
 

@@ -95,6 +95,31 @@ __global__ void phi_lower_kernel(const double* __restrict__ Y, int64_t ldy, doub
   P[(int64_t)i * ldp + j] = (j < i) ? Y[(int64_t)i * ldy + j] : (j == i ? 0.5 * Y[(int64_t)i * ldy + j] : 0.0);
 }
 
+// Lower triangle of Phi(X + u v^T) in fp64 from X in the model dtype, two columns per thread: the add_outer -> cast2d -> phi_lower
+// sequence of the Cholesky-backward tail as ONE pass that reads and writes the lower triangle only (the products that consume P
+// take it with a lower-triangle flag and never load the other side): 3 launches / ~260 MB of traffic -> 1 launch / ~60 MB at M' = 3072.
+template <typename T>
+__global__ void phi_outer_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ u, const T* __restrict__ v,
+                                 double* __restrict__ P, int64_t ldp, int n) {
+  const int i = blockIdx.y, j = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n || j > i) return;
+  const T ui = u[i];
+  const T x0 = X[(int64_t)i * ldx + j] + T(1) * ui * v[j];
+  double p0 = (double)x0, p1 = 0.0;
+  if (j == i) p0 *= 0.5;
+  if (j + 1 <= i) {
+    const T x1 = X[(int64_t)i * ldx + j + 1] + T(1) * ui * v[j + 1];
+    p1 = (j + 1 == i) ? 0.5 * (double)x1 : (double)x1;
+  }
+  double* dst = P + (int64_t)i * ldp + j;
+  if (((ldp & 1) == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0) && j + 1 < n) {
+    *reinterpret_cast<double2*>(dst) = make_double2(p0, p1);      // (the entry right of the diagonal is written as 0)
+  } else {
+    dst[0] = p0;
+    if (j + 1 < n) dst[1] = p1;
+  }
+}
+
 // A <- (A + A^T) / 2 in place
 __global__ void symmetrize_kernel(double* A, int64_t ld, int n) {
   __shared__ double ta[32][33], tb[32][33];
@@ -636,6 +661,17 @@ int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStr
   CHECK_LAUNCH();
   return DSVGP_OK;
 }
+
+template <typename T>
+int phi_outer(const T* X, int64_t ldx, const T* u, const T* v, double* P, int64_t ldp, int n, cudaStream_t st) {
+  if (n <= 0) return DSVGP_OK;
+  dim3 grid(ceil_div(ceil_div(n, 2), 128), n);
+  phi_outer_kernel<T><<<grid, 128, 0, st>>>(X, ldx, u, v, P, ldp, n);
+  CHECK_LAUNCH();
+  return DSVGP_OK;
+}
+template int phi_outer<float>(const float*, int64_t, const float*, const float*, double*, int64_t, int, cudaStream_t);
+template int phi_outer<double>(const double*, int64_t, const double*, const double*, double*, int64_t, int, cudaStream_t);
 
 int phi_lower(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st) {
   if (n <= 0) return DSVGP_OK;

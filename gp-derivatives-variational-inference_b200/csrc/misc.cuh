@@ -14,6 +14,8 @@ template <typename T> int add_outer(T* A, int64_t ld, int n, const T* u, const T
 template <typename T> int tril_minus_eye(const T* Ls, int64_t ldl, T* E, int64_t lde, int n, cudaStream_t st);
 int sym_phi(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st);
 int phi_lower(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, cudaStream_t st);
+template <typename T>
+int phi_outer(const T* X, int64_t ldx, const T* u, const T* v, double* P, int64_t ldp, int n, cudaStream_t st);
 int symmetrize(double* A, int64_t ld, int n, cudaStream_t st);
 int reduce_slabs(int rows, int cols);
 template <typename T>

@@ -165,7 +165,6 @@ class Workspace:
         self.scratch_kl = e(512, dt=F64)           # (its own partial-sum buffer: the KL runs on the side stream)
         self.H = e(Mq, self.ldg)[:, :Mq] if T == F32 else sq()
         self.X = sq()
-        self.Xd = e(Mq, Mq, dt=F64) if T == F32 else self.X
         self.Y, self.Psi, self.S = (e(Mq, Mq, dt=F64) for _ in range(3))
         self.gm = self.gLs = None      # allocated fresh by every backward pass (handed to autograd without a copy)
         self.wx = None
@@ -572,14 +571,12 @@ class Engine:
         else:
             ops.gemm(ws.E, ws.G, ws.Hp, ta=True, a_tri=TRI_UPPER, M=Mq, N=Mq, K=Mq, C2=ws.H, D2=ws.G)
             ops.gemm(ws.E, ws.H, ws.X, a_tri=TRI_LOWER, alpha=2.0, beta=2.0, D=ws.Hp, M=Mq, N=Mq, K=Mq)
-        ops.add_outer(ws.X, P.m, ws.t, 1.0)                                              # X = dA A^T
-        if T == F32:
-            ops.cast2d(ws.X, ws.Xd)
+        # X + m t^T = dA A^T enters only through Phi(.): one pass writes the lower triangle of Psi in fp64 (ops.phi_outer)
         # Cholesky backward composed with the whitening backward.  With U = L^-T X (X = dA A^T), dL = -tril(U) and
         # L^T dL = -L^T (U - su(U)) = -X + L^T su(U), where su = strictly upper part; L^T (upper) times a strictly upper matrix
         # is strictly upper, so  tril(L^T dL) = -tril(X)  EXACTLY and  dK_zz = sym(L^-T Phi(L^T dL) L^-1) = -sym(W^T Phi(X) W):
         # the two M'^3 fp64 products dL = -tril(W^T X) and Y = L^T dL of round 1 are not needed at all (0.78 ms of 2.1 at C3).
-        ops.phi_lower(ws.Xd, ws.Psi, Mq)                                                              # Phi(X): tril, halved diagonal
+        ops.phi_outer(ws.X, P.m, ws.t, ws.Psi, Mq)                        # lower triangle of Phi(X + m t^T): tril, halved diagonal
         shards = self._tail_shards(reducer)
         if shards is None:
             ops.gemm(ws.Psi, W, ws.Y, a_tri=TRI_LOWER, b_tri=TRI_LOWER, c_tri=1, alpha=-1.0, M=Mq, N=Mq, K=Mq)   # Y = -Phi(X) W (lower)

@@ -301,6 +301,11 @@ def sym_phi(Y, P, n):
     return P
 
 
+def phi_outer(X, u, v, P, n):
+    """lower triangle of P (fp64) = Phi(X + u v^T); the upper triangle of P is left as it is"""
+    call("dsvgp_phi_outer_" + suffix(X.dtype), X, _ld(X), u, v, P, _ld(P), n)
+
+
 def phi_lower(Y, P, n):
     call("dsvgp_phi_lower_f64", Y, _ld(Y), P, _ld(P), n)
     return P

@@ -256,6 +256,10 @@ int dsvgp_sym_phi_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int 
 /* Cholesky backward dK = sym(L^-T Phi(L^T dL) L^-1): Phi = tril with halved diagonal; A <- (A + A^T)/2 in place */
 int dsvgp_phi_lower_f64(const double* Y, int64_t ldy, double* P, int64_t ldp, int n, dsvgp_stream_t s);
 int dsvgp_symmetrize_f64(double* A, int64_t ld, int n, dsvgp_stream_t s);
+/* LOWER TRIANGLE of P = Phi(X + u v^T) in fp64 from X in the model dtype (the upper triangle of P is not written: its consumers
+ * take P with a lower-triangle flag): dsvgp_add_outer + dsvgp_cast2d + dsvgp_phi_lower of the Cholesky-backward tail in one pass. */
+int dsvgp_phi_outer_f32(const float* X, int64_t ldx, const float* u, const float* v, double* P, int64_t ldp, int n, dsvgp_stream_t s);
+int dsvgp_phi_outer_f64(const double* X, int64_t ldx, const double* u, const double* v, double* P, int64_t ldp, int n, dsvgp_stream_t s);
 
 /* predictive mean / diagonal variance (DirectionalGradVariationalStrategy.py:188,:192-205):
  *   pm[s][j] = sum_{i in slab s} A_ij m_i ;  pv[s][j] = sum A_ij C_ij  (C given)  or, with B' = B - A given in

@@ -616,3 +616,20 @@ def test_tc_operand_scales_and_splits(ops):
     wh, wl = mk2(), mk2()
     ops.split_half(W, sc[0:1], wh, wl, mode=1)
     assert rel((wh.double() + wl.double()) / float(s[0]), W.tril()) < 2.0 ** -21
+
+
+@pytest.mark.parametrize("dtype", [F32, F64])
+@pytest.mark.parametrize("n,pad", [(1, 0), (7, 1), (96, 0), (385, 3), (1024, 0)])
+def test_phi_outer_matches_the_three_pass_form(ops, dtype, n, pad):
+    """lower triangle of Phi(X + u v^T) in fp64 (one pass) = add_outer -> cast -> phi_lower; the upper triangle is not touched"""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    X = torch.randn(n, n + pad, device="cuda", dtype=dtype, generator=g)[:, :n]
+    u, v = (torch.randn(n, device="cuda", dtype=dtype, generator=g) for _ in range(2))
+    P = torch.full((n, n + pad), float("nan"), dtype=F64, device="cuda")[:, :n]
+    ops.phi_outer(X, u, v, P, n)
+    ref = (X + torch.outer(u, v)).double().tril()
+    ref.diagonal().mul_(0.5)
+    assert bool(torch.isnan(P.triu(1)[torch.ones(n, n, dtype=torch.bool, device="cuda").triu(2)]).all()) or n < 3
+    low = torch.ones(n, n, dtype=torch.bool, device="cuda").tril()
+    t = 1e-14 if dtype == F64 else 1e-6
+    assert float((P[low] - ref[low]).abs().max()) <= t * max(1.0, float(ref.abs().max()))
