@@ -93,6 +93,7 @@ int dsvgp_set_chol_lookahead(int on) { set_chol_lookahead(on); return get_chol_l
 int dsvgp_set_chol_mid_link(int k) { set_chol_mid_link(k); return get_chol_mid_link(); }
 int dsvgp_chol_wait_mid(dsvgp_stream_t s) { return chol_wait_mid(reinterpret_cast<cudaStream_t>(s)); }
 int dsvgp_set_chol_inv_streams(int n) { set_chol_inv_streams(n); return get_chol_inv_streams(); }
+int dsvgp_set_chol_graph(int on) { set_chol_graph(on); return get_chol_graph(); }
 int dsvgp_set_chol_priority(int on) { set_chol_priority(on); return get_chol_priority(); }
 
 int dsvgp_gemm_f32(int ta, int tb, int M, int N, int K, double alpha, const float* A, int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc, int a_tri, int b_tri, int c_tri, int batch, int64_t sA, int64_t sB, int64_t sC, const float* D, int64_t ldd, float* C2, int64_t ldc2, const float* D2, int64_t ldd2, dsvgp_stream_t s) {

@@ -11,6 +11,7 @@
 // inside one CTA in shared memory.  Status goes to a device int (0 ok, i+1 = first non-positive pivot), never to
 // the host: the caller decides when to look (no hidden synchronisation).
 #include <algorithm>
+#include <vector>
 
 #include "chol.cuh"
 #include "common.cuh"
@@ -919,15 +920,15 @@ int get_chol_lookahead() { return g_chol_lookahead; }
 static int g_chol_mid_link = 20;  // chol_wait_mid(): the diagonal block whose completion releases work the caller deferred (see there); < 0: none
 void set_chol_mid_link(int k) { g_chol_mid_link = k; }
 int get_chol_mid_link() { return g_chol_mid_link; }
-static int g_chol_inv_streams = 1; // eager inverse: 2 = T = L21 W11 products on a second stream (measured equal, eager and graph-replayed: off)
-void set_chol_inv_streams(int n) { g_chol_inv_streams = n >= 2 ? 2 : 1; }
+static int g_chol_inv_streams = 3; // eager inverse: 3 = one stream per level of the recursive doubling (default), 2 = T products on a second stream, 1 = one stream
+void set_chol_inv_streams(int n) { g_chol_inv_streams = n >= 3 ? 3 : (n == 2 ? 2 : 1); }
 int get_chol_inv_streams() { return g_chol_inv_streams; }
 static int g_chol_priority = 0;   // 1: the three chains of the factorisation on the library's high-priority streams; 0: diagonal chain on the caller's
                                   // stream (measured: no difference on any workload -- off)
 void set_chol_priority(int on) { g_chol_priority = on ? 1 : 0; }
 int get_chol_priority() { return g_chol_priority; }
 
-struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, inv2 = nullptr, bulk = nullptr; cudaEvent_t ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_T[8], ev_inv, ev_inv2, ev_pre, ev_entry, ev_done, ev_mid; bool ready = false, mid_valid = false; };
+struct SideCtx { cudaStream_t diag = nullptr, side = nullptr, inv = nullptr, inv2 = nullptr, bulk = nullptr, lvl[8] = {}; cudaEvent_t ev_lvl[8], ev_main[64], ev_side[64], ev_panel[64], ev_bulk[64], ev_T[8], ev_inv, ev_inv2, ev_pre, ev_entry, ev_done, ev_mid; bool ready = false, mid_valid = false; };
 static SideCtx g_side_ctxs[16];                         // one set of side streams + event pool per device
 
 // The first links of the chain are throughput-bound (their rank-nb0 trailing updates fill the GPU: potrf(k+2) waits for update(k)),
@@ -942,7 +943,9 @@ int chol_wait_mid(cudaStream_t s) {
   return DSVGP_OK;
 }
 
-int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
+static thread_local bool tl_own_capture = false;       // chol_enqueue runs inside the capture of the factorisation's own graph
+
+static int chol_enqueue(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
                         int nlev, int* info, cudaStream_t st) {
   if (Mp <= 0) return DSVGP_OK;
   if (!Awork || !L || !W || !info || nb0 <= 0 || nb0 > 112 || (nb0 << nlev) != Mp) return DSVGP_ERR_ARG;
@@ -1013,6 +1016,10 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     cudaEventCreateWithFlags(&sc.ev_inv2, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sc.ev_pre, cudaEventDisableTiming);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&sc.ev_T[i], cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) {
+      if (cudaStreamCreateWithPriority(&sc.lvl[i], cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return DSVGP_ERR_LAUNCH;
+      cudaEventCreateWithFlags(&sc.ev_lvl[i], cudaEventDisableTiming);
+    }
     sc.ready = true;
   }
   cudaStream_t side = sc.side, inv = sc.inv;
@@ -1032,6 +1039,8 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   const bool eager_inv = two_chains && nlev >= 1 && g_chol_variant >= 2;
   int last_side = -1, last_bulk = -1;
   unsigned t_pending = 0;                               // levels whose T product (second inverse stream) no W21 has waited for yet
+  const bool per_level = g_chol_inv_streams >= 3 && nlev <= 8;
+  unsigned lvl_used = 0;                                // level streams that carry work of this factorisation (joined at the end)
   for (int k = 0; k < nblk; ++k) {
     const int64_t o = (int64_t)k * nb0;
     // (more than 64 blocks: more steps than pooled events -- everything goes on the caller's stream, in order)
@@ -1056,7 +1065,9 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     const int m = Mp - (int)o - nb0;
     if (two_chains) cudaEventRecord(sc.ev_main[k], st);
     if (two_chains && nblk >= 8 && k == std::min(g_chol_mid_link, nblk - 1)) {
-      cudaEventRecord(sc.ev_mid, st);
+      // (inside the factorisation's own graph the record is an EXTERNAL event node: streams outside the graph may wait for it)
+      if (tl_own_capture) cudaEventRecordWithFlags(sc.ev_mid, st, cudaEventRecordExternal);
+      else cudaEventRecord(sc.ev_mid, st);
       sc.mid_valid = true;
     }
     if (m > 0) {
@@ -1112,7 +1123,36 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
         last_side = k;
       }
     }
-    if (eager_inv) {
+    if (eager_inv && per_level) {
+      // One stream PER LEVEL of the recursive doubling.  On one stream (or two: T products / W21 products) the long products of
+      // the upper levels (T and W21 of the 768- and 1536-wide pairs: 72 / 177 us) sit in front of the short ones of the blocks that
+      // follow, every such delay is inherited by everything after it, and by the last diagonal block the inverse is ten blocks
+      // behind: ~20 kernels (0.5 - 0.66 ms) ran after the factor was complete where the true dependency chain is five
+      // (W21 of 96, 192, .., 1536: 0.32 ms).  Per level, T(lev) and W21(lev) of consecutive pairs alternate on lvl[lev]; across
+      // levels the order is carried by events: the first product of block k waits for the diagonal block, every product of level
+      // lev for the W21 of level lev - 1 issued just before it (which completes the group it reads).
+      for (int lev = 0; lev < nlev && ((k + 1) & ((1 << lev) - 1)) == 0; ++lev) {
+        const int idx = (k + 1) >> lev;
+        const int b = nb0 << lev;
+        cudaStream_t ls = sc.lvl[lev];
+        if (lev == 0) cudaStreamWaitEvent(ls, sc.ev_main[k], 0);        // block k is factorised and inverted
+        else cudaStreamWaitEvent(ls, sc.ev_lvl[lev - 1], 0);            // the group below is complete (it waited for block k in turn)
+        lvl_used |= 1u << lev;
+        if (idx & 1) {                                   // TOP half ended: T = L21 W11 (needs the panel of column k)
+          const int64_t s0 = (int64_t)(idx - 1) * b;
+          cudaStreamWaitEvent(ls, sc.ev_panel[k], 0);
+          int rc = gemm<double>(false, false, b, b, b, 1.0, L + (s0 + b) * ldl + s0, ldl, W + s0 * ldw + s0, ldw, 0.0,
+                                W + s0 * ldw + (s0 + b), ldw, TRI_NONE, TRI_LOWER, 0, 1, 0, 0, 0, ls);
+          if (rc) return rc;
+          break;
+        }
+        const int64_t s0 = (int64_t)(idx - 2) * b;       // BOTTOM half ended: W21 = -W22 T (T: earlier on this same stream)
+        int rc = gemm<double>(false, false, b, b, b, -1.0, W + (s0 + b) * ldw + (s0 + b), ldw, W + s0 * ldw + (s0 + b), ldw, 0.0,
+                              W + (s0 + b) * ldw + s0, ldw, TRI_LOWER, TRI_NONE, 0, 1, 0, 0, 0, ls);
+        if (rc) return rc;
+        cudaEventRecord(sc.ev_lvl[lev], ls);
+      }
+    } else if (eager_inv) {
       bool waited = false;
       for (int lev = 0; lev < nlev && ((k + 1) & ((1 << lev) - 1)) == 0; ++lev) {
         const int idx = (k + 1) >> lev;                  // groups of 2^lev blocks finished so far
@@ -1122,10 +1162,8 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
           waited = true;
         }
         if (idx & 1) {                                   // a TOP half just ended: T = L21 W11 (needs the panel of column k)
-          // (knob) T products on a stream of their own: nothing after them on `inv` needs them before the pair's bottom half ends
-          // (2^lev blocks later).  The ~20-kernel backlog seen after the last diagonal block in a profiler trace of the
-          // factorisation ALONE turned out to be the host falling behind (~650 launch / event calls per factorisation against
-          // 34 us per block), not stream order: steps measure the same with one or two streams, eager or graph-replayed.
+          // (mode 2) T products on a stream of their own: measured equal to one stream -- the long T products still sit in front
+          // of the short ones; the per-level layout above is what removes the backlog.
           const int64_t s0 = (int64_t)(idx - 1) * b;
           cudaStream_t ts = (g_chol_inv_streams >= 2 && lev < 8) ? sc.inv2 : inv;
           if (ts != inv) {
@@ -1160,6 +1198,14 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
   }
   if (two_chains && last_side >= 0) cudaStreamWaitEvent(st, sc.ev_side[last_side], 0);
   if (last_bulk >= 0) cudaStreamWaitEvent(st, sc.ev_bulk[last_bulk], 0);
+  if (eager_inv && per_level) {
+    for (int lev = 0; lev < nlev; ++lev)
+      if (lvl_used & (1u << lev)) {
+        cudaEventRecord(sc.ev_lvl[lev], sc.lvl[lev]);
+        cudaStreamWaitEvent(st, sc.ev_lvl[lev], 0);
+      }
+    return DSVGP_OK;
+  }
   if (eager_inv) {
     cudaEventRecord(sc.ev_inv, inv);
     cudaStreamWaitEvent(st, sc.ev_inv, 0);
@@ -1179,6 +1225,92 @@ int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, doub
     rc = gemm<double>(false, false, b, b, b, -1.0, W + (int64_t)b * ldw + b, ldw, Awork + (int64_t)b * lda, lda, 0.0,
                       W + (int64_t)b * ldw, ldw, TRI_LOWER, TRI_NONE, 0, npairs, sW, sT, sW, st);
     if (rc) return rc;
+  }
+  return DSVGP_OK;
+}
+
+// ---- the factorisation as a cached CUDA graph (knob, off by default) --------------------------------------------------------
+// One factorisation is ~230 kernel launches and ~400 event calls.  The buffers of a model's factor are allocated once, so the whole
+// fork/join structure can be captured ONCE per (buffers, sizes, scheduling knobs) and replayed with a single cudaGraphLaunch.
+// Measured: the factorisation alone takes the same 1.93 ms replayed or launched (the GPU, not the host, sets its pace), so this stays
+// a knob for hosts slower than this box's.  Not used while the caller's
+// stream is itself being captured (graphs.GraphedStep): there the launches simply become part of the caller's graph.
+static int g_chol_graph = 0;
+void set_chol_graph(int on) { g_chol_graph = on ? 1 : 0; }
+int get_chol_graph() { return g_chol_graph; }
+
+struct CholGraphKey {
+  double *Awork, *L, *W;
+  int64_t lda, ldl, ldw;
+  int Mp, nb0, nlev;
+  int* info;
+  int knobs[8];
+  bool operator==(const CholGraphKey& o) const {
+    if (Awork != o.Awork || L != o.L || W != o.W || lda != o.lda || ldl != o.ldl || ldw != o.ldw || Mp != o.Mp || nb0 != o.nb0 ||
+        nlev != o.nlev || info != o.info)
+      return false;
+    for (int i = 0; i < 8; ++i)
+      if (knobs[i] != o.knobs[i]) return false;
+    return true;
+  }
+};
+struct CholGraphEntry { CholGraphKey key; cudaGraphExec_t exec; bool mid_valid; unsigned long long used; };
+static std::vector<CholGraphEntry> g_chol_graphs[16];
+static unsigned long long g_chol_graph_clock = 0;
+
+int chol_factor_inverse(double* Awork, int64_t lda, double* L, int64_t ldl, double* W, int64_t ldw, int Mp, int nb0,
+                        int nlev, int* info, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (!g_chol_graph || Mp <= 0 || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return chol_enqueue(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, st);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<CholGraphEntry>& cache = g_chol_graphs[dev & 15];
+  CholGraphKey key{Awork, L, W, lda, ldl, ldw, Mp, nb0, nlev, info,
+                   {g_chol_variant, g_chol_lookahead, g_chol_priority, g_chol_inv_streams, g_chol_mid_link, get_rank_update(),
+                    get_gemm64_async(), 0}};
+  CholGraphEntry* hit = nullptr;
+  for (auto& e : cache)
+    if (e.key == key) hit = &e;
+  if (!hit) {
+    // make sure everything with per-process one-time setup (streams, events, function attributes) has run eagerly once
+    static bool warmed[16] = {};
+    if (!warmed[dev & 15]) {
+      warmed[dev & 15] = true;
+      return chol_enqueue(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, st);
+    }
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return chol_enqueue(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, st);
+    }
+    tl_own_capture = true;
+    const int rc = chol_enqueue(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, st);
+    tl_own_capture = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != DSVGP_OK || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc != DSVGP_OK) return rc;
+      return chol_enqueue(Awork, lda, L, ldl, W, ldw, Mp, nb0, nlev, info, st);     // (nothing was enqueued by the failed capture)
+    }
+    cudaGraphDestroy(graph);
+    if (cache.size() >= 8) {                              // evict the least recently used graph
+      size_t lru = 0;
+      for (size_t i = 1; i < cache.size(); ++i)
+        if (cache[i].used < cache[lru].used) lru = i;
+      cudaGraphExecDestroy(cache[lru].exec);
+      cache.erase(cache.begin() + lru);
+    }
+    cache.push_back(CholGraphEntry{key, exec, g_side_ctxs[dev & 15].mid_valid, 0});
+    hit = &cache.back();
+  }
+  hit->used = ++g_chol_graph_clock;
+  g_side_ctxs[dev & 15].mid_valid = hit->mid_valid;
+  if (cudaGraphLaunch(hit->exec, st) != cudaSuccess) {
+    cudaGetLastError();
+    return DSVGP_ERR_LAUNCH;
   }
   return DSVGP_OK;
 }

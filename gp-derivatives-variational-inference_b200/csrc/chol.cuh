@@ -26,6 +26,8 @@ int get_chol_mid_link();
 int chol_wait_mid(cudaStream_t s);
 void set_chol_inv_streams(int n);
 int get_chol_inv_streams();
+void set_chol_graph(int on);
+int get_chol_graph();
 void set_chol_priority(int on);
 int get_chol_priority();
 void set_potrf_debug(long long* p);   // profiling aid: device buffer of 64 clock64() stamps (nullptr = off)

@@ -152,8 +152,13 @@ def chol_wait_mid():
 
 
 def set_chol_inv_streams(n):
-    """Streams of the eager inverse (1: one stream, default; 2: T products beside the W21 chain -- measured equal)."""
+    """Streams of the eager inverse (3: one per level of the recursive doubling, default; 2: T products on one extra stream; 1: one)."""
     return call_raw("dsvgp_set_chol_inv_streams", int(n))
+
+
+def set_chol_graph(on):
+    """The factorisation as a cached CUDA graph of its own (one cudaGraphLaunch instead of ~650 host calls); default off."""
+    return call_raw("dsvgp_set_chol_graph", int(bool(on)))
 
 
 def set_chol_priority(on):

@@ -125,9 +125,16 @@ int dsvgp_set_chol_priority(int on);
  * last on the current device; a no-op when that factorisation had fewer than 8 blocks.  (Measured at 32 blocks: release points 14 .. 31 equal within noise, 6 .. 10 worse.)  Capturable (an event edge inside the graph). */
 int dsvgp_set_chol_mid_link(int k);
 int dsvgp_chol_wait_mid(dsvgp_stream_t s);
-/* Streams of the eager inverse: 1 (default) = one stream; 2 = the T = L21 W11 products (issued when a pair's top half is complete,
- * needed only when its bottom half is) run on a stream of their own beside the W21 = -W22 T chain (measured equal on every
- * workload, eager and graph-replayed; results bit-identical).  Returns the value in force. */
+/* 1: dsvgp_chol_f64 captures its ~230 launches / ~400 event calls ONCE per (buffers, sizes, scheduling knobs) into a CUDA graph of
+ * its own and replays it with one cudaGraphLaunch (a cache of 8 per device); the mid-chain event of dsvgp_chol_wait_mid becomes an
+ * external event node.  Ignored while the caller's stream is being captured.  0 (default: measured equal on this host -- the GPU
+ * sets the factorisation's pace) = plain launches.  Results are bit-identical.  Returns the value in force. */
+int dsvgp_set_chol_graph(int on);
+/* Streams of the eager inverse W = L^-1 (for every pair of every level of the recursive doubling, T = L21 W11 is issued when the
+ * pair's top half is complete and W21 = -W22 T when its bottom half is): 3 (default) = one stream per level, ordered across levels
+ * by events -- on fewer streams the 72 / 177 us products of the upper levels sit in front of the short ones of the following blocks
+ * and the inverse finishes ~0.3 ms after the factor instead of one five-product dependency chain after it (factorisation alone
+ * 2.23 -> 1.93 ms at M' = 3072); 2 = T products on one extra stream; 1 = one stream.  Results bit-identical.  Returns the value in force. */
 int dsvgp_set_chol_inv_streams(int n);
 /* 1: while the trailing matrix is large, the update of step k is split into the first two block columns of the
  * trapezoid (all that the diagonal block k+2 and the panel k+1 read; side stream) and the rest (a low-priority stream of its

@@ -275,7 +275,11 @@ def test_cholesky_and_inverse(ops, Mq):
     assert rel(W[:Mq, :Mq].tril().cpu() @ Lr, torch.eye(Mq, dtype=F64)) < 1e-10
 
 
-@pytest.mark.parametrize("knob", ["priority", "lookahead", "rank_update", "priority+lookahead+rank_update", "two_inverse_streams"])
+DEFAULT_INV_STREAMS = 3
+
+
+@pytest.mark.parametrize("knob", ["priority", "lookahead", "rank_update", "priority+lookahead+rank_update", "two_inverse_streams", "per_level_inverse_streams", "one_inverse_stream",
+                                  "own_graph"])
 def test_cholesky_scheduling_knobs_keep_the_result(ops, knob):
     """The experimental schedules of the factorisation (high-priority streams, lookahead-2 split of the trailing update, rank-K
     update kernel; all off by default) give the same factor and inverse."""
@@ -300,16 +304,19 @@ def test_cholesky_scheduling_knobs_keep_the_result(ops, knob):
             ops.set_chol_lookahead(1)
         if "rank_update" in knob:
             ops.set_rank_update(1)
-        if "two_inverse_streams" in knob:
-            ops.set_chol_inv_streams(2)
+        if "inverse_stream" in knob:
+            ops.set_chol_inv_streams({"two": 2, "per": 3, "one": 1}[knob[:3]])
+        if knob == "own_graph":
+            ops.set_chol_graph(1)
         L1, W1 = run()
-        if "two_inverse_streams" in knob:                 # same kernels in another stream layout: bit-identical, run after run
+        if "inverse_stream" in knob or knob == "own_graph":   # same kernels in another stream layout / replayed from the cached graph: bit-identical, run after run
             for _ in range(5):
                 L2, W2 = run()
                 assert torch.equal(L2, L0) and torch.equal(W2, W0)
             assert torch.equal(L1, L0) and torch.equal(W1, W0)
     finally:
-        ops.set_chol_priority(0), ops.set_chol_lookahead(0), ops.set_rank_update(0), ops.set_chol_inv_streams(1)
+        ops.set_chol_priority(0), ops.set_chol_lookahead(0), ops.set_rank_update(0), ops.set_chol_inv_streams(DEFAULT_INV_STREAMS)
+        ops.set_chol_graph(0)
     assert rel(L1, L0) < 1e-12 and rel(W1, W0) < 1e-10
     assert rel(W0 @ L0, torch.eye(Mp, dtype=F64)) < 1e-9
 
