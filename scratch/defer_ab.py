@@ -1,4 +1,6 @@
-"""A/B of engine.DEFER_SIDE_WORK (side-stream work released at the mid-chain diagonal block) on the training step."""
+"""A/B of engine.DEFER_SIDE_WORK (side-stream work released at the mid-chain diagonal block) on the training step: run(name, n, mids)
+times the step for each release point (None = no deferral).  As committed it loops over the lookahead / priority knobs at the
+default release point (the last comparison made with it: no gain from either with the 31 us diagonal block)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gp-derivatives-variational-inference_b200"))

@@ -1,4 +1,6 @@
-"""A/B of the eager inverse's stream layout (dsvgp_set_chol_inv_streams 1 / 2), eager and CUDA-graph replayed steps."""
+"""A/B of the rank-K fp64 kernel modes (dsvgp_set_rank_update 0 / 2 / 1) on whole steps, eager and CUDA-graph replayed.
+The same loop with ops.set_chol_inv_streams(1 / 2) in place of set_rank_update gave the one- / two-stream inverse comparison
+(equal); the per-level layout is timed by scratch/chol_graph_ab.py."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gp-derivatives-variational-inference_b200"))
